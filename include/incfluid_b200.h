@@ -85,8 +85,17 @@ typedef struct ifl_config {
      * and comm_id holds the 128-byte ncclUniqueId all ranks share. */
     int32_t rank;
     int32_t world_size;
+    int32_t flags;            /* ifl_flags, 0 = default */
     uint8_t comm_id[128];
 } ifl_config;
+
+/* ifl_config.flags */
+typedef enum ifl_flags {
+    /* Evaluate dotProduct (F3:532) in the reference's strictly sequential order instead of
+     * the fixed-shape parallel tree.  Slow (one thread per reduction); makes the whole PCG
+     * solve bit-identical to the Java loops.  Meant for parity tests on small grids. */
+    IFL_FLAG_SEQUENTIAL_REDUCTIONS = 1
+} ifl_flags;
 
 /* Rigid body table entry = the fields of A_SolidBody (solidBodies/A_SolidBody.java:73-87).
  * cos_theta / sin_theta are cos(_theta), sin(_theta) evaluated ONCE by the

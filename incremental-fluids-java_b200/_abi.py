@@ -17,6 +17,9 @@ F1_MATRIXLESS, F2_BETTER_ADVECTION, F3_CONJUGATE_GRADIENTS, F4_SOLID_BOUNDARIES,
 
 BODY_BOX, BODY_SPHERE = 0, 1
 
+# ifl_flags
+FLAG_SEQUENTIAL_REDUCTIONS = 1
+
 
 class Config(C.Structure):
     _fields_ = [
@@ -28,7 +31,7 @@ class Config(C.Structure):
         ("particles_avg_per_cell", C.c_int32), ("particles_max_per_cell", C.c_int32),
         ("particles_min_per_cell", C.c_int32),
         ("rng_seed", C.c_uint64), ("device", C.c_int32),
-        ("rank", C.c_int32), ("world_size", C.c_int32),
+        ("rank", C.c_int32), ("world_size", C.c_int32), ("flags", C.c_int32),
         ("comm_id", C.c_uint8 * 128),
     ]
 
@@ -142,6 +145,7 @@ def default_config(variant, w, h, **overrides):
     cfg.device = 0
     cfg.rank = 0
     cfg.world_size = 1
+    cfg.flags = 0
     for k, v in overrides.items():
         if not hasattr(cfg, k):
             raise AttributeError(k)

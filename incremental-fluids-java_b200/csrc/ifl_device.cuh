@@ -1,0 +1,122 @@
+/*
+ * ifl_device.cuh -- device-side helpers shared by every kernel of libincfluid_b200.
+ *
+ * Arithmetic contract: the reference is Java double arithmetic without
+ * fused multiply-add, so every translation unit is compiled with -fmad=false and the
+ * expressions below keep the reference's left-to-right evaluation order.  IEEE double
+ * division and sqrt are correctly rounded on sm_100a by default.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define IFL_WARP 32
+#define IFL_STRIP 32 /* rows per strip of the skewed layout == warp size */
+
+/* cell types of FluidQuantity._cell (F4:60-63 enum CellType; F8:1795 adds EMPTY) */
+#define IFL_CELL_FLUID 0
+#define IFL_CELL_SOLID 1
+#define IFL_CELL_EMPTY 2
+
+namespace ifl {
+
+/* ---- Java semantics ---------------------------------------------------------- */
+/* Math.max / Math.min on doubles.  CUDA fmax/fmin differ from Java only for NaN
+ * operands (Java propagates, CUDA suppresses); a NaN residual terminates the
+ * reference (F3:616), and the solver reports it through IFL_ERR_NAN. */
+__device__ __forceinline__ double jmax(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ double jmin(double a, double b) { return fmin(a, b); }
+/* (float) x widened back to double: round-to-nearest-even */
+__device__ __forceinline__ double jfloat(double x) { return (double)__double2float_rn(x); }
+/* Math.abs((float) x) as double */
+__device__ __forceinline__ double jabsf(double x) { return (double)fabsf(__double2float_rn(x)); }
+/* (int) x for an already clamped, non-negative finite x */
+__device__ __forceinline__ int jint(double x) { return __double2int_rz(x); }
+
+/* math/Interpolation.java:77-86 */
+__device__ __forceinline__ double lerp(double a, double b, double x) { return (1.0 - x) * a + x * b; }
+
+/* Catmull-Rom weights of math/Interpolation.java:145-149.  The four polynomials do not
+ * depend on the samples, so they are evaluated once per coordinate and reused for every
+ * row; each is the literal expression of the reference, term by term, left to right. */
+struct CerpW { double a, b, c, d; };
+__device__ __forceinline__ CerpW cerp_weights(double x) {
+    double xsq = x * x;
+    double xcu = xsq * x;
+    CerpW w;
+    w.a = 0.0 - 0.5 * x + 1.0 * xsq - 0.5 * xcu;
+    w.b = 1.0 + 0.0 * x - 2.5 * xsq + 1.5 * xcu;
+    w.c = 0.0 + 0.5 * x + 2.0 * xsq - 1.5 * xcu;
+    w.d = 0.0 + 0.0 * x - 0.5 * xsq + 0.5 * xcu;
+    return w;
+}
+/* math/Interpolation.java:135-152 */
+__device__ __forceinline__ double cerp(double a, double b, double c, double d, const CerpW& w) {
+    double minV = jmin(a, jmin(b, jmin(c, d)));
+    double maxV = jmax(a, jmax(b, jmax(c, d)));
+    double t = a * w.a + b * w.b + c * w.c + d * w.d;
+    return jmin(jmax(t, minV), maxV);
+}
+
+/* ---- strip-skewed layout ------------------------------------------------------
+ * Every N-vector of the pressure solve (r p z s aDiag aPlusX aPlusY precon) lives in a
+ * layout made for the lexicographic recurrences: rows are grouped in strips of 32; in
+ * strip k the cell (x, y = 32k + l) is stored at  k*SS + (x + l)*32 + l.  One "t-row"
+ * t = x + l is the anti-diagonal a warp (lane l = row l) processes in one step, and it
+ * is 256 contiguous bytes.  tl = number of t-rows per strip (>= w + 31). */
+struct SkewGeom {
+    int w, h;
+    int nstrips;
+    int tl;             /* t-rows per strip */
+    long long ss;       /* strip stride in elements = tl * 32 */
+    long long total;    /* nstrips * ss */
+};
+__device__ __host__ __forceinline__ long long skew_index(const SkewGeom& g, int x, int y) {
+    int l = y & 31;
+    return (long long)(y >> 5) * g.ss + (long long)(x + l) * 32 + l;
+}
+
+/* non-negative float bit patterns order like unsigned ints; NaN sorts above +inf */
+__device__ __forceinline__ unsigned int absf_bits(double x) {
+    return __float_as_uint(fabsf(__double2float_rn(x)));
+}
+
+/* deterministic block sum for blockDim.x == 256: fixed shuffle tree, then warp totals
+ * added in warp order by thread 0.  Result valid in thread 0. */
+__device__ __forceinline__ double block_sum_256(double v, double* smem8) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) smem8[wid] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0) {
+        s = smem8[0];
+#pragma unroll
+        for (int i = 1; i < 8; i++) s += smem8[i];
+    }
+    __syncthreads();
+    return s;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+/* flag-in-data sentinel for the strip-to-strip boundary rows: a NaN payload no
+ * arithmetic produces (computed NaNs are the canonical 0x7ff8000000000000 or carry an
+ * input payload; no input ever holds this pattern). */
+#define IFL_SENTINEL_BITS 0xFFF8B200DEAD0001ull
+__device__ __forceinline__ bool is_sentinel(double v) {
+    return (unsigned long long)__double_as_longlong(v) == IFL_SENTINEL_BITS;
+}
+__device__ __forceinline__ double sentinel() { return __longlong_as_double((long long)IFL_SENTINEL_BITS); }
+
+__device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ double ld_volatile(const double* p) {
+    return *reinterpret_cast<const volatile double*>(p);
+}
+
+} // namespace ifl

@@ -1,0 +1,82 @@
+/*
+ * ifl_internal.h -- host-side declarations shared by the translation units of
+ * libincfluid_b200.so.  Nothing here crosses the C ABI (include/incfluid_b200.h).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/incfluid_b200.h"
+#include "ifl_device.cuh"
+
+namespace ifl {
+
+/* Geometry of one FluidQuantity (F1:105-140): size, sample offset, cell size. */
+struct QGeom {
+    int w, h;
+    double ox, oy;
+};
+
+/* Device scalars of one pressure solve.  Every solver kernel reads its coefficients
+ * from here, so a whole solve is enqueued without returning to the host. */
+struct SolveScalars {
+    double sigma;        /* z.r */
+    double alpha;        /* sigma / (z.s) */
+    double neg_alpha;
+    double beta;         /* sigmaNew / sigma */
+    double zs;
+    double max_error;    /* PCG: infinityNorm(r) (F3:579)  GS: maxDelta (F1:414) */
+    unsigned long long max_bits;   /* running max, bit pattern of a non-negative float/double */
+    int iterations;      /* iterations executed so far */
+    int done;            /* 1: converged (or NaN) -- remaining kernels of the solve return at once */
+    int nan;
+    int exceeded;
+    unsigned int ctr_a;  /* "last block" counters */
+    unsigned int ctr_b;
+    unsigned int ticket_f;  /* strip tickets of the forward / backward wavefront */
+    unsigned int ticket_b;
+    int pad;
+};
+
+struct SolveCtx {
+    SkewGeom g;
+    /* skewed N-vectors */
+    double *r, *p, *z, *s, *adiag, *aplusx, *aplusy, *precon;
+    /* strip boundary rows (flag-in-data), [nstrips][w] each; two sets for GS parity */
+    double *bnd_f, *bnd_b;
+    double *partials;     /* per-block partial sums */
+    int npartials;
+    double *stripdot;     /* per-strip partial of the dot fused into the backward sweep */
+    SolveScalars* sc;
+    double tolerance;
+    double mic_tau, mic_sigma;
+    int sequential;       /* reductions in the reference's serial order (bit-exact mode) */
+    cudaStream_t stream;
+    unsigned long long* launches;
+};
+
+/* ---- grid (row-major) kernels: ifl_grid_kernels.cu ---- */
+void launch_advect(cudaStream_t st, int variant, QGeom q, const double* src, double* dst,
+                   QGeom qu, const double* u, QGeom qv, const double* v, double timestep, double hx);
+void launch_add_inflow(cudaStream_t st, int variant, QGeom q, double* src, double hx,
+                       double x0, double y0, double x1, double y1, double value);
+void launch_build_rhs(cudaStream_t st, const SkewGeom& g, const double* u, const double* v, double* r, double hx);
+void launch_build_matrix_f3(cudaStream_t st, const SkewGeom& g, double* adiag, double* aplusx, double* aplusy, double scale);
+void launch_apply_pressure(cudaStream_t st, const SkewGeom& g, const double* p, double* u, double* v, double scale);
+void launch_skew_to_rows(cudaStream_t st, const SkewGeom& g, const double* skew, double* rows);
+void launch_rows_to_skew(cudaStream_t st, const SkewGeom& g, const double* rows, double* skew);
+void launch_max_velocity(cudaStream_t st, int w, int h, const double* u, const double* v, unsigned long long* out_bits);
+
+/* ---- solver kernels: ifl_solve_kernels.cu ---- */
+int  solve_partials_needed(const SkewGeom& g);
+void launch_build_precon(SolveCtx& c);
+void launch_apply_precon(SolveCtx& c, const double* src, double* dst, int with_dot_mode);
+void pcg_enqueue_init(SolveCtx& c);
+void pcg_enqueue_iterations(SolveCtx& c, int n);
+void pcg_enqueue_finish(SolveCtx& c, int limit);
+void launch_matvec(SolveCtx& c, const double* b, double* dst);
+void gs_enqueue_begin(SolveCtx& c);
+void gs_enqueue_iterations(SolveCtx& c, int first_iter, int n, double scale);
+void gs_enqueue_finish(SolveCtx& c, int limit);
+
+} // namespace ifl

@@ -1,0 +1,716 @@
+/*
+ * ifl_solve_kernels.cu -- the pressure solve on the strip-skewed layout (ifl_device.cuh):
+ *   - element-wise / stencil kernels of the MIC(0)-PCG loop with fused deterministic
+ *     reductions (matrixVectorProduct F3:544 + dotProduct F3:532, scaledAdd F3:570 +
+ *     infinityNorm F3:579);
+ *   - the three lexicographic recurrences as warp-per-strip anti-diagonal wavefronts:
+ *     buildPreconditioner F3:464, applyPreconditioner F3:495 (forward and backward
+ *     sweep) and the in-place Gauss-Seidel sweep of project() F1:380.
+ *
+ * Wavefront scheme.  A warp owns a strip of 32 rows (lane l = row l) and advances one
+ * anti-diagonal (one 256-byte t-row of the skewed layout) per step: lane l works on column
+ * x = t - l, so its left neighbour is its own previous result and its upper neighbour is
+ * lane l-1's previous result (one shuffle).  Any schedule that respects the left/up
+ * dependencies performs exactly the reference's per-cell operations, so results are
+ * bit-identical to the lexicographic loops.  Strip k+1 consumes the last row of strip k
+ * through a "flag-in-data" boundary row: it is pre-filled with a NaN sentinel and the
+ * consumer simply re-reads an element until it is no longer the sentinel -- no fences on
+ * the critical path.  Strips are handed out through an atomic ticket so that a waiting
+ * strip's producer is always resident (no reliance on block scheduling order).
+ *
+ * Compiled with -fmad=false.
+ */
+#include "ifl_internal.h"
+
+namespace ifl {
+
+static constexpr int EW_THREADS = 256;
+static constexpr int EW_TROWS = 64;    /* t-rows per element-wise block: 2048 elements, 8 per thread */
+static constexpr int WF_WARPS = 4;     /* strips (warps) per wavefront block */
+static constexpr int WF_U = 8;         /* register prefetch distance in steps */
+
+static dim3 ew_grid(const SkewGeom& g) { return dim3((g.tl + EW_TROWS - 1) / EW_TROWS, g.nstrips); }
+int solve_partials_needed(const SkewGeom& g) { dim3 d = ew_grid(g); return (int)(d.x * d.y); }
+static inline void count(SolveCtx& c, int n = 1) { if (c.launches) *c.launches += n; }
+
+/* iteration helper of the element-wise kernels: thread handles 8 elements, t-rows
+ * t0 + e*8 + warp, lane = l.  Visits in a fixed order (e ascending). */
+#define IFL_EW_LOOP_BEGIN(g)                                                            \
+    const int k_ = blockIdx.y;                                                          \
+    const long long base_ = (long long)k_ * (g).ss;                                     \
+    const int l_ = threadIdx.x & 31;                                                    \
+    const int y_ = k_ * 32 + l_;                                                        \
+    _Pragma("unroll") for (int e_ = 0; e_ < 8; e_++) {                                  \
+        const int t_ = blockIdx.x * EW_TROWS + e_ * 8 + (threadIdx.x >> 5);             \
+        const int x_ = t_ - l_;                                                         \
+        const long long i_ = base_ + (long long)t_ * 32 + l_;                           \
+        const bool ok_ = (t_ < (g).tl) && x_ >= 0 && x_ < (g).w && y_ < (g).h;
+#define IFL_EW_LOOP_END }
+
+enum { DOT_NONE = 0, DOT_ZS = 1, DOT_SIGMA_INIT = 2, DOT_SIGMA_NEW = 3 };
+
+__device__ __forceinline__ void apply_dot_result(SolveScalars* sc, int mode, double total) {
+    if (mode == DOT_ZS) {                       /* alpha = sigma / dotProduct(z, s)  F3:605 */
+        sc->zs = total;
+        double a = sc->sigma / total;
+        sc->alpha = a;
+        sc->neg_alpha = -a;
+    } else if (mode == DOT_SIGMA_INIT) {        /* sigma = dotProduct(z, r)  F3:602 */
+        sc->sigma = total;
+    } else if (mode == DOT_SIGMA_NEW) {         /* sigmaNew; beta = sigmaNew / sigma; sigma = sigmaNew  F3:625-627 */
+        sc->beta = total / sc->sigma;
+        sc->sigma = total;
+    }
+}
+
+/* "last block" reduction of per-block partials in a fixed order */
+__device__ __forceinline__ void finish_partials(double blocksum, double* partials, int nblocks,
+                                                SolveScalars* sc, int mode, double* smem8, bool* s_last) {
+    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) {
+        partials[bid] = blocksum;
+        __threadfence();
+        unsigned prev = atomicAdd(&sc->ctr_a, 1u);
+        *s_last = (prev == (unsigned)nblocks - 1u);
+    }
+    __syncthreads();
+    if (*s_last) {
+        __threadfence();
+        double v = 0.0;
+        for (int j = threadIdx.x; j < nblocks; j += EW_THREADS) v += ld_cg(partials + j);
+        double total = block_sum_256(v, smem8);
+        if (threadIdx.x == 0) {
+            apply_dot_result(sc, mode, total);
+            sc->ctr_a = 0;
+        }
+    }
+}
+
+/* z = A s fused with the partial sums of z.s   (matrixVectorProduct F3:544, dotProduct F3:532) */
+__global__ void __launch_bounds__(EW_THREADS)
+k_matvec_dot(SkewGeom g, const double* __restrict__ adiag, const double* __restrict__ ax,
+             const double* __restrict__ ay, const double* __restrict__ b, double* __restrict__ dst,
+             double* partials, SolveScalars* sc, int dot_mode, int check_done) {
+    if (check_done && sc->done) return;
+    __shared__ double smem8[8];
+    __shared__ bool s_last;
+    double acc = 0.0;
+    IFL_EW_LOOP_BEGIN(g)
+        if (ok_) {
+            double bc = b[i_];
+            double tv = adiag[i_] * bc;
+            if (x_ > 0) tv += ax[i_ - 32] * b[i_ - 32];
+            if (y_ > 0) {
+                long long j = (l_ > 0) ? (i_ - 33) : (base_ - g.ss + (long long)(t_ + 31) * 32 + 31);
+                tv += ay[j] * b[j];
+            }
+            if (x_ < g.w - 1) tv += ax[i_] * b[i_ + 32];
+            if (y_ < g.h - 1) {
+                long long j = (l_ < 31) ? (i_ + 33) : (base_ + g.ss + (long long)(t_ - 31) * 32);
+                tv += ay[i_] * b[j];
+            }
+            dst[i_] = tv;
+            acc += tv * bc;
+        }
+    IFL_EW_LOOP_END
+    if (dot_mode == DOT_NONE) return;
+    double bs = block_sum_256(acc, smem8);
+    finish_partials(bs, partials, gridDim.x * gridDim.y, sc, dot_mode, smem8, &s_last);
+}
+
+/* p += alpha s ; r -= alpha z ; maxError = infinityNorm(r)   (F3:606-608, scaledAdd F3:570,
+ * infinityNorm F3:579).  Also re-arms the boundary rows and tickets of the two sweeps
+ * that follow.  The last block decides convergence (F3:609-619). */
+__global__ void __launch_bounds__(EW_THREADS)
+k_update_pr(SkewGeom g, double* __restrict__ p, const double* __restrict__ s, double* __restrict__ r,
+            const double* __restrict__ z, double* __restrict__ bnd_f, double* __restrict__ bnd_b,
+            SolveScalars* sc, double tol) {
+    if (sc->done) return;
+    __shared__ unsigned s_max[8];
+    __shared__ bool s_last;
+    const double alpha = sc->alpha, nalpha = sc->neg_alpha;
+    unsigned m = 0;
+    IFL_EW_LOOP_BEGIN(g)
+        if (ok_) {
+            p[i_] = p[i_] + s[i_] * alpha;
+            double rv = r[i_] + z[i_] * nalpha;
+            r[i_] = rv;
+            unsigned bits = absf_bits(rv);
+            m = bits > m ? bits : m;
+        }
+        if (l_ == 0 && t_ < g.w) {
+            bnd_f[(long long)k_ * g.w + t_] = sentinel();
+            bnd_b[(long long)k_ * g.w + t_] = sentinel();
+        }
+    IFL_EW_LOOP_END
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned other = __shfl_down_sync(0xffffffffu, m, o);
+        m = other > m ? other : m;
+    }
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) m = s_max[i] > m ? s_max[i] : m;
+        atomicMax(&sc->max_bits, (unsigned long long)m);
+        __threadfence();
+        unsigned prev = atomicAdd(&sc->ctr_a, 1u);
+        s_last = (prev == gridDim.x * gridDim.y - 1u);
+        if (s_last) {
+            __threadfence();
+            unsigned long long mb = atomicMax(&sc->max_bits, 0ull);
+            double err = (double)__uint_as_float((unsigned)mb);
+            sc->max_error = err;
+            sc->iterations = sc->iterations + 1;
+            if (err < tol) sc->done = 1;
+            if (err != err) { sc->done = 1; sc->nan = 1; }
+            sc->max_bits = 0ull;
+            sc->ctr_a = 0;
+            sc->ctr_b = 0;
+            sc->ticket_f = 0;
+            sc->ticket_b = 0;
+        }
+    }
+}
+
+/* s = z + s * beta   (F3:626) */
+__global__ void __launch_bounds__(EW_THREADS)
+k_update_s(SkewGeom g, double* __restrict__ s, const double* __restrict__ z, SolveScalars* sc) {
+    if (sc->done) return;
+    const double beta = sc->beta;
+    IFL_EW_LOOP_BEGIN(g)
+        if (ok_) s[i_] = z[i_] + s[i_] * beta;
+    IFL_EW_LOOP_END
+}
+
+/* start of project(): s = z (arraycopy F3:596); maxError = infinityNorm(r) (F3:598) */
+__global__ void __launch_bounds__(EW_THREADS)
+k_init_s(SkewGeom g, double* __restrict__ s, const double* __restrict__ z, const double* __restrict__ r,
+         SolveScalars* sc, double tol) {
+    __shared__ unsigned s_max[8];
+    unsigned m = 0;
+    IFL_EW_LOOP_BEGIN(g)
+        if (ok_) {
+            s[i_] = z[i_];
+            unsigned bits = absf_bits(r[i_]);
+            m = bits > m ? bits : m;
+        }
+    IFL_EW_LOOP_END
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned other = __shfl_down_sync(0xffffffffu, m, o);
+        m = other > m ? other : m;
+    }
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) m = s_max[i] > m ? s_max[i] : m;
+        atomicMax(&sc->max_bits, (unsigned long long)m);
+        __threadfence();
+        unsigned prev = atomicAdd(&sc->ctr_a, 1u);
+        if (prev == gridDim.x * gridDim.y - 1u) {
+            __threadfence();
+            unsigned long long mb = atomicMax(&sc->max_bits, 0ull);
+            double err = (double)__uint_as_float((unsigned)mb);
+            sc->max_error = err;
+            sc->iterations = 0;
+            if (err < tol) sc->done = 1;
+            if (err != err) { sc->done = 1; sc->nan = 1; }
+            sc->max_bits = 0ull;
+            sc->ctr_a = 0;
+        }
+    }
+}
+
+/* (re)arm scalars, tickets and both boundary-row sets before a solve */
+__global__ void k_solve_reset(SkewGeom g, double* bnd_f, double* bnd_b, SolveScalars* sc) {
+    long long n = (long long)g.nstrips * g.w;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        bnd_f[i] = sentinel();
+        bnd_b[i] = sentinel();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->sigma = 0.0; sc->alpha = 0.0; sc->neg_alpha = 0.0; sc->beta = 0.0; sc->zs = 0.0;
+        sc->max_error = 0.0; sc->max_bits = 0ull;
+        sc->iterations = 0; sc->done = 0; sc->nan = 0; sc->exceeded = 0;
+        sc->ctr_a = 0; sc->ctr_b = 0; sc->ticket_f = 0; sc->ticket_b = 0;
+    }
+}
+
+/* re-arm only the boundary rows/tickets (between two stand-alone sweeps) */
+__global__ void k_sweep_rearm(SkewGeom g, double* bnd_f, double* bnd_b, SolveScalars* sc) {
+    long long n = (long long)g.nstrips * g.w;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        bnd_f[i] = sentinel();
+        bnd_b[i] = sentinel();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->ticket_f = 0; sc->ticket_b = 0; sc->ctr_b = 0; }
+}
+
+__global__ void k_solve_finish(SolveScalars* sc, int limit) {
+    if (!sc->done && sc->iterations >= limit) sc->exceeded = 1;
+}
+
+/* Reductions in the reference's serial order (bit-exact mode, small grids / tests):
+ * one thread walks the cells lexicographically.  dotProduct F3:532. */
+__global__ void k_dot_sequential(SkewGeom g, const double* __restrict__ a, const double* __restrict__ b,
+                                 SolveScalars* sc, int mode, int check_done) {
+    if (check_done && sc->done) return;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double result = 0.0;
+    for (int y = 0; y < g.h; y++) {
+        long long i = skew_index(g, 0, y);
+        for (int x = 0; x < g.w; x++, i += 32) result += a[i] * b[i];
+    }
+    apply_dot_result(sc, mode, result);
+}
+
+/* ---------------------------------------------------------------------------------
+ * Wavefront machinery
+ * ------------------------------------------------------------------------------- */
+
+/* Claims the next strip slot for every warp of the block.  Returns the slot or -1. */
+__device__ __forceinline__ int claim_slot(unsigned int* ticket, int nstrips) {
+    __shared__ unsigned s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    int slot = (int)s_ticket * WF_WARPS + (threadIdx.x >> 5);
+    return slot < nstrips ? slot : -1;
+}
+
+/* Flag-in-data feed of the neighbouring strip's edge row.  Lane j (< U) owns the value the
+ * edge lane needs at step j of the current block; `get(j)` spins (warp-uniformly) until
+ * the producer has replaced the sentinel. */
+template <int U>
+struct EdgeFeed {
+    const double* row;   /* neighbour strip's boundary row or nullptr */
+    int w;
+    double cur, nxt;
+    const double* acur;
+    const double* anxt;
+    __device__ __forceinline__ void init(const double* r, int w_) {
+        row = r; w = w_; cur = 0.0; nxt = 0.0; acur = nullptr; anxt = nullptr;
+    }
+    /* start fetching the values of the block whose step j needs column xin(j) */
+    __device__ __forceinline__ void prefetch(int xin_for_my_lane, int lane) {
+        anxt = nullptr; nxt = 0.0;
+        if (row != nullptr && lane < U && xin_for_my_lane >= 0 && xin_for_my_lane < w) {
+            anxt = row + xin_for_my_lane;
+            nxt = ld_volatile(anxt);
+        }
+    }
+    __device__ __forceinline__ void advance() { cur = nxt; acur = anxt; }
+    __device__ __forceinline__ double get(int j, int lane) {
+        double v = __shfl_sync(0xffffffffu, cur, j);
+        while (is_sentinel(v)) {
+            if (lane == j) cur = ld_volatile(acur);
+            v = __shfl_sync(0xffffffffu, cur, j);
+        }
+        return v;
+    }
+};
+
+/* applyPreconditioner F3:495: DIR=+1 forward substitution (first loop nest), DIR=-1
+ * backward substitution (second loop nest).  WITH_DOT (backward only) accumulates
+ * dotProduct(dst, rr) per strip (F3:602 / F3:625). */
+template <int DIR, bool WITH_DOT>
+__global__ void __launch_bounds__(WF_WARPS * 32)
+k_precon_sweep(SkewGeom g, const double* src, double* dst,
+               const double* __restrict__ ax, const double* __restrict__ ay, const double* __restrict__ pre,
+               const double* __restrict__ rr, double* bnd, double* stripdot,
+               SolveScalars* sc, int dot_mode, int check_done) {
+    constexpr int U = WF_U;
+    if (check_done && sc->done) return;
+    const int slot = claim_slot(DIR > 0 ? &sc->ticket_f : &sc->ticket_b, g.nstrips);
+    if (slot < 0) return;
+    const int k = DIR > 0 ? slot : g.nstrips - 1 - slot;
+    const int lane = threadIdx.x & 31;
+    const int y = k * 32 + lane;
+    const bool yok = y < g.h;
+    const int w = g.w, h = g.h;
+    const long long base = (long long)k * g.ss + lane;
+    const int nblk = (w + 31 + U - 1) / U;
+    const int tfirst = DIR > 0 ? 0 : nblk * U - 1;
+    constexpr int E_IN = DIR > 0 ? 0 : 31;
+    constexpr int E_OUT = DIR > 0 ? 31 : 0;
+    const bool has_prev = DIR > 0 ? (k > 0) : (k < g.nstrips - 1);
+
+    /* up-cell coefficient streams of the forward sweep: (x, y-1) lives at i-33, or in the
+     * previous strip's lane 31 for lane 0 */
+    long long upbase = base - 33;
+    if (DIR > 0 && lane == 0) upbase = (long long)(k - 1) * g.ss + 31LL * 32 + 31;
+    const bool has_up = DIR > 0 && y > 0;
+
+    double A[U], AX[U], PR[U], AY[U], PRU[U], RR[U];
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+        int t = tfirst + DIR * j;
+        A[j] = src[base + (long long)t * 32];
+        AX[j] = ax[base + (long long)t * 32];
+        PR[j] = pre[base + (long long)t * 32];
+        if (DIR > 0) {
+            bool okup = has_up && (t - lane) >= 0 && (t - lane) < w;
+            AY[j] = okup ? ay[upbase + (long long)t * 32] : 0.0;
+            PRU[j] = okup ? pre[upbase + (long long)t * 32] : 0.0;
+        } else {
+            AY[j] = ay[base + (long long)t * 32];
+            PRU[j] = 0.0;
+        }
+        RR[j] = WITH_DOT ? rr[base + (long long)t * 32] : 0.0;
+    }
+
+    EdgeFeed<U> feed;
+    feed.init(has_prev ? bnd + (long long)(k - DIR) * w : nullptr, w);
+    feed.prefetch(tfirst + DIR * lane - E_IN, lane);
+    feed.advance();
+
+    double dprev = 0.0, cxprev = 0.0, acc = 0.0;
+    for (int b = 0; b < nblk; b++) {
+        const int t0 = tfirst + DIR * b * U;
+        feed.prefetch(t0 + DIR * (U + lane) - E_IN, lane);
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const int t = t0 + DIR * j;
+            const int x = t - lane;
+            double dn = (DIR > 0) ? __shfl_up_sync(0xffffffffu, dprev, 1) : __shfl_down_sync(0xffffffffu, dprev, 1);
+            const double bv = feed.get(j, lane);
+            if (lane == E_IN) dn = bv;
+            const double pr = PR[j];
+            double v = A[j];
+            double d;
+            if (DIR > 0) {
+                const double cyu = AY[j] * PRU[j];
+                if (x > 0) v = v - cxprev * dprev;
+                if (y > 0) v = v - cyu * dn;
+                d = v * pr;
+                cxprev = AX[j] * pr;
+            } else {
+                const double cx = AX[j] * pr;
+                const double cy = AY[j] * pr;
+                if (x < w - 1) v = v - cx * dprev;
+                if (y < h - 1) v = v - cy * dn;
+                d = v * pr;
+            }
+            const bool active = yok && x >= 0 && x < w;
+            if (active) {
+                dst[base + (long long)t * 32] = d;
+                if (lane == E_OUT) bnd[(long long)k * w + x] = d;
+                if (WITH_DOT) acc += d * RR[j];
+            }
+            dprev = d;
+            /* rotate the prefetch registers: fetch the operands of step t + DIR*U */
+            const int tn = t + DIR * U;
+            if (tn >= 0 && tn < g.tl) {
+                A[j] = src[base + (long long)tn * 32];
+                AX[j] = ax[base + (long long)tn * 32];
+                PR[j] = pre[base + (long long)tn * 32];
+                if (DIR > 0) {
+                    bool okup = has_up && (tn - lane) >= 0 && (tn - lane) < w;
+                    AY[j] = okup ? ay[upbase + (long long)tn * 32] : 0.0;
+                    PRU[j] = okup ? pre[upbase + (long long)tn * 32] : 0.0;
+                } else {
+                    AY[j] = ay[base + (long long)tn * 32];
+                }
+                if (WITH_DOT) RR[j] = rr[base + (long long)tn * 32];
+            }
+        }
+        feed.advance();
+    }
+
+    if (WITH_DOT) {
+        double ws = warp_sum(acc);
+        if (lane == 0) {
+            stripdot[k] = ws;
+            __threadfence();
+            unsigned prev = atomicAdd(&sc->ctr_b, 1u);
+            if (prev == (unsigned)g.nstrips - 1u) {
+                __threadfence();
+                double total = 0.0;
+                for (int kk = 0; kk < g.nstrips; kk++) total += ld_cg(stripdot + kk);
+                if (dot_mode != DOT_NONE) apply_dot_result(sc, dot_mode, total);
+                sc->ctr_b = 0;
+            }
+        }
+    }
+}
+
+/* buildPreconditioner F3:464 -- MIC(0) with tau/sigma, lexicographic recurrence on precon */
+__global__ void __launch_bounds__(WF_WARPS * 32)
+k_build_precon(SkewGeom g, const double* __restrict__ adiag, const double* __restrict__ ax,
+               const double* __restrict__ ay, double* pre, double* bnd, SolveScalars* sc,
+               double tau, double sigma) {
+    constexpr int U = WF_U;
+    const int slot = claim_slot(&sc->ticket_f, g.nstrips);
+    if (slot < 0) return;
+    const int k = slot;
+    const int lane = threadIdx.x & 31;
+    const int y = k * 32 + lane;
+    const bool yok = y < g.h;
+    const int w = g.w;
+    const long long base = (long long)k * g.ss + lane;
+    const int nblk = (w + 31 + U - 1) / U;
+    long long upbase = base - 33;
+    if (lane == 0) upbase = (long long)(k - 1) * g.ss + 31LL * 32 + 31;
+    const bool has_up = y > 0;
+
+    double AD[U], AX[U], AY[U], AXU[U], AYU[U];
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+        int t = j;
+        AD[j] = adiag[base + (long long)t * 32];
+        AX[j] = ax[base + (long long)t * 32];
+        AY[j] = ay[base + (long long)t * 32];
+        bool okup = has_up && (t - lane) >= 0 && (t - lane) < w;
+        AXU[j] = okup ? ax[upbase + (long long)t * 32] : 0.0;
+        AYU[j] = okup ? ay[upbase + (long long)t * 32] : 0.0;
+    }
+    EdgeFeed<U> feed;
+    feed.init(k > 0 ? bnd + (long long)(k - 1) * w : nullptr, w);
+    feed.prefetch(lane, lane);
+    feed.advance();
+
+    double pprev = 0.0, axprev = 0.0, ayprev = 0.0;
+    for (int b = 0; b < nblk; b++) {
+        const int t0 = b * U;
+        feed.prefetch(t0 + U + lane, lane);
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const int t = t0 + j;
+            const int x = t - lane;
+            double pu = __shfl_up_sync(0xffffffffu, pprev, 1);
+            const double bv = feed.get(j, lane);
+            if (lane == 0) pu = bv;
+            const double ad = AD[j];
+            double e = ad;
+            if (x > 0) {
+                double px = axprev * pprev;
+                double py = ayprev * pprev;
+                e -= (px * px + tau * px * py);
+            }
+            if (y > 0) {
+                double px = AXU[j] * pu;
+                double py = AYU[j] * pu;
+                e -= (py * py + tau * px * py);
+            }
+            if (e < sigma * ad) e = ad;
+            const double pc = 1.0 / sqrt(e);
+            const bool active = yok && x >= 0 && x < w;
+            if (active) {
+                pre[base + (long long)t * 32] = pc;
+                if (lane == 31) bnd[(long long)k * w + x] = pc;
+            }
+            pprev = pc; axprev = AX[j]; ayprev = AY[j];
+            const int tn = t + U;
+            if (tn < g.tl) {
+                AD[j] = adiag[base + (long long)tn * 32];
+                AX[j] = ax[base + (long long)tn * 32];
+                AY[j] = ay[base + (long long)tn * 32];
+                bool okup = has_up && (tn - lane) >= 0 && (tn - lane) < w;
+                AXU[j] = okup ? ax[upbase + (long long)tn * 32] : 0.0;
+                AYU[j] = okup ? ay[upbase + (long long)tn * 32] : 0.0;
+            }
+        }
+        feed.advance();
+    }
+}
+
+/* One in-place lexicographic Gauss-Seidel sweep of project()  F1:380 (=F2:395).
+ * `parity` selects the boundary-row set of this sweep; the other set is re-armed here
+ * for the next sweep.  The last strip to finish decides convergence (F1:420). */
+__global__ void __launch_bounds__(WF_WARPS * 32)
+k_gs_sweep(SkewGeom g, const double* __restrict__ r, double* p, double* bnd_use, double* bnd_rearm,
+           SolveScalars* sc, double scale, double tol) {
+    constexpr int U = WF_U;
+    if (sc->done) return;
+    const int slot = claim_slot(&sc->ticket_f, g.nstrips);
+    if (slot < 0) return;
+    const int k = slot;
+    const int lane = threadIdx.x & 31;
+    const int y = k * 32 + lane;
+    const bool yok = y < g.h;
+    const int w = g.w, h = g.h;
+    const long long base = (long long)k * g.ss + lane;
+    const int nblk = (w + 31 + U - 1) / U;
+    for (int x = lane; x < w; x += 32) bnd_rearm[(long long)k * w + x] = sentinel();
+
+    /* old value of the cell below: (x, y+1) is at i+33, or in the next strip's lane 0 */
+    long long dnbase = base + 33;
+    if (lane == 31) dnbase = (long long)(k + 1) * g.ss - 31LL * 32;
+    const bool has_dn = y < h - 1;
+
+    double R[U], PO[U], PD[U];
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+        int t = j;
+        R[j] = r[base + (long long)t * 32];
+        PO[j] = __ldcg(p + base + (long long)t * 32);
+        bool okdn = has_dn && (t - lane) >= 0 && (t - lane) < w;
+        PD[j] = okdn ? __ldcg(p + dnbase + (long long)t * 32) : 0.0;
+    }
+    EdgeFeed<U> feed;
+    feed.init(k > 0 ? bnd_use + (long long)(k - 1) * w : nullptr, w);
+    feed.prefetch(lane, lane);
+    feed.advance();
+
+    double pprev = 0.0;
+    unsigned long long mbits = 0ull;
+    for (int b = 0; b < nblk; b++) {
+        const int t0 = b * U;
+        feed.prefetch(t0 + U + lane, lane);
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const int t = t0 + j;
+            const int x = t - lane;
+            double pu = __shfl_up_sync(0xffffffffu, pprev, 1);
+            const double bv = feed.get(j, lane);
+            if (lane == 0) pu = bv;
+            const double pold = PO[j];
+            /* fetch p(x+1, y) = own old value of the next step before it is needed; the
+             * register of step j+1 still holds it (rotation happens after use) */
+            const int tn = t + U;
+            const double pright = PO[(j + 1) % U];
+            double diag = 0.0, offDiag = 0.0;
+            if (x > 0)     { diag += scale; offDiag -= scale * pprev; }
+            if (y > 0)     { diag += scale; offDiag -= scale * pu; }
+            if (x < w - 1) { diag += scale; offDiag -= scale * pright; }
+            if (y < h - 1) { diag += scale; offDiag -= scale * PD[j]; }
+            const double newP = (R[j] - offDiag) / diag;
+            const bool active = yok && x >= 0 && x < w;
+            if (active) {
+                /* F1:414: old p rounded through float, difference taken in double */
+                double delta = fabs(jfloat(pold) - newP);
+                unsigned long long db = (unsigned long long)__double_as_longlong(delta);
+                mbits = db > mbits ? db : mbits;
+                p[base + (long long)t * 32] = newP;
+                if (lane == 31) bnd_use[(long long)k * w + x] = newP;
+            }
+            pprev = newP;
+            if (tn < g.tl) {
+                R[j] = r[base + (long long)tn * 32];
+                PO[j] = __ldcg(p + base + (long long)tn * 32);
+                bool okdn = has_dn && (tn - lane) >= 0 && (tn - lane) < w;
+                PD[j] = okdn ? __ldcg(p + dnbase + (long long)tn * 32) : 0.0;
+            }
+        }
+        feed.advance();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_down_sync(0xffffffffu, mbits, o);
+        mbits = other > mbits ? other : mbits;
+    }
+    if (lane == 0) {
+        atomicMax(&sc->max_bits, mbits);
+        __threadfence();
+        unsigned prev = atomicAdd(&sc->ctr_b, 1u);
+        if (prev == (unsigned)g.nstrips - 1u) {
+            __threadfence();
+            unsigned long long mb = atomicMax(&sc->max_bits, 0ull);
+            double md = __longlong_as_double((long long)mb);
+            sc->max_error = md;
+            sc->iterations = sc->iterations + 1;
+            if (md < tol) sc->done = 1;
+            sc->max_bits = 0ull;
+            sc->ctr_b = 0;
+            sc->ticket_f = 0;
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------
+ * host-side enqueue helpers
+ * ------------------------------------------------------------------------------- */
+static inline int wf_blocks(const SkewGeom& g) { return (g.nstrips + WF_WARPS - 1) / WF_WARPS; }
+static inline int rearm_blocks(const SkewGeom& g) {
+    long long n = (long long)g.nstrips * g.w;
+    long long b = (n + 255) / 256;
+    return (int)(b < 1 ? 1 : (b > 1184 ? 1184 : b));
+}
+
+void launch_build_precon(SolveCtx& c) {
+    k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
+    k_build_precon<<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.precon,
+                                                                  c.bnd_f, c.sc, c.mic_tau, c.mic_sigma);
+    count(c, 2);
+}
+
+/* dst = M^-1 src: forward then backward sweep.  Boundary rows must be armed. */
+static void enqueue_precon(SolveCtx& c, const double* src, double* dst, int dot_mode, int check_done) {
+    k_precon_sweep<1, false><<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(
+        c.g, src, dst, c.aplusx, c.aplusy, c.precon, nullptr, c.bnd_f, c.stripdot, c.sc, DOT_NONE, check_done);
+    int fused_mode = c.sequential ? DOT_NONE : dot_mode;
+    if (dot_mode != DOT_NONE)
+        k_precon_sweep<-1, true><<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(
+            c.g, dst, dst, c.aplusx, c.aplusy, c.precon, src, c.bnd_b, c.stripdot, c.sc, fused_mode, check_done);
+    else
+        k_precon_sweep<-1, false><<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(
+            c.g, dst, dst, c.aplusx, c.aplusy, c.precon, nullptr, c.bnd_b, c.stripdot, c.sc, DOT_NONE, check_done);
+    count(c, 2);
+    if (c.sequential && dot_mode != DOT_NONE) {
+        k_dot_sequential<<<1, 32, 0, c.stream>>>(c.g, dst, src, c.sc, dot_mode, check_done);
+        count(c);
+    }
+}
+
+void launch_apply_precon(SolveCtx& c, const double* src, double* dst, int /*with_dot_mode*/) {
+    k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
+    count(c);
+    enqueue_precon(c, src, dst, DOT_NONE, 0);
+}
+
+void launch_matvec(SolveCtx& c, const double* b, double* dst) {
+    k_matvec_dot<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, b, dst,
+                                                           c.partials, c.sc, DOT_NONE, 0);
+    count(c);
+}
+
+/* project() F3:590-602: p = 0; z = M^-1 r; s = z; maxError; sigma = z.r */
+void pcg_enqueue_init(SolveCtx& c) {
+    cudaMemsetAsync(c.p, 0, sizeof(double) * (size_t)c.g.total, c.stream);
+    k_solve_reset<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
+    count(c);
+    enqueue_precon(c, c.r, c.z, DOT_SIGMA_INIT, 0);
+    k_init_s<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.r, c.sc, c.tolerance);
+    count(c);
+}
+
+/* n iterations of the loop body F3:603-628; every kernel returns at once after convergence */
+void pcg_enqueue_iterations(SolveCtx& c, int n) {
+    dim3 eg = ew_grid(c.g);
+    for (int it = 0; it < n; it++) {
+        k_matvec_dot<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.s, c.z, c.partials,
+                                                      c.sc, c.sequential ? DOT_NONE : DOT_ZS, 1);
+        count(c);
+        if (c.sequential) {
+            k_dot_sequential<<<1, 32, 0, c.stream>>>(c.g, c.z, c.s, c.sc, DOT_ZS, 1);
+            count(c);
+        }
+        k_update_pr<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.p, c.s, c.r, c.z, c.bnd_f, c.bnd_b, c.sc, c.tolerance);
+        count(c);
+        enqueue_precon(c, c.r, c.z, DOT_SIGMA_NEW, 1);
+        k_update_s<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.sc);
+        count(c);
+    }
+}
+
+void pcg_enqueue_finish(SolveCtx& c, int limit) {
+    k_solve_finish<<<1, 1, 0, c.stream>>>(c.sc, limit);
+    count(c);
+}
+
+/* Gauss-Seidel project() F1:380: _p is warm-started, so only the control state is reset */
+void gs_enqueue_begin(SolveCtx& c) {
+    k_solve_reset<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
+    count(c);
+}
+void gs_enqueue_iterations(SolveCtx& c, int first_iter, int n, double scale) {
+    for (int it = first_iter; it < first_iter + n; it++) {
+        double* use = (it & 1) ? c.bnd_b : c.bnd_f;
+        double* rearm = (it & 1) ? c.bnd_f : c.bnd_b;
+        k_gs_sweep<<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(c.g, c.r, c.p, use, rearm, c.sc, scale, c.tolerance);
+        count(c);
+    }
+}
+void gs_enqueue_finish(SolveCtx& c, int limit) { pcg_enqueue_finish(c, limit); }
+
+} // namespace ifl

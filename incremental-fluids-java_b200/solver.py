@@ -1,0 +1,210 @@
+"""Host-side mirror of the reference's Java API for the timestep hot path.
+
+Class and method names follow the reference (physics.EulerianFluids.ExplicitFluid<N>*.FluidSolver /
+FluidQuantity, physics.solidBodies.SolidBox / SolidSphere): `FluidSolver(w, h, density)`,
+`addInflow(...)`, `update(timestep)`, `maxTimestep()`; field state is read like the Java code reads
+`solver._d._src[i]`.  Every method is a thin call into the C ABI (include/incfluid_b200.h) -- the same
+entry points a Java FluidSolver binds with Panama FFM.  No arithmetic happens here.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _abi
+from ._lib import load, check, IflError  # noqa: F401
+
+_dp = C.POINTER(C.c_double)
+
+
+class SolidBody:
+    """A_SolidBody (solidBodies/A_SolidBody.java:73-87) as a plain record."""
+    TYPE = None
+
+    def __init__(self, posX, posY, scaleX, scaleY, theta, velX, velY, velTheta):
+        self._posX, self._posY = posX, posY
+        self._scaleX, self._scaleY = scaleX, scaleY
+        self._theta = theta
+        self._velX, self._velY, self._velTheta = velX, velY, velTheta
+
+    def update(self, timestep):
+        """A_SolidBody.update (A_SolidBody.java:215): explicit Euler pose update."""
+        self._posX += self._velX * timestep
+        self._posY += self._velY * timestep
+        self._theta += self._velTheta * timestep
+
+    def as_abi(self):
+        b = _abi.Body()
+        b.type = self.TYPE
+        b.pos_x, b.pos_y = self._posX, self._posY
+        b.scale_x, b.scale_y = self._scaleX, self._scaleY
+        b.theta = self._theta
+        b.cos_theta, b.sin_theta = math.cos(self._theta), math.sin(self._theta)
+        b.vel_x, b.vel_y, b.vel_theta = self._velX, self._velY, self._velTheta
+        return b
+
+
+class SolidBox(SolidBody):
+    """SolidBox(x, y, sx, sy, theta, vx, vy, vt) -- solidBodies/SolidBox.java:75"""
+    TYPE = _abi.BODY_BOX
+
+
+class SolidSphere(SolidBody):
+    """SolidSphere(x, y, s, theta, vx, vy, vt) -- solidBodies/SolidSphere.java:57"""
+    TYPE = _abi.BODY_SPHERE
+
+    def __init__(self, x, y, s, theta, velX, velY, velTheta):
+        super().__init__(x, y, s, s, theta, velX, velY, velTheta)
+
+
+class FluidQuantity:
+    """View of one device-resident FluidQuantity (F1:105): `_src` / `_dst` copy the buffers out."""
+
+    def __init__(self, solver, name, w, h, ox, oy):
+        self._solver, self._name = solver, name
+        self._w, self._h, self._ox, self._oy = w, h, ox, oy
+        self._hx = solver._hx
+
+    @property
+    def _src(self):
+        return self._solver.read_field(self._name)
+
+    @_src.setter
+    def _src(self, values):
+        self._solver.write_field(self._name, values)
+
+    @property
+    def _dst(self):
+        return self._solver.read_field(self._name + "_dst")
+
+
+class FluidSolver:
+    """FluidSolver of ExplicitFluid<variant>: same constructor arguments and methods as the reference.
+
+    FluidSolver(w, h, density)                         F1:262, F2:305, F3:339
+    FluidSolver(w, h, density, bodies)                 F4:594, F5:707
+    FluidSolver(w, h, rhoAir, rhoSoot, diffusion, bodies)  F6:763, F7:769, F8:858
+    """
+
+    def __init__(self, w, h, density, *rest, variant=_abi.F3_CONJUGATE_GRADIENTS, device=0, **overrides):
+        _, self._fn = load()
+        bodies = None
+        cfg_kw = dict(density=density, device=device)
+        if variant in (_abi.F4_SOLID_BOUNDARIES, _abi.F5_CURVED_BOUNDARIES):
+            (bodies,) = rest
+        elif variant >= _abi.F6_HEAT:
+            rho_soot, diffusion, bodies = rest
+            cfg_kw.update(density_soot=rho_soot, diffusion=diffusion)
+        elif rest:
+            raise TypeError("FluidSolver(w, h, density) takes no further positional arguments for F1-F3")
+        cfg_kw.update(overrides)
+        self.cfg = _abi.default_config(variant, w, h, **cfg_kw)
+        self._w, self._h = w, h
+        self._hx = 1.0 / min(w, h)
+        self._variant = variant
+        self._h_ = C.c_void_p()
+        check(self._fn["ifl_create"](C.byref(self.cfg), C.byref(self._h_)))
+        self.status = _abi.StepStatus()
+        self._d = FluidQuantity(self, "d", w, h, 0.5, 0.5)
+        self._u = FluidQuantity(self, "u", w + 1, h, 0.0, 0.5)
+        self._v = FluidQuantity(self, "v", w, h + 1, 0.5, 0.0)
+        if variant >= _abi.F6_HEAT:
+            self._t = FluidQuantity(self, "t", w, h, 0.5, 0.5)
+        self._bodies = bodies
+        if bodies is not None:
+            self.set_bodies(bodies)
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h_", None) and self._h_.value:
+            self._fn["ifl_destroy"](self._h_)
+            self._h_ = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- the reference's FluidSolver methods ---------------------------------------------
+    def addInflow(self, x, y, w, h, d, *rest):
+        """addInflow(x,y,w,h,d,u,v) F1:298 / addInflow(x,y,w,h,d,t,u,v) F6:1233"""
+        if len(rest) == 2:
+            t, (u, v) = 0.0, rest
+        else:
+            t, u, v = rest
+        check(self._fn["ifl_add_inflow"](self._h_, x, y, w, h, d, t, u, v))
+
+    def update(self, timestep, want_status=True):
+        """FluidSolver.update(timestep) F1:276 ... F8:1306; returns what the reference only logs."""
+        st = C.byref(self.status) if want_status else None
+        check(self._fn["ifl_update"](self._h_, timestep, st), allow=(_abi.ERR_NAN,))
+        return self.status.as_dict() if want_status else None
+
+    def maxTimestep(self):
+        """FluidSolver.maxTimestep() F1:309"""
+        out = C.c_double()
+        check(self._fn["ifl_max_timestep"](self._h_, C.byref(out)))
+        return out.value
+
+    def ambientT(self):
+        """FluidSolver.ambientT() F6:1240"""
+        return self.cfg.t_ambient
+
+    # -- beyond the reference: batched stepping, stages, raw field access -------------------
+    def set_bodies(self, bodies):
+        arr = (_abi.Body * max(len(bodies), 1))(*[b.as_abi() if isinstance(b, SolidBody) else b for b in bodies])
+        check(self._fn["ifl_set_bodies"](self._h_, arr, len(bodies)))
+
+    def run_steps(self, n, timestep, rect, want_status=True):
+        """n x { addInflow(*rect); update(timestep) } -- the body of the reference's main() loop."""
+        st = C.byref(self.status) if want_status else None
+        check(self._fn["ifl_run_steps"](self._h_, n, timestep, *rect, st), allow=(_abi.ERR_NAN,))
+        return self.status.as_dict() if want_status else None
+
+    def run_stage(self, stage, timestep=0.0, want_status=False):
+        st = C.byref(self.status) if want_status else None
+        check(self._fn["ifl_run_stage"](self._h_, _abi.STAGES[stage], timestep, st), allow=(_abi.ERR_NAN,))
+        return self.status.as_dict() if want_status else None
+
+    def field_size(self, name):
+        n = C.c_size_t()
+        check(self._fn["ifl_field_size"](self._h_, _abi.FIELDS[name], C.byref(n)))
+        return n.value
+
+    def read_field(self, name, out=None):
+        n = self.field_size(name)
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+        assert out.dtype == np.float64 and out.size == n and out.flags.c_contiguous
+        check(self._fn["ifl_read_field"](self._h_, _abi.FIELDS[name], out.ctypes.data_as(_dp), n))
+        return out
+
+    def write_field(self, name, values):
+        arr = np.ascontiguousarray(values, dtype=np.float64).ravel()
+        check(self._fn["ifl_write_field"](self._h_, _abi.FIELDS[name], arr.ctypes.data_as(_dp), arr.size))
+
+    # aliases so parity tests drive oracle and product with the same calls
+    read = read_field
+    write = write_field
+    add_inflow = addInflow
+    max_timestep = maxTimestep
+
+    def synchronize(self):
+        check(self._fn["ifl_synchronize"](self._h_))
+
+    def launch_count(self):
+        n = C.c_uint64()
+        check(self._fn["ifl_launch_count"](self._h_, C.byref(n)))
+        return n.value
+
+    def last_timing(self):
+        out = (C.c_double * 3)()
+        check(self._fn["ifl_last_timing"](self._h_, out))
+        return {"projection_ms": out[0], "advection_ms": out[1], "total_ms": out[2]}

@@ -1,0 +1,180 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): <= 1e-12 relative per advection step, <= 1e-9 relative for pressure
+and fields after 100 steps.  What is actually asserted is stricter wherever the design allows it:
+  * every kernel except the parallel dot products performs the reference's per-cell operations in the
+    reference's order, so advection, RHS, matrix, MIC(0), both triangular sweeps, the mat-vec, the
+    Gauss-Seidel solver and pressure application are compared BIT-EXACT (np.array_equal);
+  * with IFL_FLAG_SEQUENTIAL_REDUCTIONS the dot products are serial too and whole PCG timesteps are
+    bit-exact; without it (the fast path) the fixed-tree sums differ in the last bits and the fields
+    are compared with the stated tolerance, iteration counts included.
+"""
+import numpy as np
+import pytest
+
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    denom = max(np.max(np.abs(b)), 1e-300)
+    return float(np.max(np.abs(a - b)) / denom)
+
+
+def pair(ifl, oracle_cls, variant, w, h, **kw):
+    abi = ifl.abi
+    g = ifl.FluidSolver(w, h, scenes.DENSITY, variant=variant, **kw)
+    o = oracle_cls(abi, abi.default_config(variant, w, h, **kw))
+    return g, o
+
+
+def assert_fields_equal(g, o, names, exact=True, tol=0.0):
+    for n in names:
+        a, b = g.read(n), o.read(n)
+        if exact:
+            bad = np.flatnonzero(a != b)
+            assert bad.size == 0, f"{n}: {bad.size} cells differ, first idx {bad[:5]}, gpu {a[bad[:3]]} ref {b[bad[:3]]}"
+        else:
+            assert rel_err(a, b) <= tol, f"{n}: rel err {rel_err(a, b):.3e} > {tol}"
+
+
+SIZES = [(128, 128), (100, 70), (33, 65), (64, 200)]
+
+
+@pytest.mark.parametrize("variant_name", ["F1_MATRIXLESS", "F3_CONJUGATE_GRADIENTS"])
+@pytest.mark.parametrize("w,h", SIZES)
+def test_advect_bit_exact(ifl, oracle_cls, variant_name, w, h):
+    variant = getattr(ifl.abi, variant_name)
+    g, o = pair(ifl, oracle_cls, variant, w, h)
+    d, u, v = scenes.analytic_velocity(w, h)
+    for s in (g, o):
+        s.write("d", d); s.write("u", u); s.write("v", v)
+        for st in ("advect_d", "advect_u", "advect_v"):
+            s.run_stage(st, scenes.DT)
+    assert_fields_equal(g, o, ["d_dst", "u_dst", "v_dst"])       # <= 1e-12 bar; asserted at 0 ulp
+
+
+@pytest.mark.parametrize("variant_name", ["F1_MATRIXLESS", "F3_CONJUGATE_GRADIENTS"])
+def test_add_inflow_bit_exact(ifl, oracle_cls, variant_name):
+    variant = getattr(ifl.abi, variant_name)
+    for (w, h) in [(128, 128), (96, 40), (40, 96)]:
+        g, o = pair(ifl, oracle_cls, variant, w, h)
+        rect = scenes.inflow_for(ifl.abi, variant)
+        for s in (g, o):
+            s.add_inflow(*rect)
+            s.add_inflow(0.1, 0.1, 0.5, 0.3, 0.5, 0.0, -1.0, 2.0)
+        assert_fields_equal(g, o, ["d", "u", "v"])
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+def test_pcg_stages_bit_exact(ifl, oracle_cls, w, h):
+    """buildRhs, buildPressureMatrix, buildPreconditioner, applyPreconditioner, matrixVectorProduct,
+    applyPressure in isolation on random velocities."""
+    g, o = pair(ifl, oracle_cls, ifl.abi.F3_CONJUGATE_GRADIENTS, w, h)
+    rng = np.random.default_rng(w * 1000 + h)
+    u = rng.normal(size=(w + 1) * h) * 1e-2
+    v = rng.normal(size=w * (h + 1)) * 1e-2
+    svec = rng.normal(size=w * h)
+    pvec = rng.normal(size=w * h)
+    for s in (g, o):
+        s.write("u", u); s.write("v", v)
+        s.run_stage("build_rhs")
+        s.run_stage("build_matrix", scenes.DT)
+        s.run_stage("build_precon")
+    assert_fields_equal(g, o, ["r", "adiag", "aplusx", "aplusy", "precon"])
+    for s in (g, o):
+        s.run_stage("apply_precon")
+    assert_fields_equal(g, o, ["z"])
+    for s in (g, o):
+        s.write("s", svec)
+        s.run_stage("matvec")
+    assert_fields_equal(g, o, ["z"])
+    for s in (g, o):
+        s.write("p", pvec)
+        s.run_stage("apply_pressure", scenes.DT)
+    assert_fields_equal(g, o, ["u", "v"])
+
+
+@pytest.mark.parametrize("w,h", [(128, 128), (100, 70), (33, 65)])
+def test_gauss_seidel_timesteps_bit_exact(ifl, oracle_cls, w, h):
+    """F1 (config 1): whole timesteps -- GS keeps the lexicographic order, max is order independent."""
+    g, o = pair(ifl, oracle_cls, ifl.abi.F1_MATRIXLESS, w, h)
+    for step in range(4):
+        for s in (g, o):
+            s.add_inflow(*scenes.F1_INFLOW)
+        sg, so = g.update(scenes.DT), o.update(scenes.DT)
+        assert sg["iterations_pressure"] == so["iterations_pressure"], (step, sg, so)
+        assert sg["residual_pressure"] == so["residual_pressure"]
+        assert sg["exceeded_budget"] == so["exceeded_budget"]
+        assert_fields_equal(g, o, ["p", "d", "u", "v"])
+
+
+def test_f1_config1_100_steps(ifl, oracle_cls):
+    """BASELINE config 1: 128x128 inflow scene, 100 steps (bar 1e-9; GS path is bit exact)."""
+    g, o = pair(ifl, oracle_cls, ifl.abi.F1_MATRIXLESS, 128, 128)
+    sg = g.run_steps(100, scenes.DT, scenes.F1_INFLOW)
+    so = o.run_steps(100, scenes.DT, scenes.F1_INFLOW)
+    assert sg["iterations_pressure"] == so["iterations_pressure"]
+    assert_fields_equal(g, o, ["p", "d", "u", "v"])
+
+
+@pytest.mark.parametrize("w,h", [(128, 128), (100, 70), (33, 65)])
+def test_pcg_sequential_reductions_bit_exact(ifl, oracle_cls, w, h):
+    """F3 with serial dot products: the complete PCG timestep is bit-identical to the reference order."""
+    flags = ifl.abi.FLAG_SEQUENTIAL_REDUCTIONS
+    g, o = pair(ifl, oracle_cls, ifl.abi.F3_CONJUGATE_GRADIENTS, w, h, flags=flags)
+    for step in range(3):
+        for s in (g, o):
+            s.add_inflow(*scenes.F3_INFLOW)
+        sg, so = g.update(scenes.DT), o.update(scenes.DT)
+        assert sg["iterations_pressure"] == so["iterations_pressure"], (step, sg, so)
+        assert sg["residual_pressure"] == so["residual_pressure"]
+        assert_fields_equal(g, o, ["p", "r", "d", "u", "v"])
+
+
+@pytest.mark.parametrize("variant_name", ["F2_BETTER_ADVECTION", "F3_CONJUGATE_GRADIENTS"])
+def test_fast_path_100_steps_within_tolerance(ifl, oracle_cls, variant_name):
+    """Fast path (parallel fixed-tree dot products), reference scene 128x128, 100 steps: <= 1e-9 relative."""
+    variant = getattr(ifl.abi, variant_name)
+    g, o = pair(ifl, oracle_cls, variant, 128, 128)
+    its_g, its_o = [], []
+    for step in range(100):
+        for s in (g, o):
+            s.add_inflow(*scenes.F3_INFLOW)
+        its_g.append(g.update(scenes.DT)["iterations_pressure"])
+        its_o.append(o.update(scenes.DT)["iterations_pressure"])
+    assert its_g == its_o
+    exact = variant == ifl.abi.F2_BETTER_ADVECTION      # F2 = RK3/cerp advection + Gauss-Seidel: no sums at all
+    assert_fields_equal(g, o, ["p", "d", "u", "v"], exact=exact, tol=1e-9)
+
+
+def test_max_timestep_matches(ifl, oracle_cls):
+    g, o = pair(ifl, oracle_cls, ifl.abi.F1_MATRIXLESS, 64, 48)
+    d, u, v = scenes.analytic_velocity(64, 48)
+    for s in (g, o):
+        s.write("u", u); s.write("v", v)
+    assert g.max_timestep() == o.max_timestep()
+
+
+def test_projection_property_large_grid(ifl):
+    """Size-independent property at BASELINE config 2 size (1024^2): after project + applyPressure the
+    recomputed divergence RHS is below the solver tolerance scale."""
+    w = h = 1024
+    g = ifl.FluidSolver(w, h, scenes.DENSITY, variant=ifl.abi.F3_CONJUGATE_GRADIENTS)
+    g.add_inflow(*scenes.F3_INFLOW)
+    st = g.update(scenes.DT)
+    assert st["nan_residual"] == 0
+    assert 0 < st["iterations_pressure"] <= 600
+    g.run_stage("build_rhs")
+    r = g.read("r")
+    # advection moved the field after the projection, so only boundedness is asserted here
+    assert np.all(np.isfinite(r))
+    # project again from the advected state and verify the residual contract of the solver itself
+    for stg in ("build_matrix", "build_precon", "project"):
+        g.run_stage(stg, scenes.DT)
+    st2 = g.run_stage("apply_pressure", scenes.DT, want_status=True)
+    g.run_stage("build_rhs")
+    r2 = g.read("r")
+    if not st2["exceeded_budget"]:
+        assert np.max(np.abs(r2)) < 1e-3
