@@ -238,6 +238,23 @@ int ifl_launch_count(const ifl_solver* s, uint64_t* count);
  * (CUDA events on the handle's stream): [0] projection, [1] advection, [2] whole call. */
 int ifl_last_timing(ifl_solver* s, double out_ms[3]);
 
+/* Live kernel timing for the roofline report (bench.py).  With profiling enabled the solver
+ * brackets the kernels of ONE iteration per enqueued chunk with CUDA events on the handle's
+ * stream (a sample; iterations that ran after convergence are discarded).  ifl_kernel_timing
+ * returns the average device time per launch of kernel `which` over the samples collected
+ * since the last ifl_set_profiling(s, 1). */
+typedef enum ifl_kernel {
+    IFL_KERNEL_MATVEC_DOT = 0,    /* matrixVectorProduct + dotProduct        F3:544 F3:532 */
+    IFL_KERNEL_UPDATE_PR = 1,     /* 2x scaledAdd + infinityNorm             F3:570 F3:579 */
+    IFL_KERNEL_PRECON_FWD = 2,    /* applyPreconditioner, forward sweep      F3:496-507   */
+    IFL_KERNEL_PRECON_BWD = 3,    /* applyPreconditioner, backward sweep + dotProduct F3:509-521 */
+    IFL_KERNEL_UPDATE_S = 4,      /* scaledAdd(s, z, s, beta)                F3:626 */
+    IFL_KERNEL_GS_SWEEP = 5,      /* one Gauss-Seidel sweep                  F1:383-417 */
+    IFL_KERNEL_COUNT = 6
+} ifl_kernel;
+int ifl_set_profiling(ifl_solver* s, int32_t enable);
+int ifl_kernel_timing(ifl_solver* s, int32_t which, double* avg_ms, int32_t* samples);
+
 /* Human readable text for the last error on this thread. */
 const char* ifl_last_error(void);
 int ifl_abi_version(void);

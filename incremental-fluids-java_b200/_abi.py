@@ -1,7 +1,7 @@
 """ctypes view of include/incfluid_b200.h (the C-ABI drop-in boundary).
 
 Only plain structs, enums and prototypes live here; nothing in this module computes.
-The same struct definitions are reused by the test-side oracle harness so that both
+The same struct definitions are reused by the test harness so that both
 sides of a parity test are driven with byte-identical configuration.
 """
 import ctypes as C
@@ -79,6 +79,8 @@ STAGES = {
     "particles_to_grid": 22, "grid_to_particles": 23, "advect_particles": 24,
 }
 
+KERNELS = {"matvec_dot": 0, "update_pr": 1, "precon_fwd": 2, "precon_bwd": 3, "update_s": 4, "gs_sweep": 5}
+
 _dp = C.POINTER(C.c_double)
 
 # name -> (restype, argtypes) for every symbol include/incfluid_b200.h declares
@@ -101,6 +103,8 @@ PROTOTYPES = {
     "ifl_synchronize": (C.c_int, [C.c_void_p]),
     "ifl_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "ifl_last_timing": (C.c_int, [C.c_void_p, _dp]),
+    "ifl_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
+    "ifl_kernel_timing": (C.c_int, [C.c_void_p, C.c_int32, _dp, C.POINTER(C.c_int32)]),
     "ifl_last_error": (C.c_char_p, []),
     "ifl_abi_version": (C.c_int, []),
 }

@@ -55,6 +55,7 @@ struct ifl_solver {
     unsigned long long launches = 0;
     ifl_step_status last{};
     int chunk_pcg = 32, chunk_gs = 64;
+    Profiler prof;
 };
 
 static bool uses_pcg(const ifl_solver* s) { return s->cfg.variant >= IFL_F3_CONJUGATE_GRADIENTS; }
@@ -117,6 +118,10 @@ void ifl_destroy(ifl_solver* s) {
     if (s->sx.sc) cudaFree(s->sx.sc);
     if (s->d_maxbits) cudaFree(s->d_maxbits);
     if (s->h_sc) cudaFreeHost(s->h_sc);
+    if (s->prof.created) {
+        for (int i = 0; i < Profiler::NS; i++) for (int j = 0; j < Profiler::NE; j++) cudaEventDestroy(s->prof.ev[i][j]);
+        cudaFree(s->prof.d_done);
+    }
     for (auto& e : s->ev_chunk) if (e) cudaEventDestroy(e);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -166,6 +171,7 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     s->sx.sequential = (cfg->flags & IFL_FLAG_SEQUENTIAL_REDUCTIONS) ? 1 : 0;
     s->sx.stream = s->stream;
     s->sx.launches = &s->launches;
+    s->sx.prof = &s->prof;
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaDeviceSynchronize());
     return IFL_OK;
@@ -489,6 +495,45 @@ int ifl_synchronize(ifl_solver* s) {
 int ifl_launch_count(const ifl_solver* s, uint64_t* count) {
     if (!s || !count) INVALID("NULL argument");
     *count = s->launches;
+    return IFL_OK;
+}
+
+int ifl_set_profiling(ifl_solver* s, int32_t enable) {
+    if (!s) INVALID("NULL handle");
+    CU(cudaSetDevice(s->cfg.device));
+    Profiler& p = s->prof;
+    if (enable && !p.created) {
+        for (int i = 0; i < Profiler::NS; i++) for (int j = 0; j < Profiler::NE; j++) CU(cudaEventCreate(&p.ev[i][j]));
+        CU(cudaMalloc(&p.d_done, sizeof(int) * Profiler::NS));
+        p.created = true;
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    p.count = 0;
+    p.enabled = enable ? 1 : 0;
+    return IFL_OK;
+}
+
+int ifl_kernel_timing(ifl_solver* s, int32_t which, double* avg_ms, int32_t* samples) {
+    if (!s || !avg_ms || !samples) INVALID("NULL argument");
+    if (which < 0 || which >= IFL_KERNEL_COUNT) INVALID("unknown kernel id");
+    CU(cudaSetDevice(s->cfg.device));
+    Profiler& p = s->prof;
+    *avg_ms = 0.0; *samples = 0;
+    if (!p.created || p.count == 0) return IFL_OK;
+    CU(cudaStreamSynchronize(s->stream));
+    static int h_done[Profiler::NS];
+    CU(cudaMemcpy(h_done, p.d_done, sizeof(int) * p.count, cudaMemcpyDeviceToHost));
+    const int want_kind = which == IFL_KERNEL_GS_SWEEP ? 1 : 0;
+    const int e0 = which == IFL_KERNEL_GS_SWEEP ? 0 : which;
+    double sum = 0.0; int n = 0;
+    for (int i = 0; i < p.count; i++) {
+        if (p.kind[i] != want_kind || h_done[i]) continue;
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, p.ev[i][e0], p.ev[i][e0 + 1]));
+        sum += ms; n++;
+    }
+    *samples = n;
+    *avg_ms = n ? sum / n : 0.0;
     return IFL_OK;
 }
 

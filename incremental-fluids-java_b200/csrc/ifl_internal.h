@@ -38,6 +38,18 @@ struct SolveScalars {
     int pad;
 };
 
+/* event-sampled kernel timing (ifl_set_profiling / ifl_kernel_timing) */
+struct Profiler {
+    static const int NS = 128;        /* samples kept */
+    static const int NE = 6;          /* events per sample: before/after the 5 kernels of an iteration */
+    int enabled = 0;
+    int count = 0;                    /* samples recorded */
+    cudaEvent_t ev[NS][NE];
+    int kind[NS];                     /* 0 = PCG iteration, 1 = GS sweep */
+    int* d_done = nullptr;            /* done flag seen by the sampled iteration */
+    bool created = false;
+};
+
 struct SolveCtx {
     SkewGeom g;
     /* skewed N-vectors */
@@ -53,6 +65,7 @@ struct SolveCtx {
     int sequential;       /* reductions in the reference's serial order (bit-exact mode) */
     cudaStream_t stream;
     unsigned long long* launches;
+    Profiler* prof;
 };
 
 /* ---- grid (row-major) kernels: ifl_grid_kernels.cu ---- */

@@ -635,9 +635,11 @@ void launch_build_precon(SolveCtx& c) {
 }
 
 /* dst = M^-1 src: forward then backward sweep.  Boundary rows must be armed. */
-static void enqueue_precon(SolveCtx& c, const double* src, double* dst, int dot_mode, int check_done) {
+static inline void prof_mark(SolveCtx& c, int slot, int e);
+static void enqueue_precon(SolveCtx& c, const double* src, double* dst, int dot_mode, int check_done, int ps = -1) {
     k_precon_sweep<1, false><<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(
         c.g, src, dst, c.aplusx, c.aplusy, c.precon, nullptr, c.bnd_f, c.stripdot, c.sc, DOT_NONE, check_done);
+    prof_mark(c, ps, 3);
     int fused_mode = c.sequential ? DOT_NONE : dot_mode;
     if (dot_mode != DOT_NONE)
         k_precon_sweep<-1, true><<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(
@@ -645,6 +647,7 @@ static void enqueue_precon(SolveCtx& c, const double* src, double* dst, int dot_
     else
         k_precon_sweep<-1, false><<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(
             c.g, dst, dst, c.aplusx, c.aplusy, c.precon, nullptr, c.bnd_b, c.stripdot, c.sc, DOT_NONE, check_done);
+    prof_mark(c, ps, 4);
     count(c, 2);
     if (c.sequential && dot_mode != DOT_NONE) {
         k_dot_sequential<<<1, 32, 0, c.stream>>>(c.g, dst, src, c.sc, dot_mode, check_done);
@@ -674,22 +677,42 @@ void pcg_enqueue_init(SolveCtx& c) {
     count(c);
 }
 
+__global__ void k_record_done(const SolveScalars* sc, int* out) { *out = sc->done; }
+
+/* profiling: returns the sample slot to fill for this chunk, or -1 */
+static int prof_begin(SolveCtx& c, int kind) {
+    Profiler* p = c.prof;
+    if (!p || !p->enabled || p->count >= Profiler::NS) return -1;
+    int slot = p->count++;
+    p->kind[slot] = kind;
+    k_record_done<<<1, 1, 0, c.stream>>>(c.sc, p->d_done + slot);
+    cudaEventRecord(p->ev[slot][0], c.stream);
+    return slot;
+}
+static inline void prof_mark(SolveCtx& c, int slot, int e) {
+    if (slot >= 0) cudaEventRecord(c.prof->ev[slot][e], c.stream);
+}
+
 /* n iterations of the loop body F3:603-628; every kernel returns at once after convergence */
 void pcg_enqueue_iterations(SolveCtx& c, int n) {
     dim3 eg = ew_grid(c.g);
     for (int it = 0; it < n; it++) {
+        const int ps = (it == 0 && !c.sequential) ? prof_begin(c, 0) : -1;
         k_matvec_dot<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.s, c.z, c.partials,
                                                       c.sc, c.sequential ? DOT_NONE : DOT_ZS, 1);
         count(c);
+        prof_mark(c, ps, 1);
         if (c.sequential) {
             k_dot_sequential<<<1, 32, 0, c.stream>>>(c.g, c.z, c.s, c.sc, DOT_ZS, 1);
             count(c);
         }
         k_update_pr<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.p, c.s, c.r, c.z, c.bnd_f, c.bnd_b, c.sc, c.tolerance);
         count(c);
-        enqueue_precon(c, c.r, c.z, DOT_SIGMA_NEW, 1);
+        prof_mark(c, ps, 2);
+        enqueue_precon(c, c.r, c.z, DOT_SIGMA_NEW, 1, ps);
         k_update_s<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.sc);
         count(c);
+        prof_mark(c, ps, 5);
     }
 }
 
@@ -707,8 +730,10 @@ void gs_enqueue_iterations(SolveCtx& c, int first_iter, int n, double scale) {
     for (int it = first_iter; it < first_iter + n; it++) {
         double* use = (it & 1) ? c.bnd_b : c.bnd_f;
         double* rearm = (it & 1) ? c.bnd_f : c.bnd_b;
+        const int ps = (it == first_iter) ? prof_begin(c, 1) : -1;
         k_gs_sweep<<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(c.g, c.r, c.p, use, rearm, c.sc, scale, c.tolerance);
         count(c);
+        prof_mark(c, ps, 1);
     }
 }
 void gs_enqueue_finish(SolveCtx& c, int limit) { pcg_enqueue_finish(c, limit); }

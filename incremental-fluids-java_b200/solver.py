@@ -190,7 +190,7 @@ class FluidSolver:
         arr = np.ascontiguousarray(values, dtype=np.float64).ravel()
         check(self._fn["ifl_write_field"](self._h_, _abi.FIELDS[name], arr.ctypes.data_as(_dp), arr.size))
 
-    # aliases so parity tests drive oracle and product with the same calls
+    # snake_case aliases (used by the parity tests)
     read = read_field
     write = write_field
     add_inflow = addInflow
@@ -203,6 +203,15 @@ class FluidSolver:
         n = C.c_uint64()
         check(self._fn["ifl_launch_count"](self._h_, C.byref(n)))
         return n.value
+
+    def set_profiling(self, enable=True):
+        check(self._fn["ifl_set_profiling"](self._h_, 1 if enable else 0))
+
+    def kernel_timing(self, kernel):
+        """(average ms per launch, samples) of one solver kernel, from live CUDA-event samples."""
+        ms, n = C.c_double(), C.c_int32()
+        check(self._fn["ifl_kernel_timing"](self._h_, _abi.KERNELS[kernel], C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def last_timing(self):
         out = (C.c_double * 3)()
