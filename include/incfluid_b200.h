@@ -255,6 +255,11 @@ typedef enum ifl_kernel {
 int ifl_set_profiling(ifl_solver* s, int32_t enable);
 int ifl_kernel_timing(ifl_solver* s, int32_t which, double* avg_ms, int32_t* samples);
 
+/* Diagnostic for profiles/: per-strip timestamps of one applyPreconditioner(z, r) on the resident
+ * state.  out[(sweep*nstrips + k)*8 + i], sweep 0 = forward, 1 = backward; i: 0 enter, 1 after the
+ * first block, 2 unused, 3 end (device ns), 4 unused, 5 blocks, 6 ticket slot, 7 SM id. */
+int ifl_wavefront_trace(ifl_solver* s, int64_t* out, size_t capacity);
+
 /* Human readable text for the last error on this thread. */
 const char* ifl_last_error(void);
 int ifl_abi_version(void);

@@ -111,6 +111,8 @@ void ifl_destroy(ifl_solver* s) {
         for (int i = 0; i < 2; i++) if (q->buf[i]) cudaFree(q->buf[i]);
     if (s->skew_block) cudaFree(s->skew_block);
     if (s->scratch) cudaFree(s->scratch);
+    if (s->sx.pack_f) cudaFree(s->sx.pack_f);
+    if (s->sx.pack_b) cudaFree(s->sx.pack_b);
     if (s->sx.bnd_f) cudaFree(s->sx.bnd_f);
     if (s->sx.bnd_b) cudaFree(s->sx.bnd_b);
     if (s->sx.partials) cudaFree(s->sx.partials);
@@ -145,12 +147,19 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     g.tl = ((s->w + 31 + 15) / 16) * 16 + 16;
     g.ss = (long long)g.tl * 32;
     g.total = (long long)g.nstrips * g.ss;
-    const size_t guard = 64;
+    /* one all-zero strip before and after each vector: the wavefront kernels read the
+     * "row above the first" / "row below the last" from there instead of branching */
+    const size_t guard = (size_t)g.ss;
     const size_t per = (size_t)g.total + 2 * guard;
     CU(cudaMalloc(&s->skew_block, sizeof(double) * per * 8));
     CU(cudaMemset(s->skew_block, 0, sizeof(double) * per * 8));
     double** vecs[8] = {&s->sx.r, &s->sx.p, &s->sx.z, &s->sx.s, &s->sx.adiag, &s->sx.aplusx, &s->sx.aplusy, &s->sx.precon};
     for (int i = 0; i < 8; i++) *vecs[i] = s->skew_block + per * i + guard;
+    const size_t npack = (size_t)g.nstrips * g.tl * 32 * 3;
+    CU(cudaMalloc(&s->sx.pack_f, sizeof(double) * npack));
+    CU(cudaMalloc(&s->sx.pack_b, sizeof(double) * npack));
+    CU(cudaMemset(s->sx.pack_f, 0, sizeof(double) * npack));
+    CU(cudaMemset(s->sx.pack_b, 0, sizeof(double) * npack));
     size_t nb = (size_t)g.nstrips * g.w;
     CU(cudaMalloc(&s->sx.bnd_f, sizeof(double) * nb));
     CU(cudaMalloc(&s->sx.bnd_b, sizeof(double) * nb));
@@ -172,6 +181,7 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     s->sx.stream = s->stream;
     s->sx.launches = &s->launches;
     s->sx.prof = &s->prof;
+    s->sx.trace = nullptr;
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaDeviceSynchronize());
     return IFL_OK;
@@ -495,6 +505,27 @@ int ifl_synchronize(ifl_solver* s) {
 int ifl_launch_count(const ifl_solver* s, uint64_t* count) {
     if (!s || !count) INVALID("NULL argument");
     *count = s->launches;
+    return IFL_OK;
+}
+
+/* Diagnostic: run applyPreconditioner(z, r) once on the resident state and return, per strip and
+ * sweep, {enter, after first block, mid, end} device timestamps (ns), the number of blocks that had
+ * to poll their neighbour, block count, ticket slot and SM id: out[(sweep*nstrips + k)*8 + 0..7]. */
+int ifl_wavefront_trace(ifl_solver* s, int64_t* out, size_t capacity) {
+    if (!s || !out) INVALID("NULL argument");
+    if (!uses_pcg(s)) INVALID("wavefront trace needs a PCG variant");
+    CU(cudaSetDevice(s->cfg.device));
+    size_t n = (size_t)s->sx.g.nstrips * 16;
+    if (capacity < n) INVALID("capacity < 16 * nstrips");
+    long long* d = nullptr;
+    CU(cudaMalloc(&d, sizeof(long long) * n));
+    CU(cudaMemsetAsync(d, 0, sizeof(long long) * n, s->stream));
+    s->sx.trace = d;
+    launch_apply_precon(s->sx, s->sx.r, s->sx.z, 0);
+    s->sx.trace = nullptr;
+    CU(cudaMemcpyAsync(out, d, sizeof(long long) * n, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaFree(d));
     return IFL_OK;
 }
 

@@ -114,6 +114,16 @@ __device__ __forceinline__ bool is_sentinel(double v) {
 }
 __device__ __forceinline__ double sentinel() { return __longlong_as_double((long long)IFL_SENTINEL_BITS); }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned get_smid() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
 __device__ __forceinline__ double ld_volatile(const double* p) {
     return *reinterpret_cast<const volatile double*>(p);

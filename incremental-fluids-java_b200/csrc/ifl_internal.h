@@ -54,6 +54,8 @@ struct SolveCtx {
     SkewGeom g;
     /* skewed N-vectors */
     double *r, *p, *z, *s, *adiag, *aplusx, *aplusy, *precon;
+    /* per-solve packed operands of the triangular sweeps (products aPlusX*precon, aPlusY*precon, precon) */
+    double *pack_f, *pack_b;   /* [strip][tl/16][3][16][32], see k_precon_coeffs */
     /* strip boundary rows (flag-in-data), [nstrips][w] each; two sets for GS parity */
     double *bnd_f, *bnd_b;
     double *partials;     /* per-block partial sums */
@@ -66,6 +68,7 @@ struct SolveCtx {
     cudaStream_t stream;
     unsigned long long* launches;
     Profiler* prof;
+    long long* trace;     /* diagnostic: per-strip timestamps of the next apply_precon, or nullptr */
 };
 
 /* ---- grid (row-major) kernels: ifl_grid_kernels.cu ---- */

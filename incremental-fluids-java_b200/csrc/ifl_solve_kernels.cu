@@ -20,6 +20,7 @@
  *
  * Compiled with -fmad=false.
  */
+#include <cstdlib>
 #include "ifl_internal.h"
 
 namespace ifl {
@@ -303,120 +304,268 @@ struct EdgeFeed {
     __device__ __forceinline__ double get(int j, int lane) {
         double v = __shfl_sync(0xffffffffu, cur, j);
         while (is_sentinel(v)) {
-            if (lane == j) cur = ld_volatile(acur);
+            /* one round trip re-reads every value of the block that is still missing */
+            if (lane >= j && lane < U && acur != nullptr && is_sentinel(cur)) cur = ld_volatile(acur);
             v = __shfl_sync(0xffffffffu, cur, j);
         }
         return v;
     }
 };
 
+
+/* Edge feed of the two triangular sweeps.  The lane whose result leaves the strip (E_OUT: lane 31
+ * forward, lane 0 backward) is also the lane that READS the neighbouring strip's edge row: it puts
+ * that value into the register every lane shuffles, and the shuffle is a rotation, so the lane on
+ * the other edge (E_IN) receives the boundary value with the same single shuffle that hands every
+ * other lane its neighbour's result -- no second shuffle or select on the dependency chain. */
+template <int U>
+struct RotFeed {
+    const double* row;   /* neighbour strip's boundary row (only the feeder lane dereferences it) */
+    int w;
+    bool feeder;
+    double cur[U], nxt[U];
+    __device__ __forceinline__ void init(const double* r, int w_, bool feeder_) {
+        row = r; w = w_; feeder = feeder_ && (r != nullptr);
+#pragma unroll
+        for (int j = 0; j < U; j++) { cur[j] = 0.0; nxt[j] = 0.0; }
+    }
+    /* x0 = column needed at step 0 of the block, columns advance by dir per step */
+    __device__ __forceinline__ void prefetch(int x0, int dir) {
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const int x = x0 + dir * j;
+            nxt[j] = (feeder && x >= 0 && x < w) ? ld_volatile(row + x) : 0.0;
+        }
+    }
+    __device__ __forceinline__ void advance() {
+#pragma unroll
+        for (int j = 0; j < U; j++) cur[j] = nxt[j];
+    }
+    /* warp-uniform: are all values of the current block present? */
+    __device__ __forceinline__ bool ready() const {
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < U; j++) ok = ok && !is_sentinel(cur[j]);
+        return __all_sync(0xffffffffu, ok);
+    }
+    /* spin until the value of step j (column x) has arrived; re-reads all missing later ones too */
+    __device__ __forceinline__ void wait(int j0, int x0, int dir) {
+        for (;;) {
+            bool ok = !is_sentinel(cur[j0]);
+            if (__all_sync(0xffffffffu, ok)) return;
+#pragma unroll
+            for (int j = 0; j < U; j++)
+                if (j >= j0 && is_sentinel(cur[j])) cur[j] = ld_volatile(row + x0 + dir * j);
+        }
+    }
+};
+
+/* ---- TMA (bulk async copy) staging ------------------------------------------------
+ * In the skewed layout the operands a warp needs for U consecutive steps are, per array, ONE
+ * contiguous run of U*256 bytes.  Lane 0 streams them into a per-warp shared-memory ring with
+ * cp.async.bulk (mbarrier completion), several blocks ahead; the lanes then read their
+ * operands with conflict-free 8-byte LDS.  (Register-rotating LDG prefetch does not work
+ * here: with 6 scoreboard slots the wait for the oldest load also waits for the youngest.) */
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "IFL_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra IFL_DONE;\n"
+        "bra IFL_WAIT;\n"
+        "IFL_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+static constexpr int SW_U = 16;                     /* steps (t-rows) per staged block of the triangular sweeps */
+static constexpr int SW_STAGES = 2;                 /* ring depth: block b+1 streams in while block b is computed */
+static constexpr int SW_TILE = SW_U * 32;           /* doubles per array per block (4 KB) */
+static constexpr int SW_PACK = 3 * SW_TILE;         /* packed coefficient block: 3 arrays (12 KB) */
+
+/* Packed sweep coefficients.  applyPreconditioner multiplies `aPlusX[i]*precon[i]` and
+ * `aPlusY[i]*precon[i]` before it touches dst (F3:500,503,514,517); those products are the same in
+ * every PCG iteration, so they are formed once per solve -- same operands, same rounding -- and
+ * stored per strip in blocks of SW_U t-rows, [3][SW_U][32] doubles, so that ONE bulk copy fetches
+ * every static operand of SW_U wavefront steps:
+ *     forward pack : cx = aPlusX*precon (own cell), cy = (aPlusY*precon) of the cell above, precon
+ *     backward pack: cx = aPlusX*precon,            cy = aPlusY*precon (own cell),          precon */
+__global__ void __launch_bounds__(EW_THREADS)
+k_precon_coeffs(SkewGeom g, const double* __restrict__ ax, const double* __restrict__ ay,
+                const double* __restrict__ pre, double* __restrict__ pack_f, double* __restrict__ pack_b) {
+    const long long pstrip = (long long)(g.tl / SW_U) * SW_PACK;
+    IFL_EW_LOOP_BEGIN(g)
+        if (ok_) {
+            const double pr = pre[i_];
+            const double cx = ax[i_] * pr;
+            const double cy = ay[i_] * pr;
+            const long long j = (l_ > 0) ? (i_ - 33) : (base_ - g.ss + (long long)(t_ + 31) * 32 + 31);
+            const double cyu = ay[j] * pre[j];
+            const long long o = (long long)k_ * pstrip + (long long)(t_ / SW_U) * SW_PACK + (t_ % SW_U) * 32 + l_;
+            pack_f[o] = cx; pack_f[o + SW_TILE] = cyu; pack_f[o + 2 * SW_TILE] = pr;
+            pack_b[o] = cx; pack_b[o + SW_TILE] = cy;  pack_b[o + 2 * SW_TILE] = pr;
+        }
+    IFL_EW_LOOP_END
+}
+
+/* SW_U consecutive steps of one strip.  tile_a: staged src block [SW_U][32]; tile_c: staged
+ * coefficient pack [3][SW_U][32]; tile_r: staged rr block (fused dot) */
+template <int DIR, bool WITH_DOT, bool CHECKED, bool FASTFEED>
+__device__ __forceinline__ void sweep_steps(const double* tile_a, const double* tile_c, const double* tile_r,
+                                            const int t0, const int lane, const int w, const bool yok,
+                                            double* pdst, double* pbnd, RotFeed<SW_U>& feed,
+                                            double& dprev, double& cxprev, double& acc) {
+    constexpr int U = SW_U;
+    constexpr int E_IN = DIR > 0 ? 0 : 31;
+    constexpr int E_OUT = DIR > 0 ? 31 : 0;
+    const int srclane = (lane - DIR) & 31;          /* rotation: E_IN reads from E_OUT */
+    const bool is_out = lane == E_OUT;
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+        const int row = (DIR > 0 ? j : U - 1 - j) * 32;
+        const double a = tile_a[row];
+        const double cx = tile_c[row];
+        const double cyv = tile_c[SW_TILE + row];
+        const double pr = tile_c[2 * SW_TILE + row];
+        if (!FASTFEED) feed.wait(j, t0 - E_IN, DIR);
+        const double give = is_out ? feed.cur[j] : dprev;
+        const double dn = __shfl_sync(0xffffffffu, give, srclane);
+        double v = a;
+        if (DIR > 0) {
+            v = v - cxprev * dprev;      /* (aPlusX[i-1]*precon[i-1]) * dst[i-1]   F3:500 */
+            v = v - cyv * dn;            /* (aPlusY[i-w]*precon[i-w]) * dst[i-w]   F3:503 */
+            cxprev = cx;
+        } else {
+            v = v - cx * dprev;          /* (aPlusX[i]*precon[i]) * dst[i+1]       F3:514 */
+            v = v - cyv * dn;            /* (aPlusY[i]*precon[i]) * dst[i+w]       F3:517 */
+        }
+        const double d = v * pr;
+        if (CHECKED) {
+            const int x = t0 + DIR * j - lane;
+            const bool active = yok && x >= 0 && x < w;
+            if (active) pdst[DIR * j * 32] = d;
+            if (active && is_out) pbnd[DIR * j] = d;
+        } else {
+            /* interior block: only rows y >= h are inactive; they hold +0.0, and storing +0.0 into
+             * their (zero) padding cells keeps the padding zero -- no branch needed */
+            pdst[DIR * j * 32] = d;
+            if (is_out) pbnd[DIR * j] = d;
+        }
+        /* inactive lanes hold +0.0 and rr is zero in the padding: adding them is exact */
+        if (WITH_DOT) acc += d * tile_r[row];
+        dprev = d;
+    }
+}
+
 /* applyPreconditioner F3:495: DIR=+1 forward substitution (first loop nest), DIR=-1
  * backward substitution (second loop nest).  WITH_DOT (backward only) accumulates
- * dotProduct(dst, rr) per strip (F3:602 / F3:625). */
+ * dotProduct(dst, rr) per strip (F3:602 / F3:625).
+ *
+ * The reference guards the two neighbour terms with x>0 / y>0 (x<w-1 / y<h-1).  Here the
+ * guards are implicit: every skewed array is zero outside the grid (padding cells, plus one
+ * all-zero strip before and after), and inactive lanes provably carry +0.0, so the guarded
+ * products are +0.0 and `v - (+0.0)` returns v bit-for-bit (also for v = -0.0).  For the
+ * backward sweep aPlusX(w-1,y) and aPlusY(x,h-1) are +0.0 by construction (F3:447,454). */
 template <int DIR, bool WITH_DOT>
 __global__ void __launch_bounds__(WF_WARPS * 32)
-k_precon_sweep(SkewGeom g, const double* src, double* dst,
-               const double* __restrict__ ax, const double* __restrict__ ay, const double* __restrict__ pre,
+k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restrict__ pack,
                const double* __restrict__ rr, double* bnd, double* stripdot,
-               SolveScalars* sc, int dot_mode, int check_done) {
-    constexpr int U = WF_U;
+               SolveScalars* sc, int dot_mode, int check_done, long long* trace) {
+    constexpr int U = SW_U;
+    constexpr int S = SW_STAGES;
+    constexpr int STAGE = (WITH_DOT ? 2 : 1) * SW_TILE + SW_PACK;     /* doubles per stage */
+    extern __shared__ __align__(128) unsigned char wf_smem[];
     if (check_done && sc->done) return;
+    const long long tr_enter = trace ? (long long)globaltimer_ns() : 0;
     const int slot = claim_slot(DIR > 0 ? &sc->ticket_f : &sc->ticket_b, g.nstrips);
     if (slot < 0) return;
     const int k = DIR > 0 ? slot : g.nstrips - 1 - slot;
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int y = k * 32 + lane;
     const bool yok = y < g.h;
-    const int w = g.w, h = g.h;
-    const long long base = (long long)k * g.ss + lane;
+    const int w = g.w;
     const int nblk = (w + 31 + U - 1) / U;
     const int tfirst = DIR > 0 ? 0 : nblk * U - 1;
     constexpr int E_IN = DIR > 0 ? 0 : 31;
-    constexpr int E_OUT = DIR > 0 ? 31 : 0;
     const bool has_prev = DIR > 0 ? (k > 0) : (k < g.nstrips - 1);
 
-    /* up-cell coefficient streams of the forward sweep: (x, y-1) lives at i-33, or in the
-     * previous strip's lane 31 for lane 0 */
-    long long upbase = base - 33;
-    if (DIR > 0 && lane == 0) upbase = (long long)(k - 1) * g.ss + 31LL * 32 + 31;
-    const bool has_up = DIR > 0 && y > 0;
-
-    double A[U], AX[U], PR[U], AY[U], PRU[U], RR[U];
-#pragma unroll
-    for (int j = 0; j < U; j++) {
-        int t = tfirst + DIR * j;
-        A[j] = src[base + (long long)t * 32];
-        AX[j] = ax[base + (long long)t * 32];
-        PR[j] = pre[base + (long long)t * 32];
-        if (DIR > 0) {
-            bool okup = has_up && (t - lane) >= 0 && (t - lane) < w;
-            AY[j] = okup ? ay[upbase + (long long)t * 32] : 0.0;
-            PRU[j] = okup ? pre[upbase + (long long)t * 32] : 0.0;
-        } else {
-            AY[j] = ay[base + (long long)t * 32];
-            PRU[j] = 0.0;
-        }
-        RR[j] = WITH_DOT ? rr[base + (long long)t * 32] : 0.0;
+    /* per-warp ring of S stages: [src tile | coefficient pack | rr tile], then S mbarriers */
+    double* ring = reinterpret_cast<double*>(wf_smem) + (size_t)warp * S * STAGE;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(
+        wf_smem + (size_t)WF_WARPS * S * STAGE * sizeof(double)) + warp * S;
+    const double* gsrc = src + (long long)k * g.ss;
+    const double* grr = WITH_DOT ? rr + (long long)k * g.ss : nullptr;
+    const double* gpack = pack + (long long)k * (g.tl / U) * SW_PACK;
+    /* block b covers t-rows [gb*U, gb*U + U) with gb = b forward, nblk-1-b backward */
+    auto issue = [&](int b) {
+        const int st = b % S;
+        const int gb = DIR > 0 ? b : nblk - 1 - b;
+        double* sdst = ring + (size_t)st * STAGE;
+        mbar_expect_tx(&bars[st], STAGE * sizeof(double));
+        bulk_g2s(sdst, gsrc + (long long)gb * SW_TILE, SW_TILE * sizeof(double), &bars[st]);
+        bulk_g2s(sdst + SW_TILE, gpack + (long long)gb * SW_PACK, SW_PACK * sizeof(double), &bars[st]);
+        if (WITH_DOT) bulk_g2s(sdst + SW_TILE + SW_PACK, grr + (long long)gb * SW_TILE, SW_TILE * sizeof(double), &bars[st]);
+    };
+    if (lane == 0) {
+        for (int i = 0; i < S; i++) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int b = 0; b < S && b < nblk; b++) issue(b);
     }
+    __syncwarp();
 
-    EdgeFeed<U> feed;
-    feed.init(has_prev ? bnd + (long long)(k - DIR) * w : nullptr, w);
-    feed.prefetch(tfirst + DIR * lane - E_IN, lane);
+    double* pdst = dst + (long long)k * g.ss + lane + (long long)tfirst * 32;
+    double* pbnd = bnd + (long long)k * w + (tfirst - lane);   /* column x = t - lane of this strip's edge row */
+
+    RotFeed<U> feed;
+    feed.init(has_prev ? bnd + (long long)(k - DIR) * w : nullptr, w, lane == (DIR > 0 ? 31 : 0));
+    feed.prefetch(tfirst - E_IN, DIR);
     feed.advance();
 
     double dprev = 0.0, cxprev = 0.0, acc = 0.0;
+    long long tr_first = 0;
     for (int b = 0; b < nblk; b++) {
         const int t0 = tfirst + DIR * b * U;
-        feed.prefetch(t0 + DIR * (U + lane) - E_IN, lane);
-#pragma unroll
-        for (int j = 0; j < U; j++) {
-            const int t = t0 + DIR * j;
-            const int x = t - lane;
-            double dn = (DIR > 0) ? __shfl_up_sync(0xffffffffu, dprev, 1) : __shfl_down_sync(0xffffffffu, dprev, 1);
-            const double bv = feed.get(j, lane);
-            if (lane == E_IN) dn = bv;
-            const double pr = PR[j];
-            double v = A[j];
-            double d;
-            if (DIR > 0) {
-                const double cyu = AY[j] * PRU[j];
-                if (x > 0) v = v - cxprev * dprev;
-                if (y > 0) v = v - cyu * dn;
-                d = v * pr;
-                cxprev = AX[j] * pr;
-            } else {
-                const double cx = AX[j] * pr;
-                const double cy = AY[j] * pr;
-                if (x < w - 1) v = v - cx * dprev;
-                if (y < h - 1) v = v - cy * dn;
-                d = v * pr;
-            }
-            const bool active = yok && x >= 0 && x < w;
-            if (active) {
-                dst[base + (long long)t * 32] = d;
-                if (lane == E_OUT) bnd[(long long)k * w + x] = d;
-                if (WITH_DOT) acc += d * RR[j];
-            }
-            dprev = d;
-            /* rotate the prefetch registers: fetch the operands of step t + DIR*U */
-            const int tn = t + DIR * U;
-            if (tn >= 0 && tn < g.tl) {
-                A[j] = src[base + (long long)tn * 32];
-                AX[j] = ax[base + (long long)tn * 32];
-                PR[j] = pre[base + (long long)tn * 32];
-                if (DIR > 0) {
-                    bool okup = has_up && (tn - lane) >= 0 && (tn - lane) < w;
-                    AY[j] = okup ? ay[upbase + (long long)tn * 32] : 0.0;
-                    PRU[j] = okup ? pre[upbase + (long long)tn * 32] : 0.0;
-                } else {
-                    AY[j] = ay[base + (long long)tn * 32];
-                }
-                if (WITH_DOT) RR[j] = rr[base + (long long)tn * 32];
-            }
+        const int st = b % S;
+        feed.prefetch(t0 + DIR * U - E_IN, DIR);
+        const bool fast_feed = feed.ready();
+        if (trace && b == 1) tr_first = (long long)globaltimer_ns();
+        const int tlo = DIR > 0 ? t0 : t0 - (U - 1);
+        const bool interior = (tlo - 31 >= 0) && (tlo + U - 1 < w);
+        mbar_wait(&bars[st], (unsigned)((b / S) & 1));
+        const double* tile_a = ring + (size_t)st * STAGE + lane;
+        const double* tile_c = tile_a + SW_TILE;
+        const double* tile_r = tile_a + SW_TILE + SW_PACK;
+        if (interior) {
+            if (fast_feed) sweep_steps<DIR, WITH_DOT, false, true>(tile_a, tile_c, tile_r, t0, lane, w, yok, pdst, pbnd, feed, dprev, cxprev, acc);
+            else sweep_steps<DIR, WITH_DOT, false, false>(tile_a, tile_c, tile_r, t0, lane, w, yok, pdst, pbnd, feed, dprev, cxprev, acc);
+        } else {
+            sweep_steps<DIR, WITH_DOT, true, false>(tile_a, tile_c, tile_r, t0, lane, w, yok, pdst, pbnd, feed, dprev, cxprev, acc);
         }
+        pdst += DIR * U * 32;
+        pbnd += DIR * U;
+        __syncwarp();
+        if (lane == 0 && b + S < nblk) issue(b + S);
         feed.advance();
     }
 
+    if (trace && lane == 0) {
+        long long* tr = trace + (long long)k * 8;
+        tr[0] = tr_enter; tr[1] = tr_first; tr[2] = 0; tr[3] = (long long)globaltimer_ns();
+        tr[4] = 0; tr[5] = nblk; tr[6] = slot; tr[7] = (long long)get_smid();
+    }
     if (WITH_DOT) {
         double ws = warp_sum(acc);
         if (lane == 0) {
@@ -631,22 +780,38 @@ void launch_build_precon(SolveCtx& c) {
     k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
     k_build_precon<<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.precon,
                                                                   c.bnd_f, c.sc, c.mic_tau, c.mic_sigma);
-    count(c, 2);
+    k_precon_coeffs<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.aplusx, c.aplusy, c.precon, c.pack_f, c.pack_b);
+    count(c, 3);
+}
+
+static size_t sweep_smem(bool with_dot) {
+    size_t stage = ((with_dot ? 2 : 1) * SW_TILE + SW_PACK) * sizeof(double);
+    return (size_t)WF_WARPS * SW_STAGES * stage + (size_t)WF_WARPS * SW_STAGES * 8;
+}
+static void sweep_attrs_once() {
+    static bool done = false;
+    if (done) return;
+    cudaFuncSetAttribute(k_precon_sweep<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem(false));
+    cudaFuncSetAttribute(k_precon_sweep<-1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem(false));
+    cudaFuncSetAttribute(k_precon_sweep<-1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem(true));
+    done = true;
 }
 
 /* dst = M^-1 src: forward then backward sweep.  Boundary rows must be armed. */
 static inline void prof_mark(SolveCtx& c, int slot, int e);
 static void enqueue_precon(SolveCtx& c, const double* src, double* dst, int dot_mode, int check_done, int ps = -1) {
-    k_precon_sweep<1, false><<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(
-        c.g, src, dst, c.aplusx, c.aplusy, c.precon, nullptr, c.bnd_f, c.stripdot, c.sc, DOT_NONE, check_done);
+    sweep_attrs_once();
+    k_precon_sweep<1, false><<<wf_blocks(c.g), WF_WARPS * 32, sweep_smem(false), c.stream>>>(
+        c.g, src, dst, c.pack_f, nullptr, c.bnd_f, c.stripdot, c.sc, DOT_NONE, check_done, c.trace);
     prof_mark(c, ps, 3);
     int fused_mode = c.sequential ? DOT_NONE : dot_mode;
+    long long* tr2 = c.trace ? c.trace + 8 * c.g.nstrips : nullptr;
     if (dot_mode != DOT_NONE)
-        k_precon_sweep<-1, true><<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(
-            c.g, dst, dst, c.aplusx, c.aplusy, c.precon, src, c.bnd_b, c.stripdot, c.sc, fused_mode, check_done);
+        k_precon_sweep<-1, true><<<wf_blocks(c.g), WF_WARPS * 32, sweep_smem(true), c.stream>>>(
+            c.g, dst, dst, c.pack_b, src, c.bnd_b, c.stripdot, c.sc, fused_mode, check_done, tr2);
     else
-        k_precon_sweep<-1, false><<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(
-            c.g, dst, dst, c.aplusx, c.aplusy, c.precon, nullptr, c.bnd_b, c.stripdot, c.sc, DOT_NONE, check_done);
+        k_precon_sweep<-1, false><<<wf_blocks(c.g), WF_WARPS * 32, sweep_smem(false), c.stream>>>(
+            c.g, dst, dst, c.pack_b, nullptr, c.bnd_b, c.stripdot, c.sc, DOT_NONE, check_done, tr2);
     prof_mark(c, ps, 4);
     count(c, 2);
     if (c.sequential && dot_mode != DOT_NONE) {

@@ -213,6 +213,13 @@ class FluidSolver:
         check(self._fn["ifl_kernel_timing"](self._h_, _abi.KERNELS[kernel], C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def wavefront_trace(self):
+        """Per-strip timestamps of one applyPreconditioner: array [2 sweeps][nstrips][8] (see the header)."""
+        nstrips = (self._h + 31) // 32
+        out = np.zeros(2 * nstrips * 8, dtype=np.int64)
+        check(self._fn["ifl_wavefront_trace"](self._h_, out.ctypes.data_as(C.POINTER(C.c_int64)), out.size))
+        return out.reshape(2, nstrips, 8)
+
     def last_timing(self):
         out = (C.c_double * 3)()
         check(self._fn["ifl_last_timing"](self._h_, out))
