@@ -32,6 +32,9 @@ struct Quantity {             /* FluidQuantity: _src/_dst ping-pong (F1:105-147)
     QGeom q{};
     double* buf[2] = {nullptr, nullptr};
     int cur = 0;
+    SolidQ sq{};              /* F4+: _phi/_volume/_normalX/_normalY/_cell/_body/_mask (F4:138-153, F5:241-266) */
+    bool present = false;
+    SolidView view() const { return SolidView{sq.cell, sq.body, sq.volume}; }
     double* src() const { return buf[cur]; }
     double* dst() const { return buf[cur ^ 1]; }
     void swap() { cur ^= 1; }                       /* F1:143 */
@@ -43,7 +46,7 @@ struct ifl_solver {
     int w, h;
     double hx;
     cudaStream_t stream = nullptr;
-    Quantity d, u, v;
+    Quantity d, t, u, v;
     SolveCtx sx{};
     double* skew_block = nullptr;      /* one allocation holding the 8 skewed N-vectors */
     double* scratch = nullptr;         /* (w+1)*(h+1) doubles for layout conversions */
@@ -56,9 +59,21 @@ struct ifl_solver {
     ifl_step_status last{};
     int chunk_pcg = 32, chunk_gs = 64;
     Profiler prof;
+    /* F4+ */
+    ifl_body* d_bodies = nullptr;
+    int nbodies = 0, bodies_cap = 0;
+    double *udens = nullptr, *vdens = nullptr;      /* _uDensity/_vDensity F7:757-758 */
+    unsigned char* extrap_state = nullptr;
+    unsigned int* d_progress = nullptr;
+    unsigned int* h_progress = nullptr;
+    SolveScalars* sc_heat = nullptr;                /* device copy of the heat solve's final scalars */
+    SolveScalars* h_sc_heat = nullptr;
 };
 
 static bool uses_pcg(const ifl_solver* s) { return s->cfg.variant >= IFL_F3_CONJUGATE_GRADIENTS; }
+static bool has_solids(const ifl_solver* s) { return s->cfg.variant >= IFL_F4_SOLID_BOUNDARIES; }
+static bool has_heat(const ifl_solver* s) { return s->cfg.variant >= IFL_F6_HEAT; }
+static bool has_vardens(const ifl_solver* s) { return s->cfg.variant >= IFL_F7_VARIABLE_DENSITY; }
 
 extern "C" {
 
@@ -93,13 +108,29 @@ int ifl_default_config(ifl_config* cfg, int32_t variant, int32_t w, int32_t h) {
     return IFL_OK;
 }
 
-static int alloc_quantity(Quantity& q, int w, int h, double ox, double oy) {
+static int alloc_quantity(Quantity& q, int w, int h, double ox, double oy, int variant = 0, cudaStream_t st = nullptr) {
     q.q = QGeom{w, h, ox, oy};
+    q.present = true;
     for (int i = 0; i < 2; i++) {
         CU(cudaMalloc(&q.buf[i], sizeof(double) * q.count()));
         CU(cudaMemset(q.buf[i], 0, sizeof(double) * q.count()));
     }
     q.cur = 0;
+    if (variant >= IFL_F4_SOLID_BOUNDARIES) {
+        SolidQ& s = q.sq;
+        s.w = w; s.h = h; s.ox = ox; s.oy = oy;
+        const size_t n = q.count(), np = (size_t)(w + 1) * (h + 1);
+        CU(cudaMalloc(&s.phi, sizeof(double) * np));       CU(cudaMemset(s.phi, 0, sizeof(double) * np));
+        CU(cudaMalloc(&s.volume, sizeof(double) * n));
+        CU(cudaMalloc(&s.normalX, sizeof(double) * n));    CU(cudaMemset(s.normalX, 0, sizeof(double) * n));
+        CU(cudaMalloc(&s.normalY, sizeof(double) * n));    CU(cudaMemset(s.normalY, 0, sizeof(double) * n));
+        CU(cudaMalloc(&s.cell, n));
+        CU(cudaMalloc(&s.body, sizeof(int) * n));          CU(cudaMemset(s.body, 0, sizeof(int) * n));
+        CU(cudaMalloc(&s.mask, sizeof(int) * n));          CU(cudaMemset(s.mask, 0, sizeof(int) * n));
+        /* F5:313-316: _cell = FLUID, _volume = 1.0; F4:183 leaves _cell null (3 = neither fluid nor solid) */
+        launch_fill_value(st, s.volume, n, 1.0);
+        launch_fill_u8(st, s.cell, n, variant == IFL_F4_SOLID_BOUNDARIES ? 3 : IFL_CELL_FLUID);
+    }
     return IFL_OK;
 }
 
@@ -107,8 +138,16 @@ void ifl_destroy(ifl_solver* s) {
     if (!s) return;
     cudaSetDevice(s->cfg.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    for (Quantity* q : {&s->d, &s->u, &s->v})
+    for (Quantity* q : {&s->d, &s->t, &s->u, &s->v}) {
         for (int i = 0; i < 2; i++) if (q->buf[i]) cudaFree(q->buf[i]);
+        void* ptrs[] = {q->sq.phi, q->sq.volume, q->sq.normalX, q->sq.normalY, q->sq.cell, q->sq.body, q->sq.mask};
+        for (void* p : ptrs) if (p) cudaFree(p);
+    }
+    void* extra[] = {s->d_bodies, s->udens, s->vdens, s->extrap_state, s->d_progress, s->sc_heat,
+                     s->sx.fl ? (void*)(s->sx.fl - s->sx.g.ss) : nullptr};
+    for (void* p : extra) if (p) cudaFree(p);
+    if (s->h_progress) cudaFreeHost(s->h_progress);
+    if (s->h_sc_heat) cudaFreeHost(s->h_sc_heat);
     if (s->skew_block) cudaFree(s->skew_block);
     if (s->scratch) cudaFree(s->scratch);
     if (s->sx.pack_f) cudaFree(s->sx.pack_f);
@@ -137,9 +176,25 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     CU(cudaSetDevice(cfg->device));
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     int rc;
-    if ((rc = alloc_quantity(s->d, s->w, s->h, 0.5, 0.5))) return rc;       /* F1:268 */
-    if ((rc = alloc_quantity(s->u, s->w + 1, s->h, 0.0, 0.5))) return rc;   /* F1:269 */
-    if ((rc = alloc_quantity(s->v, s->w, s->h + 1, 0.5, 0.0))) return rc;   /* F1:270 */
+    const int var = cfg->variant;
+    if ((rc = alloc_quantity(s->d, s->w, s->h, 0.5, 0.5, var, s->stream))) return rc;       /* F1:268 */
+    if ((rc = alloc_quantity(s->u, s->w + 1, s->h, 0.0, 0.5, var, s->stream))) return rc;   /* F1:269 */
+    if ((rc = alloc_quantity(s->v, s->w, s->h + 1, 0.5, 0.0, var, s->stream))) return rc;   /* F1:270 */
+    if (has_heat(s)) {
+        if ((rc = alloc_quantity(s->t, s->w, s->h, 0.5, 0.5, var, s->stream))) return rc;   /* F6:792 */
+        launch_fill_value(s->stream, s->t.src(), s->t.count(), cfg->t_ambient);             /* F6:797-799 */
+    }
+    if (has_vardens(s)) {
+        CU(cudaMalloc(&s->udens, sizeof(double) * s->u.count())); CU(cudaMemset(s->udens, 0, sizeof(double) * s->u.count()));
+        CU(cudaMalloc(&s->vdens, sizeof(double) * s->v.count())); CU(cudaMemset(s->vdens, 0, sizeof(double) * s->v.count()));
+    }
+    if (has_solids(s)) {
+        CU(cudaMalloc(&s->extrap_state, (size_t)(s->w + 1) * (s->h + 1)));
+        CU(cudaMalloc(&s->d_progress, sizeof(unsigned int)));
+        CU(cudaMallocHost(&s->h_progress, sizeof(unsigned int)));
+        CU(cudaMalloc(&s->sc_heat, sizeof(SolveScalars))); CU(cudaMemset(s->sc_heat, 0, sizeof(SolveScalars)));
+        CU(cudaMallocHost(&s->h_sc_heat, sizeof(SolveScalars))); memset(s->h_sc_heat, 0, sizeof(SolveScalars));
+    }
 
     SkewGeom& g = s->sx.g;
     g.w = s->w; g.h = s->h;
@@ -171,13 +226,20 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     CU(cudaMalloc(&s->d_maxbits, sizeof(unsigned long long)));
     CU(cudaMallocHost(&s->h_sc, sizeof(SolveScalars) * 2));
     memset(s->h_sc, 0, sizeof(SolveScalars) * 2);
-    CU(cudaMalloc(&s->scratch, sizeof(double) * (size_t)(s->w + 1) * (s->h + 1)));
+    CU(cudaMalloc(&s->scratch, sizeof(double) * (size_t)(s->w + 2) * (s->h + 2)));
     for (auto& e : s->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : s->ev) CU(cudaEventCreate(&e));
     s->sx.tolerance = cfg->tolerance;
     s->sx.mic_tau = cfg->mic_tau;
     s->sx.mic_sigma = cfg->mic_sigma;
     s->sx.sequential = (cfg->flags & IFL_FLAG_SEQUENTIAL_REDUCTIONS) ? 1 : 0;
+    s->sx.fl = nullptr;
+    s->sx.mask_vector_ops = has_heat(s) ? 1 : 0;                /* F6:999-1064 vs F4:825-878 */
+    if (has_solids(s)) {
+        CU(cudaMalloc(&s->sx.fl, (size_t)per));
+        CU(cudaMemset(s->sx.fl, 0, (size_t)per));
+        s->sx.fl += guard;
+    }
     s->sx.stream = s->stream;
     s->sx.launches = &s->launches;
     s->sx.prof = &s->prof;
@@ -193,7 +255,7 @@ int ifl_create(const ifl_config* cfg, ifl_solver** out) {
     if (cfg->abi_version != IFL_ABI_VERSION) INVALID("abi_version mismatch");
     if (cfg->w < 2 || cfg->h < 2) INVALID("grid must be at least 2x2");
     if (cfg->variant < IFL_F1_MATRIXLESS || cfg->variant > IFL_F8_FLIP) INVALID("unknown variant");
-    if (cfg->variant > IFL_F3_CONJUGATE_GRADIENTS) {
+    if (cfg->variant > IFL_F7_VARIABLE_DENSITY) {
         snprintf(g_err, sizeof g_err, "variant %d is not implemented by this build", cfg->variant);
         return IFL_ERR_UNSUPPORTED;
     }
@@ -219,18 +281,33 @@ int ifl_create(const ifl_config* cfg, ifl_solver** out) {
 
 int ifl_set_bodies(ifl_solver* s, const ifl_body* bodies, int32_t count) {
     if (!s) INVALID("NULL handle");
-    (void)bodies;
-    if (count == 0) return IFL_OK;
-    snprintf(g_err, sizeof g_err, "variant %d has no solid bodies", s->cfg.variant);
-    return IFL_ERR_UNSUPPORTED;
+    if (count < 0 || (count > 0 && !bodies)) INVALID("bad body table");
+    if (!has_solids(s)) {
+        if (count == 0) return IFL_OK;
+        snprintf(g_err, sizeof g_err, "variant %d has no solid bodies", s->cfg.variant);
+        return IFL_ERR_UNSUPPORTED;
+    }
+    CU(cudaSetDevice(s->cfg.device));
+    if (count > s->bodies_cap) {
+        if (s->d_bodies) CU(cudaFree(s->d_bodies));
+        CU(cudaMalloc(&s->d_bodies, sizeof(ifl_body) * count));
+        s->bodies_cap = count;
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    if (count > 0) CU(cudaMemcpy(s->d_bodies, bodies, sizeof(ifl_body) * count, cudaMemcpyHostToDevice));
+    s->nbodies = count;
+    return IFL_OK;
 }
 
 int ifl_add_inflow(ifl_solver* s, double x, double y, double w, double h, double d, double t, double u, double v) {
     if (!s) INVALID("NULL handle");
-    (void)t;
     CU(cudaSetDevice(s->cfg.device));
-    /* FluidSolver.addInflow F1:298 / F3:385 */
+    /* FluidSolver.addInflow F1:298 / F3:385 / F6:1233 */
     launch_add_inflow(s->stream, s->cfg.variant, s->d.q, s->d.src(), s->hx, x, y, x + w, y + h, d);
+    if (has_heat(s)) {
+        launch_add_inflow(s->stream, s->cfg.variant, s->t.q, s->t.src(), s->hx, x, y, x + w, y + h, t);
+        s->launches++;
+    }
     launch_add_inflow(s->stream, s->cfg.variant, s->u.q, s->u.src(), s->hx, x, y, x + w, y + h, u);
     launch_add_inflow(s->stream, s->cfg.variant, s->v.q, s->v.src(), s->hx, x, y, x + w, y + h, v);
     s->launches += 3;
@@ -275,8 +352,16 @@ static int fetch_status(ifl_solver* s, ifl_step_status* st) {
     s->last.residual_pressure = h.max_error;
     s->last.exceeded_budget = h.exceeded ? 1 : 0;
     s->last.nan_residual = h.nan;
+    if (has_heat(s)) {
+        CU(cudaMemcpy(s->h_sc_heat, s->sc_heat, sizeof(SolveScalars), cudaMemcpyDeviceToHost));
+        const SolveScalars& hh = *s->h_sc_heat;
+        s->last.iterations_heat = hh.iterations;
+        s->last.residual_heat = hh.max_error;
+        if (hh.exceeded) s->last.exceeded_budget |= 2;
+        if (hh.nan) s->last.nan_residual = 1;
+    }
     if (st) *st = s->last;
-    return h.nan ? IFL_ERR_NAN : IFL_OK;
+    return s->last.nan_residual ? IFL_ERR_NAN : IFL_OK;
 }
 
 static int stage_build_rhs(ifl_solver* s) {
@@ -311,7 +396,139 @@ static int stage_advect(ifl_solver* s, Quantity& q, double timestep) {
     return IFL_OK;
 }
 
+/* ---- F4-F7 stages ----------------------------------------------------------------------------- */
+static int stage_fill_solid_fields(ifl_solver* s) {
+    /* FluidQuantity.fillSolidFields returns at once for an empty body list (F4:330) */
+    if (s->nbodies > 0) {
+        for (Quantity* q : {&s->d, &s->t, &s->u, &s->v}) {
+            if (!q->present) continue;
+            launch_fill_solid_fields(s->stream, q->sq, s->d_bodies, s->nbodies, s->hx, s->cfg.variant);
+            s->launches += s->cfg.variant >= IFL_F5_CURVED_BOUNDARIES ? 2 : 1;
+        }
+    }
+    launch_cell_flags(s->stream, s->sx.g, s->d.sq.cell, s->sx.fl);
+    s->launches++;
+    return IFL_OK;
+}
+static int stage_set_boundary(ifl_solver* s) {
+    launch_set_boundary(s->stream, s->w, s->h, s->d.sq.cell, s->d.sq.body, s->d_bodies, s->u.src(), s->v.src(), s->hx);
+    s->launches++;
+    return IFL_OK;
+}
+static int stage_build_rhs_solid(ifl_solver* s) {
+    launch_build_rhs_solid(s->stream, s->sx.g, s->d.view(), s->u.view(), s->v.view(), s->u.src(), s->v.src(),
+                           s->d_bodies, s->nbodies, s->sx.r, s->hx, s->cfg.variant);
+    s->launches++;
+    return IFL_OK;
+}
+static int stage_compute_densities(ifl_solver* s) {
+    launch_compute_densities(s->stream, s->w, s->h, s->d.src(), s->t.src(), s->udens, s->vdens,
+                             s->cfg.density, s->cfg.density_soot, s->cfg.t_ambient);
+    s->launches++;
+    return IFL_OK;
+}
+static int stage_build_matrix_solid(ifl_solver* s, double timestep) {
+    const int var = s->cfg.variant;
+    double scale; int mode;
+    if (var >= IFL_F7_VARIABLE_DENSITY) { scale = timestep / (s->hx * s->hx); mode = 2; }                 /* F7:878 */
+    else { scale = timestep / (s->cfg.density * s->hx * s->hx); mode = var >= IFL_F5_CURVED_BOUNDARIES ? 1 : 0; }  /* F4:714, F5:826 */
+    launch_build_matrix_solid(s->stream, s->sx.g, s->d.sq.cell, s->u.sq.volume, s->v.sq.volume, s->udens, s->vdens,
+                              scale, mode, s->sx.adiag, s->sx.aplusx, s->sx.aplusy);
+    s->launches++;
+    return IFL_OK;
+}
+__global__ void k_copy_scalars(const SolveScalars* a, SolveScalars* b) { *b = *a; }
+static int stage_project(ifl_solver* s, double timestep);
+/* F6:1190-1201 (=F7:1221-1232): r <- T; heat matrix; MIC; project; T <- p */
+static int stage_heat_solve(ifl_solver* s, double timestep) {
+    launch_rows_to_skew(s->stream, s->sx.g, s->t.src(), s->sx.r);
+    double scale = s->cfg.diffusion * timestep * 1.0 / (s->hx * s->hx);                                    /* F6:888 */
+    launch_build_matrix_solid(s->stream, s->sx.g, s->d.sq.cell, nullptr, nullptr, nullptr, nullptr, scale, 3,
+                              s->sx.adiag, s->sx.aplusx, s->sx.aplusy);
+    s->launches += 2;
+    launch_build_precon(s->sx);
+    int rc = stage_project(s, timestep);
+    if (rc) return rc;
+    k_copy_scalars<<<1, 1, 0, s->stream>>>(s->sx.sc, s->sc_heat);
+    launch_skew_to_rows(s->stream, s->sx.g, s->sx.p, s->t.src());
+    s->launches += 2;
+    return IFL_OK;
+}
+static int stage_add_buoyancy(ifl_solver* s, double timestep) {
+    launch_add_buoyancy(s->stream, s->w, s->h, s->d.src(), s->t.src(), s->v.src(), timestep, s->cfg.gravity,
+                        s->cfg.density, s->cfg.density_soot, s->cfg.t_ambient);
+    s->launches++;
+    return IFL_OK;
+}
+static int stage_apply_pressure_solid(ifl_solver* s, double timestep) {
+    const bool vd = has_vardens(s);
+    double scale = vd ? timestep / s->hx : timestep / (s->cfg.density * s->hx);                           /* F7:1149 / F4:928 */
+    launch_apply_pressure_solid(s->stream, s->sx.g, s->d.sq.cell, s->sx.p, s->u.src(), s->v.src(), s->udens, s->vdens,
+                                scale, vd ? 1 : 0);
+    s->launches++;
+    return IFL_OK;
+}
+/* FluidQuantity.extrapolate F4:452: sweeps until no pending solid cell can be filled any more */
+static int stage_extrapolate(ifl_solver* s, Quantity& q) {
+    launch_extrap_fill_mask(s->stream, q.sq, s->extrap_state);
+    s->launches++;
+    const int batch = 4;
+    const int max_batches = (q.q.w + q.q.h) / batch + 2;
+    for (int b = 0; b < max_batches; b++) {
+        CU(cudaMemsetAsync(s->d_progress, 0, sizeof(unsigned int), s->stream));
+        for (int i = 0; i < batch; i++) launch_extrap_sweep(s->stream, q.sq, q.src(), s->extrap_state, s->d_progress);
+        s->launches += batch;
+        CU(cudaMemcpyAsync(s->h_progress, s->d_progress, sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        if (*s->h_progress == 0) break;
+    }
+    return IFL_OK;
+}
+static int stage_advect_solid(ifl_solver* s, Quantity& q, double timestep) {
+    launch_advect_solid(s->stream, q.q, q.src(), q.dst(), s->u.q, s->u.src(), s->v.q, s->v.src(),
+                        q.sq.cell, q.sq.body, s->d_bodies, timestep, s->hx);
+    s->launches++;
+    return IFL_OK;
+}
+static int stage_project(ifl_solver* s, double timestep);
+static int stage_apply_pressure(ifl_solver* s, double timestep);
+
+/* FluidSolver.update F4:617 / F5:1089 / F6:1181 / F7:1212 */
+static int update_solid(ifl_solver* s, double timestep) {
+    int rc;
+    CU(cudaEventRecord(s->ev[0], s->stream));
+    stage_fill_solid_fields(s);
+    if (has_heat(s)) {
+        if ((rc = stage_heat_solve(s, timestep))) return rc;
+        if ((rc = stage_extrapolate(s, s->t))) return rc;
+        stage_add_buoyancy(s, timestep);
+    }
+    stage_set_boundary(s);
+    stage_build_rhs_solid(s);
+    if (has_vardens(s)) stage_compute_densities(s);
+    stage_build_matrix_solid(s, timestep);
+    launch_build_precon(s->sx);
+    if ((rc = stage_project(s, timestep))) return rc;
+    stage_apply_pressure_solid(s, timestep);
+    if ((rc = stage_extrapolate(s, s->d))) return rc;
+    if ((rc = stage_extrapolate(s, s->u))) return rc;
+    if ((rc = stage_extrapolate(s, s->v))) return rc;
+    stage_set_boundary(s);
+    CU(cudaEventRecord(s->ev[1], s->stream));
+    stage_advect_solid(s, s->d, timestep);
+    if (has_heat(s)) stage_advect_solid(s, s->t, timestep);
+    stage_advect_solid(s, s->u, timestep);
+    stage_advect_solid(s, s->v, timestep);
+    s->d.swap(); s->u.swap(); s->v.swap();
+    if (has_heat(s)) s->t.swap();
+    CU(cudaEventRecord(s->ev[2], s->stream));
+    s->ev_valid = true;
+    CU(cudaGetLastError());
+    return IFL_OK;
+}
+
 static int update_impl(ifl_solver* s, double timestep) {
+    if (has_solids(s)) return update_solid(s, timestep);
     /* FluidSolver.update  F1:276 / F2:322 / F3:361 */
     CU(cudaEventRecord(s->ev[0], s->stream));
     stage_build_rhs(s);
@@ -362,19 +579,31 @@ int ifl_run_stage(ifl_solver* s, int32_t stage, double timestep, ifl_step_status
     CU(cudaSetDevice(s->cfg.device));
     int rc = IFL_OK;
     switch (stage) {
-        case IFL_STAGE_BUILD_RHS: rc = stage_build_rhs(s); break;
+        case IFL_STAGE_BUILD_RHS: rc = has_solids(s) ? stage_build_rhs_solid(s) : stage_build_rhs(s); break;
         case IFL_STAGE_BUILD_MATRIX:
             if (!uses_pcg(s)) goto unsupported;
-            rc = stage_build_matrix(s, timestep); break;
+            rc = has_solids(s) ? stage_build_matrix_solid(s, timestep) : stage_build_matrix(s, timestep); break;
         case IFL_STAGE_BUILD_PRECON:
             if (!uses_pcg(s)) goto unsupported;
             launch_build_precon(s->sx); break;
         case IFL_STAGE_PROJECT: rc = stage_project(s, timestep); break;
-        case IFL_STAGE_APPLY_PRESSURE: rc = stage_apply_pressure(s, timestep); break;
-        case IFL_STAGE_ADVECT_D: rc = stage_advect(s, s->d, timestep); break;
-        case IFL_STAGE_ADVECT_U: rc = stage_advect(s, s->u, timestep); break;
-        case IFL_STAGE_ADVECT_V: rc = stage_advect(s, s->v, timestep); break;
-        case IFL_STAGE_SWAP: s->d.swap(); s->u.swap(); s->v.swap(); break;
+        case IFL_STAGE_APPLY_PRESSURE: rc = has_solids(s) ? stage_apply_pressure_solid(s, timestep) : stage_apply_pressure(s, timestep); break;
+        case IFL_STAGE_ADVECT_D: rc = has_solids(s) ? stage_advect_solid(s, s->d, timestep) : stage_advect(s, s->d, timestep); break;
+        case IFL_STAGE_ADVECT_T:
+            if (!has_heat(s)) goto unsupported;
+            rc = stage_advect_solid(s, s->t, timestep); break;
+        case IFL_STAGE_ADVECT_U: rc = has_solids(s) ? stage_advect_solid(s, s->u, timestep) : stage_advect(s, s->u, timestep); break;
+        case IFL_STAGE_ADVECT_V: rc = has_solids(s) ? stage_advect_solid(s, s->v, timestep) : stage_advect(s, s->v, timestep); break;
+        case IFL_STAGE_SWAP: s->d.swap(); s->u.swap(); s->v.swap(); if (has_heat(s)) s->t.swap(); break;
+        case IFL_STAGE_FILL_SOLID_FIELDS: if (!has_solids(s)) goto unsupported; rc = stage_fill_solid_fields(s); break;
+        case IFL_STAGE_SET_BOUNDARY: if (!has_solids(s)) goto unsupported; rc = stage_set_boundary(s); break;
+        case IFL_STAGE_EXTRAPOLATE_D: if (!has_solids(s)) goto unsupported; rc = stage_extrapolate(s, s->d); break;
+        case IFL_STAGE_EXTRAPOLATE_T: if (!has_heat(s)) goto unsupported; rc = stage_extrapolate(s, s->t); break;
+        case IFL_STAGE_EXTRAPOLATE_U: if (!has_solids(s)) goto unsupported; rc = stage_extrapolate(s, s->u); break;
+        case IFL_STAGE_EXTRAPOLATE_V: if (!has_solids(s)) goto unsupported; rc = stage_extrapolate(s, s->v); break;
+        case IFL_STAGE_HEAT_SOLVE: if (!has_heat(s)) goto unsupported; rc = stage_heat_solve(s, timestep); break;
+        case IFL_STAGE_ADD_BUOYANCY: if (!has_heat(s)) goto unsupported; rc = stage_add_buoyancy(s, timestep); break;
+        case IFL_STAGE_COMPUTE_DENSITIES: if (!has_vardens(s)) goto unsupported; rc = stage_compute_densities(s); break;
         case IFL_STAGE_APPLY_PRECON:
             if (!uses_pcg(s)) goto unsupported;
             launch_apply_precon(s->sx, s->sx.r, s->sx.z, 0); break;
@@ -409,10 +638,15 @@ int ifl_max_timestep(ifl_solver* s, double* out) {
     return IFL_OK;
 }
 
-/* field lookup: returns device pointer and element count; skewed != 0 for solve vectors */
-static int field_ptr(ifl_solver* s, int32_t field, double** ptr, size_t* count, int* skewed) {
-    *skewed = 0;
+/* field lookup: device pointer, element count and storage kind */
+enum { KIND_ROWS = 0, KIND_SKEW = 1, KIND_U8 = 2, KIND_I32 = 3 };
+static int field_ptr(ifl_solver* s, int32_t field, void** ptr, size_t* count, int* kind) {
+    *kind = KIND_ROWS;
     size_t n = (size_t)s->w * s->h;
+    auto bad = [&]() {
+        snprintf(g_err, sizeof g_err, "field %d does not exist for variant %d", field, s->cfg.variant);
+        return IFL_ERR_INVALID;
+    };
     switch (field) {
         case IFL_FIELD_D: *ptr = s->d.src(); *count = s->d.count(); return IFL_OK;
         case IFL_FIELD_U: *ptr = s->u.src(); *count = s->u.count(); return IFL_OK;
@@ -420,6 +654,10 @@ static int field_ptr(ifl_solver* s, int32_t field, double** ptr, size_t* count, 
         case IFL_FIELD_D_DST: *ptr = s->d.dst(); *count = s->d.count(); return IFL_OK;
         case IFL_FIELD_U_DST: *ptr = s->u.dst(); *count = s->u.count(); return IFL_OK;
         case IFL_FIELD_V_DST: *ptr = s->v.dst(); *count = s->v.count(); return IFL_OK;
+        case IFL_FIELD_T: if (!has_heat(s)) return bad(); *ptr = s->t.src(); *count = s->t.count(); return IFL_OK;
+        case IFL_FIELD_T_DST: if (!has_heat(s)) return bad(); *ptr = s->t.dst(); *count = s->t.count(); return IFL_OK;
+        case IFL_FIELD_UDENSITY: if (!has_vardens(s)) return bad(); *ptr = s->udens; *count = s->u.count(); return IFL_OK;
+        case IFL_FIELD_VDENSITY: if (!has_vardens(s)) return bad(); *ptr = s->vdens; *count = s->v.count(); return IFL_OK;
         case IFL_FIELD_P: *ptr = s->sx.p; break;
         case IFL_FIELD_R: *ptr = s->sx.r; break;
         case IFL_FIELD_Z: *ptr = s->sx.z; break;
@@ -428,34 +666,47 @@ static int field_ptr(ifl_solver* s, int32_t field, double** ptr, size_t* count, 
         case IFL_FIELD_ADIAG: *ptr = s->sx.adiag; break;
         case IFL_FIELD_APLUSX: *ptr = s->sx.aplusx; break;
         case IFL_FIELD_APLUSY: *ptr = s->sx.aplusy; break;
-        default:
-            snprintf(g_err, sizeof g_err, "field %d does not exist for variant %d", field, s->cfg.variant);
-            return IFL_ERR_INVALID;
+        default: {
+            if (!has_solids(s) || field < IFL_FIELD_VOLUME_D || field > IFL_FIELD_PHI_V) return bad();
+            const int qi = (field - IFL_FIELD_VOLUME_D) % 4, grp = (field - IFL_FIELD_VOLUME_D) / 4;
+            Quantity* q = qi == 0 ? &s->d : qi == 1 ? &s->t : qi == 2 ? &s->u : &s->v;
+            if (!q->present) return bad();
+            *count = q->count();
+            switch (grp) {
+                case 0: if (s->cfg.variant < IFL_F5_CURVED_BOUNDARIES) return bad(); *ptr = q->sq.volume; return IFL_OK;
+                case 1: *ptr = q->sq.normalX; return IFL_OK;
+                case 2: *ptr = q->sq.normalY; return IFL_OK;
+                case 3: *ptr = q->sq.cell; *kind = KIND_U8; return IFL_OK;
+                case 4: *ptr = q->sq.body; *kind = KIND_I32; return IFL_OK;
+                case 5: if (s->cfg.variant < IFL_F5_CURVED_BOUNDARIES) return bad();
+                        *ptr = q->sq.phi; *count = (size_t)(q->q.w + 1) * (q->q.h + 1); return IFL_OK;
+            }
+            return bad();
+        }
     }
     *count = n;
-    *skewed = 1;
+    *kind = KIND_SKEW;
     return IFL_OK;
 }
 
 int ifl_field_size(const ifl_solver* s, int32_t field, size_t* count) {
     if (!s || !count) INVALID("NULL argument");
-    double* p; int sk;
-    return field_ptr(const_cast<ifl_solver*>(s), field, &p, count, &sk);
+    void* p; int kind;
+    return field_ptr(const_cast<ifl_solver*>(s), field, &p, count, &kind);
 }
 
 int ifl_read_field(ifl_solver* s, int32_t field, double* host, size_t count) {
     if (!s || !host) INVALID("NULL argument");
     CU(cudaSetDevice(s->cfg.device));
-    double* p; size_t n; int sk;
-    int rc = field_ptr(s, field, &p, &n, &sk);
+    void* p; size_t n; int kind;
+    int rc = field_ptr(s, field, &p, &n, &kind);
     if (rc) return rc;
     if (n != count) INVALID("count does not match ifl_field_size");
-    if (sk) {
-        launch_skew_to_rows(s->stream, s->sx.g, p, s->scratch);
-        s->launches++;
-        p = s->scratch;
-    }
-    CU(cudaMemcpyAsync(host, p, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
+    const double* srcp = (const double*)p;
+    if (kind == KIND_SKEW) { launch_skew_to_rows(s->stream, s->sx.g, (const double*)p, s->scratch); srcp = s->scratch; s->launches++; }
+    else if (kind == KIND_U8) { launch_u8_to_double(s->stream, (const unsigned char*)p, s->scratch, n); srcp = s->scratch; s->launches++; }
+    else if (kind == KIND_I32) { launch_i32_to_double(s->stream, (const int*)p, s->scratch, n); srcp = s->scratch; s->launches++; }
+    CU(cudaMemcpyAsync(host, srcp, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return IFL_OK;
 }
@@ -463,13 +714,17 @@ int ifl_read_field(ifl_solver* s, int32_t field, double* host, size_t count) {
 int ifl_write_field(ifl_solver* s, int32_t field, const double* host, size_t count) {
     if (!s || !host) INVALID("NULL argument");
     CU(cudaSetDevice(s->cfg.device));
-    double* p; size_t n; int sk;
-    int rc = field_ptr(s, field, &p, &n, &sk);
+    void* p; size_t n; int kind;
+    int rc = field_ptr(s, field, &p, &n, &kind);
     if (rc) return rc;
     if (n != count) INVALID("count does not match ifl_field_size");
-    if (sk) {
+    if (kind == KIND_U8 || kind == KIND_I32) {
+        snprintf(g_err, sizeof g_err, "field %d (cell/body) is derived by fillSolidFields and is read-only", field);
+        return IFL_ERR_UNSUPPORTED;
+    }
+    if (kind == KIND_SKEW) {
         CU(cudaMemcpyAsync(s->scratch, host, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-        launch_rows_to_skew(s->stream, s->sx.g, s->scratch, p);
+        launch_rows_to_skew(s->stream, s->sx.g, s->scratch, (double*)p);
         s->launches++;
     } else {
         CU(cudaMemcpyAsync(p, host, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));

@@ -17,6 +17,24 @@ struct QGeom {
     double ox, oy;
 };
 
+/* Per-quantity solid data of F4+ (F4:138-153, F5:241-266), device pointers. */
+struct SolidQ {
+    int w, h;
+    double ox, oy;
+    double* phi;            /* (w+1)*(h+1) */
+    double* volume;
+    double* normalX;
+    double* normalY;
+    unsigned char* cell;    /* IFL_CELL_* */
+    int* body;
+    int* mask;
+};
+struct SolidView {
+    const unsigned char* cell;
+    const int* body;
+    const double* volume;
+};
+
 /* Device scalars of one pressure solve.  Every solver kernel reads its coefficients
  * from here, so a whole solve is enqueued without returning to the host. */
 struct SolveScalars {
@@ -65,6 +83,8 @@ struct SolveCtx {
     double tolerance;
     double mic_tau, mic_sigma;
     int sequential;       /* reductions in the reference's serial order (bit-exact mode) */
+    unsigned char* fl;    /* skewed fluid flags of _d._cell (F4+), nullptr for F1-F3 */
+    int mask_vector_ops;  /* F6+: dotProduct/scaledAdd/infinityNorm only over fluid cells (F6:999-1064) */
     cudaStream_t stream;
     unsigned long long* launches;
     Profiler* prof;
@@ -82,6 +102,32 @@ void launch_apply_pressure(cudaStream_t st, const SkewGeom& g, const double* p, 
 void launch_skew_to_rows(cudaStream_t st, const SkewGeom& g, const double* skew, double* rows);
 void launch_rows_to_skew(cudaStream_t st, const SkewGeom& g, const double* rows, double* skew);
 void launch_max_velocity(cudaStream_t st, int w, int h, const double* u, const double* v, unsigned long long* out_bits);
+
+/* ---- F4-F7 grid kernels: ifl_solid_kernels.cu ---- */
+void launch_fill_solid_fields(cudaStream_t st, const SolidQ& q, const ifl_body* bodies, int nbodies, double hx, int variant);
+void launch_cell_flags(cudaStream_t st, const SkewGeom& g, const unsigned char* cell, unsigned char* fl);
+void launch_set_boundary(cudaStream_t st, int w, int h, const unsigned char* cell, const int* body,
+                         const ifl_body* bodies, double* u, double* v, double hx);
+void launch_build_rhs_solid(cudaStream_t st, const SkewGeom& g, const SolidView& d, const SolidView& uq, const SolidView& vq,
+                            const double* u, const double* v, const ifl_body* bodies, int nbodies, double* r, double hx, int variant);
+void launch_compute_densities(cudaStream_t st, int w, int h, const double* dsrc, const double* tsrc, double* ud, double* vd,
+                              double rho_air, double rho_soot, double t_amb);
+void launch_build_matrix_solid(cudaStream_t st, const SkewGeom& g, const unsigned char* cell, const double* uvol, const double* vvol,
+                               const double* ud, const double* vd, double scale, int mode,
+                               double* adiag, double* aplusx, double* aplusy);
+void launch_apply_pressure_solid(cudaStream_t st, const SkewGeom& g, const unsigned char* cell, const double* p, double* u, double* v,
+                                 const double* ud, const double* vd, double scale, int use_density);
+void launch_add_buoyancy(cudaStream_t st, int w, int h, const double* dsrc, const double* tsrc, double* v,
+                         double timestep, double gravity, double rho_air, double rho_soot, double t_amb);
+void launch_extrap_fill_mask(cudaStream_t st, const SolidQ& q, unsigned char* state);
+void launch_extrap_sweep(cudaStream_t st, const SolidQ& q, double* src, unsigned char* state, unsigned int* progress);
+void launch_advect_solid(cudaStream_t st, QGeom q, const double* src, double* dst, QGeom qu, const double* u, QGeom qv,
+                         const double* v, const unsigned char* cell, const int* body, const ifl_body* bodies,
+                         double timestep, double hx);
+void launch_fill_value(cudaStream_t st, double* p, size_t n, double v);
+void launch_fill_u8(cudaStream_t st, unsigned char* p, size_t n, unsigned char v);
+void launch_u8_to_double(cudaStream_t st, const unsigned char* a, double* out, size_t n);
+void launch_i32_to_double(cudaStream_t st, const int* a, double* out, size_t n);
 
 /* ---- solver kernels: ifl_solve_kernels.cu ---- */
 int  solve_partials_needed(const SkewGeom& g);

@@ -91,7 +91,7 @@ __device__ __forceinline__ void finish_partials(double blocksum, double* partial
 __global__ void __launch_bounds__(EW_THREADS)
 k_matvec_dot(SkewGeom g, const double* __restrict__ adiag, const double* __restrict__ ax,
              const double* __restrict__ ay, const double* __restrict__ b, double* __restrict__ dst,
-             double* partials, SolveScalars* sc, int dot_mode, int check_done) {
+             double* partials, SolveScalars* sc, int dot_mode, int check_done, const unsigned char* __restrict__ fl) {
     if (check_done && sc->done) return;
     __shared__ double smem8[8];
     __shared__ bool s_last;
@@ -110,8 +110,8 @@ k_matvec_dot(SkewGeom g, const double* __restrict__ adiag, const double* __restr
                 long long j = (l_ < 31) ? (i_ + 33) : (base_ + g.ss + (long long)(t_ - 31) * 32);
                 tv += ay[i_] * b[j];
             }
-            dst[i_] = tv;
-            acc += tv * bc;
+            dst[i_] = tv;                                   /* matrixVectorProduct is never masked (F6:1011) */
+            if (fl == nullptr || fl[i_]) acc += tv * bc;    /* dotProduct: fluid cells only from F6 on (F6:999) */
         }
     IFL_EW_LOOP_END
     if (dot_mode == DOT_NONE) return;
@@ -125,14 +125,14 @@ k_matvec_dot(SkewGeom g, const double* __restrict__ adiag, const double* __restr
 __global__ void __launch_bounds__(EW_THREADS)
 k_update_pr(SkewGeom g, double* __restrict__ p, const double* __restrict__ s, double* __restrict__ r,
             const double* __restrict__ z, double* __restrict__ bnd_f, double* __restrict__ bnd_b,
-            SolveScalars* sc, double tol) {
+            SolveScalars* sc, double tol, const unsigned char* __restrict__ fl) {
     if (sc->done) return;
     __shared__ unsigned s_max[8];
     __shared__ bool s_last;
     const double alpha = sc->alpha, nalpha = sc->neg_alpha;
     unsigned m = 0;
     IFL_EW_LOOP_BEGIN(g)
-        if (ok_) {
+        if (ok_ && (fl == nullptr || fl[i_])) {
             p[i_] = p[i_] + s[i_] * alpha;
             double rv = r[i_] + z[i_] * nalpha;
             r[i_] = rv;
@@ -176,25 +176,28 @@ k_update_pr(SkewGeom g, double* __restrict__ p, const double* __restrict__ s, do
 
 /* s = z + s * beta   (F3:626) */
 __global__ void __launch_bounds__(EW_THREADS)
-k_update_s(SkewGeom g, double* __restrict__ s, const double* __restrict__ z, SolveScalars* sc) {
+k_update_s(SkewGeom g, double* __restrict__ s, const double* __restrict__ z, SolveScalars* sc,
+           const unsigned char* __restrict__ fl) {
     if (sc->done) return;
     const double beta = sc->beta;
     IFL_EW_LOOP_BEGIN(g)
-        if (ok_) s[i_] = z[i_] + s[i_] * beta;
+        if (ok_ && (fl == nullptr || fl[i_])) s[i_] = z[i_] + s[i_] * beta;
     IFL_EW_LOOP_END
 }
 
 /* start of project(): s = z (arraycopy F3:596); maxError = infinityNorm(r) (F3:598) */
 __global__ void __launch_bounds__(EW_THREADS)
 k_init_s(SkewGeom g, double* __restrict__ s, const double* __restrict__ z, const double* __restrict__ r,
-         SolveScalars* sc, double tol) {
+         SolveScalars* sc, double tol, const unsigned char* __restrict__ fl) {
     __shared__ unsigned s_max[8];
     unsigned m = 0;
     IFL_EW_LOOP_BEGIN(g)
         if (ok_) {
-            s[i_] = z[i_];
-            unsigned bits = absf_bits(r[i_]);
-            m = bits > m ? bits : m;
+            s[i_] = z[i_];                                  /* arraycopy: every cell */
+            if (fl == nullptr || fl[i_]) {                  /* infinityNorm: fluid cells only from F6 on (F6:1054) */
+                unsigned bits = absf_bits(r[i_]);
+                m = bits > m ? bits : m;
+            }
         }
     IFL_EW_LOOP_END
 #pragma unroll
@@ -255,13 +258,14 @@ __global__ void k_solve_finish(SolveScalars* sc, int limit) {
 /* Reductions in the reference's serial order (bit-exact mode, small grids / tests):
  * one thread walks the cells lexicographically.  dotProduct F3:532. */
 __global__ void k_dot_sequential(SkewGeom g, const double* __restrict__ a, const double* __restrict__ b,
-                                 SolveScalars* sc, int mode, int check_done) {
+                                 SolveScalars* sc, int mode, int check_done, const unsigned char* __restrict__ fl) {
     if (check_done && sc->done) return;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double result = 0.0;
     for (int y = 0; y < g.h; y++) {
         long long i = skew_index(g, 0, y);
-        for (int x = 0; x < g.w; x++, i += 32) result += a[i] * b[i];
+        for (int x = 0; x < g.w; x++, i += 32)
+            if (fl == nullptr || fl[i]) result += a[i] * b[i];
     }
     apply_dot_result(sc, mode, result);
 }
@@ -403,15 +407,23 @@ static constexpr int SW_PACK = 3 * SW_TILE;         /* packed coefficient block:
  *     backward pack: cx = aPlusX*precon,            cy = aPlusY*precon (own cell),          precon */
 __global__ void __launch_bounds__(EW_THREADS)
 k_precon_coeffs(SkewGeom g, const double* __restrict__ ax, const double* __restrict__ ay,
-                const double* __restrict__ pre, double* __restrict__ pack_f, double* __restrict__ pack_b) {
+                const double* __restrict__ pre, double* __restrict__ pack_f, double* __restrict__ pack_b,
+                const unsigned char* __restrict__ fl) {
     const long long pstrip = (long long)(g.tl / SW_U) * SW_PACK;
     IFL_EW_LOOP_BEGIN(g)
         if (ok_) {
-            const double pr = pre[i_];
-            const double cx = ax[i_] * pr;
-            const double cy = ay[i_] * pr;
             const long long j = (l_ > 0) ? (i_ - 33) : (base_ - g.ss + (long long)(t_ + 31) * 32 + 31);
-            const double cyu = ay[j] * pre[j];
+            double pr = pre[i_];
+            double cx = ax[i_] * pr;
+            double cy = ay[i_] * pr;
+            double cyu = ay[j] * pre[j];
+            if (fl != nullptr) {
+                /* F4+: non-fluid cells are skipped by applyPreconditioner and never used as neighbours
+                 * (F4:783-807).  They are tagged with a NaN precon (the sweep then neither computes nor
+                 * stores them and hands +0.0 to its neighbours) and exact +0.0 products. */
+                if (!fl[j]) cyu = 0.0;
+                if (!fl[i_]) { cx = 0.0; cy = 0.0; pr = __longlong_as_double(0x7ff8000000000b20ll); }
+            }
             const long long o = (long long)k_ * pstrip + (long long)(t_ / SW_U) * SW_PACK + (t_ % SW_U) * 32 + l_;
             pack_f[o] = cx; pack_f[o + SW_TILE] = cyu; pack_f[o + 2 * SW_TILE] = pr;
             pack_b[o] = cx; pack_b[o + SW_TILE] = cy;  pack_b[o + 2 * SW_TILE] = pr;
@@ -421,7 +433,7 @@ k_precon_coeffs(SkewGeom g, const double* __restrict__ ax, const double* __restr
 
 /* SW_U consecutive steps of one strip.  tile_a: staged src block [SW_U][32]; tile_c: staged
  * coefficient pack [3][SW_U][32]; tile_r: staged rr block (fused dot) */
-template <int DIR, bool WITH_DOT, bool CHECKED, bool FASTFEED>
+template <int DIR, bool WITH_DOT, bool CHECKED, bool FASTFEED, bool MASKED>
 __device__ __forceinline__ void sweep_steps(const double* tile_a, const double* tile_c, const double* tile_r,
                                             const int t0, const int lane, const int w, const bool yok,
                                             double* pdst, double* pbnd, RotFeed<SW_U>& feed,
@@ -450,16 +462,18 @@ __device__ __forceinline__ void sweep_steps(const double* tile_a, const double* 
             v = v - cx * dprev;          /* (aPlusX[i]*precon[i]) * dst[i+1]       F3:514 */
             v = v - cyv * dn;            /* (aPlusY[i]*precon[i]) * dst[i+w]       F3:517 */
         }
-        const double d = v * pr;
+        double d = v * pr;
+        const bool fluid = MASKED ? (pr == pr) : true;      /* NaN precon tags a non-fluid cell (k_precon_coeffs) */
+        if (MASKED) d = fluid ? d : 0.0;                     /* skipped cell: dst stays, neighbours see +0.0 */
         if (CHECKED) {
             const int x = t0 + DIR * j - lane;
             const bool active = yok && x >= 0 && x < w;
-            if (active) pdst[DIR * j * 32] = d;
+            if (active && fluid) pdst[DIR * j * 32] = d;
             if (active && is_out) pbnd[DIR * j] = d;
         } else {
             /* interior block: only rows y >= h are inactive; they hold +0.0, and storing +0.0 into
              * their (zero) padding cells keeps the padding zero -- no branch needed */
-            pdst[DIR * j * 32] = d;
+            if (fluid) pdst[DIR * j * 32] = d;
             if (is_out) pbnd[DIR * j] = d;
         }
         /* inactive lanes hold +0.0 and rr is zero in the padding: adding them is exact */
@@ -477,7 +491,7 @@ __device__ __forceinline__ void sweep_steps(const double* tile_a, const double* 
  * all-zero strip before and after), and inactive lanes provably carry +0.0, so the guarded
  * products are +0.0 and `v - (+0.0)` returns v bit-for-bit (also for v = -0.0).  For the
  * backward sweep aPlusX(w-1,y) and aPlusY(x,h-1) are +0.0 by construction (F3:447,454). */
-template <int DIR, bool WITH_DOT>
+template <int DIR, bool WITH_DOT, bool MASKED>
 __global__ void __launch_bounds__(WF_WARPS * 32)
 k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restrict__ pack,
                const double* __restrict__ rr, double* bnd, double* stripdot,
@@ -549,10 +563,10 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
         const double* tile_c = tile_a + SW_TILE;
         const double* tile_r = tile_a + SW_TILE + SW_PACK;
         if (interior) {
-            if (fast_feed) sweep_steps<DIR, WITH_DOT, false, true>(tile_a, tile_c, tile_r, t0, lane, w, yok, pdst, pbnd, feed, dprev, cxprev, acc);
-            else sweep_steps<DIR, WITH_DOT, false, false>(tile_a, tile_c, tile_r, t0, lane, w, yok, pdst, pbnd, feed, dprev, cxprev, acc);
+            if (fast_feed) sweep_steps<DIR, WITH_DOT, false, true, MASKED>(tile_a, tile_c, tile_r, t0, lane, w, yok, pdst, pbnd, feed, dprev, cxprev, acc);
+            else sweep_steps<DIR, WITH_DOT, false, false, MASKED>(tile_a, tile_c, tile_r, t0, lane, w, yok, pdst, pbnd, feed, dprev, cxprev, acc);
         } else {
-            sweep_steps<DIR, WITH_DOT, true, false>(tile_a, tile_c, tile_r, t0, lane, w, yok, pdst, pbnd, feed, dprev, cxprev, acc);
+            sweep_steps<DIR, WITH_DOT, true, false, MASKED>(tile_a, tile_c, tile_r, t0, lane, w, yok, pdst, pbnd, feed, dprev, cxprev, acc);
         }
         pdst += DIR * U * 32;
         pbnd += DIR * U;
@@ -583,11 +597,13 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     }
 }
 
-/* buildPreconditioner F3:464 -- MIC(0) with tau/sigma, lexicographic recurrence on precon */
+/* buildPreconditioner F3:464 / masked F4:744 (=F5:858, F6:918, F7:951) -- MIC(0) with tau/sigma,
+ * lexicographic recurrence on precon.  fl = skewed fluid flags (F4+: non-fluid cells are skipped and
+ * never used as neighbours) or nullptr. */
 __global__ void __launch_bounds__(WF_WARPS * 32)
 k_build_precon(SkewGeom g, const double* __restrict__ adiag, const double* __restrict__ ax,
                const double* __restrict__ ay, double* pre, double* bnd, SolveScalars* sc,
-               double tau, double sigma) {
+               double tau, double sigma, const unsigned char* __restrict__ fl) {
     constexpr int U = WF_U;
     const int slot = claim_slot(&sc->ticket_f, g.nstrips);
     if (slot < 0) return;
@@ -601,8 +617,10 @@ k_build_precon(SkewGeom g, const double* __restrict__ adiag, const double* __res
     long long upbase = base - 33;
     if (lane == 0) upbase = (long long)(k - 1) * g.ss + 31LL * 32 + 31;
     const bool has_up = y > 0;
+    const bool masked = fl != nullptr;
 
     double AD[U], AX[U], AY[U], AXU[U], AYU[U];
+    unsigned char FL[U], FLU[U];
 #pragma unroll
     for (int j = 0; j < U; j++) {
         int t = j;
@@ -612,6 +630,8 @@ k_build_precon(SkewGeom g, const double* __restrict__ adiag, const double* __res
         bool okup = has_up && (t - lane) >= 0 && (t - lane) < w;
         AXU[j] = okup ? ax[upbase + (long long)t * 32] : 0.0;
         AYU[j] = okup ? ay[upbase + (long long)t * 32] : 0.0;
+        FL[j] = masked ? fl[base + (long long)t * 32] : 1;
+        FLU[j] = (masked && okup) ? fl[upbase + (long long)t * 32] : 1;
     }
     EdgeFeed<U> feed;
     feed.init(k > 0 ? bnd + (long long)(k - 1) * w : nullptr, w);
@@ -619,6 +639,7 @@ k_build_precon(SkewGeom g, const double* __restrict__ adiag, const double* __res
     feed.advance();
 
     double pprev = 0.0, axprev = 0.0, ayprev = 0.0;
+    bool flprev = false;
     for (int b = 0; b < nblk; b++) {
         const int t0 = b * U;
         feed.prefetch(t0 + U + lane, lane);
@@ -630,13 +651,14 @@ k_build_precon(SkewGeom g, const double* __restrict__ adiag, const double* __res
             const double bv = feed.get(j, lane);
             if (lane == 0) pu = bv;
             const double ad = AD[j];
+            const bool fself = FL[j] != 0;
             double e = ad;
-            if (x > 0) {
+            if (x > 0 && flprev) {
                 double px = axprev * pprev;
                 double py = ayprev * pprev;
                 e -= (px * px + tau * px * py);
             }
-            if (y > 0) {
+            if (y > 0 && FLU[j]) {
                 double px = AXU[j] * pu;
                 double py = AYU[j] * pu;
                 e -= (py * py + tau * px * py);
@@ -645,10 +667,10 @@ k_build_precon(SkewGeom g, const double* __restrict__ adiag, const double* __res
             const double pc = 1.0 / sqrt(e);
             const bool active = yok && x >= 0 && x < w;
             if (active) {
-                pre[base + (long long)t * 32] = pc;
-                if (lane == 31) bnd[(long long)k * w + x] = pc;
+                if (fself) pre[base + (long long)t * 32] = pc;
+                if (lane == 31) bnd[(long long)k * w + x] = fself ? pc : 0.0;   /* flag-in-data: always publish */
             }
-            pprev = pc; axprev = AX[j]; ayprev = AY[j];
+            pprev = pc; axprev = AX[j]; ayprev = AY[j]; flprev = fself;
             const int tn = t + U;
             if (tn < g.tl) {
                 AD[j] = adiag[base + (long long)tn * 32];
@@ -657,6 +679,8 @@ k_build_precon(SkewGeom g, const double* __restrict__ adiag, const double* __res
                 bool okup = has_up && (tn - lane) >= 0 && (tn - lane) < w;
                 AXU[j] = okup ? ax[upbase + (long long)tn * 32] : 0.0;
                 AYU[j] = okup ? ay[upbase + (long long)tn * 32] : 0.0;
+                FL[j] = masked ? fl[base + (long long)tn * 32] : 1;
+                FLU[j] = (masked && okup) ? fl[upbase + (long long)tn * 32] : 1;
             }
         }
         feed.advance();
@@ -779,8 +803,8 @@ static inline int rearm_blocks(const SkewGeom& g) {
 void launch_build_precon(SolveCtx& c) {
     k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
     k_build_precon<<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.precon,
-                                                                  c.bnd_f, c.sc, c.mic_tau, c.mic_sigma);
-    k_precon_coeffs<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.aplusx, c.aplusy, c.precon, c.pack_f, c.pack_b);
+                                                                  c.bnd_f, c.sc, c.mic_tau, c.mic_sigma, c.fl);
+    k_precon_coeffs<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.aplusx, c.aplusy, c.precon, c.pack_f, c.pack_b, c.fl);
     count(c, 3);
 }
 
@@ -788,34 +812,39 @@ static size_t sweep_smem(bool with_dot) {
     size_t stage = ((with_dot ? 2 : 1) * SW_TILE + SW_PACK) * sizeof(double);
     return (size_t)WF_WARPS * SW_STAGES * stage + (size_t)WF_WARPS * SW_STAGES * 8;
 }
-static void sweep_attrs_once() {
-    static bool done = false;
-    if (done) return;
-    cudaFuncSetAttribute(k_precon_sweep<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem(false));
-    cudaFuncSetAttribute(k_precon_sweep<-1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem(false));
-    cudaFuncSetAttribute(k_precon_sweep<-1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem(true));
-    done = true;
+template <int DIR, bool WITH_DOT, bool MASKED>
+static void launch_sweep(SolveCtx& c, const double* src, double* dst, const double* pack, const double* rr, double* bnd,
+                         int dot_mode, int check_done, long long* trace) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_precon_sweep<DIR, WITH_DOT, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sweep_smem(WITH_DOT));
+        attr_done = true;
+    }
+    k_precon_sweep<DIR, WITH_DOT, MASKED><<<wf_blocks(c.g), WF_WARPS * 32, sweep_smem(WITH_DOT), c.stream>>>(
+        c.g, src, dst, pack, rr, bnd, c.stripdot, c.sc, dot_mode, check_done, trace);
 }
 
 /* dst = M^-1 src: forward then backward sweep.  Boundary rows must be armed. */
 static inline void prof_mark(SolveCtx& c, int slot, int e);
 static void enqueue_precon(SolveCtx& c, const double* src, double* dst, int dot_mode, int check_done, int ps = -1) {
-    sweep_attrs_once();
-    k_precon_sweep<1, false><<<wf_blocks(c.g), WF_WARPS * 32, sweep_smem(false), c.stream>>>(
-        c.g, src, dst, c.pack_f, nullptr, c.bnd_f, c.stripdot, c.sc, DOT_NONE, check_done, c.trace);
+    const bool masked = c.fl != nullptr;
+    if (masked) launch_sweep<1, false, true>(c, src, dst, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
+    else        launch_sweep<1, false, false>(c, src, dst, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
     prof_mark(c, ps, 3);
     int fused_mode = c.sequential ? DOT_NONE : dot_mode;
     long long* tr2 = c.trace ? c.trace + 8 * c.g.nstrips : nullptr;
-    if (dot_mode != DOT_NONE)
-        k_precon_sweep<-1, true><<<wf_blocks(c.g), WF_WARPS * 32, sweep_smem(true), c.stream>>>(
-            c.g, dst, dst, c.pack_b, src, c.bnd_b, c.stripdot, c.sc, fused_mode, check_done, tr2);
-    else
-        k_precon_sweep<-1, false><<<wf_blocks(c.g), WF_WARPS * 32, sweep_smem(false), c.stream>>>(
-            c.g, dst, dst, c.pack_b, nullptr, c.bnd_b, c.stripdot, c.sc, DOT_NONE, check_done, tr2);
+    if (dot_mode != DOT_NONE) {
+        if (masked) launch_sweep<-1, true, true>(c, dst, dst, c.pack_b, src, c.bnd_b, fused_mode, check_done, tr2);
+        else        launch_sweep<-1, true, false>(c, dst, dst, c.pack_b, src, c.bnd_b, fused_mode, check_done, tr2);
+    } else {
+        if (masked) launch_sweep<-1, false, true>(c, dst, dst, c.pack_b, nullptr, c.bnd_b, DOT_NONE, check_done, tr2);
+        else        launch_sweep<-1, false, false>(c, dst, dst, c.pack_b, nullptr, c.bnd_b, DOT_NONE, check_done, tr2);
+    }
     prof_mark(c, ps, 4);
     count(c, 2);
     if (c.sequential && dot_mode != DOT_NONE) {
-        k_dot_sequential<<<1, 32, 0, c.stream>>>(c.g, dst, src, c.sc, dot_mode, check_done);
+        k_dot_sequential<<<1, 32, 0, c.stream>>>(c.g, dst, src, c.sc, dot_mode, check_done, c.mask_vector_ops ? c.fl : nullptr);
         count(c);
     }
 }
@@ -828,7 +857,7 @@ void launch_apply_precon(SolveCtx& c, const double* src, double* dst, int /*with
 
 void launch_matvec(SolveCtx& c, const double* b, double* dst) {
     k_matvec_dot<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, b, dst,
-                                                           c.partials, c.sc, DOT_NONE, 0);
+                                                           c.partials, c.sc, DOT_NONE, 0, nullptr);
     count(c);
 }
 
@@ -838,7 +867,7 @@ void pcg_enqueue_init(SolveCtx& c) {
     k_solve_reset<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
     count(c);
     enqueue_precon(c, c.r, c.z, DOT_SIGMA_INIT, 0);
-    k_init_s<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.r, c.sc, c.tolerance);
+    k_init_s<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.r, c.sc, c.tolerance, c.mask_vector_ops ? c.fl : nullptr);
     count(c);
 }
 
@@ -861,21 +890,22 @@ static inline void prof_mark(SolveCtx& c, int slot, int e) {
 /* n iterations of the loop body F3:603-628; every kernel returns at once after convergence */
 void pcg_enqueue_iterations(SolveCtx& c, int n) {
     dim3 eg = ew_grid(c.g);
+    const unsigned char* mfl = c.mask_vector_ops ? c.fl : nullptr;
     for (int it = 0; it < n; it++) {
         const int ps = (it == 0 && !c.sequential) ? prof_begin(c, 0) : -1;
         k_matvec_dot<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.s, c.z, c.partials,
-                                                      c.sc, c.sequential ? DOT_NONE : DOT_ZS, 1);
+                                                      c.sc, c.sequential ? DOT_NONE : DOT_ZS, 1, mfl);
         count(c);
         prof_mark(c, ps, 1);
         if (c.sequential) {
-            k_dot_sequential<<<1, 32, 0, c.stream>>>(c.g, c.z, c.s, c.sc, DOT_ZS, 1);
+            k_dot_sequential<<<1, 32, 0, c.stream>>>(c.g, c.z, c.s, c.sc, DOT_ZS, 1, mfl);
             count(c);
         }
-        k_update_pr<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.p, c.s, c.r, c.z, c.bnd_f, c.bnd_b, c.sc, c.tolerance);
+        k_update_pr<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.p, c.s, c.r, c.z, c.bnd_f, c.bnd_b, c.sc, c.tolerance, mfl);
         count(c);
         prof_mark(c, ps, 2);
         enqueue_precon(c, c.r, c.z, DOT_SIGMA_NEW, 1, ps);
-        k_update_s<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.sc);
+        k_update_s<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.sc, mfl);
         count(c);
         prof_mark(c, ps, 5);
     }

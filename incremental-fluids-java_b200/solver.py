@@ -114,6 +114,11 @@ class FluidSolver:
         if bodies is not None:
             self.set_bodies(bodies)
 
+    def sync_bodies(self):
+        """Re-send the shared `bodies` list after main() advanced it (body.update(dt), F4:98)."""
+        if self._bodies is not None:
+            self.set_bodies(self._bodies)
+
     # -- lifetime -------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h_", None) and self._h_.value:

@@ -87,21 +87,132 @@ inline double cubicPulse(double x) {
     return 1.0 - x * x * (3.0 - 2.0 * x);
 }
 
-enum { CELL_FLUID = 0, CELL_SOLID = 1, CELL_EMPTY = 2 };
-
 struct Vec2 { double x, y; };
+
+enum { CELL_FLUID = 0, CELL_SOLID = 1, CELL_EMPTY = 2, CELL_NULL = 3 /* F4: _cell entries stay null until fillSolidFields runs (F4:183) */ };
+
+/* ---- solidBodies/A_SolidBody.java, SolidBox.java, SolidSphere.java --------------------------------
+ * cos(theta)/sin(theta) come precomputed in ifl_body (see include/incfluid_b200.h): the reference
+ * calls Math.cos/sin inside rotate() (A_SolidBody.java:65-71), which is not bit-specified. */
+struct Body {
+    ifl_body b;
+    /* A_SolidBody.rotate(x, y, phi) with phi = +theta (dir=+1) or -theta (dir=-1): cos is even, sin is odd */
+    Vec2 rotate(double x, double y, int dir) const {
+        double c = b.cos_theta, sn = dir > 0 ? b.sin_theta : -b.sin_theta;
+        return {c * x + sn * y, -sn * x + c * y};
+    }
+    static double nsgn(double v) {                     /* SolidBox.java:54-60: signum, 0 for 0 */
+        double r = jsignum(v);
+        if (std::fabs(r) == 0) return 0;
+        return r;
+    }
+    double distance(double x, double y) const {
+        if (b.type == IFL_BODY_BOX) {                  /* SolidBox.java:80 */
+            x -= b.pos_x; y -= b.pos_y;
+            Vec2 r = rotate(x, y, -1);
+            double dx = std::fabs(r.x) - b.scale_x * 0.5;
+            double dy = std::fabs(r.y) - b.scale_y * 0.5;
+            if (dx >= 0.0 || dy >= 0.0) return length(jmax(dx, 0.0), jmax(dy, 0.0));
+            return jmax(dx, dy);
+        }
+        return length(x - b.pos_x, y - b.pos_y) - b.scale_x * 0.5;     /* SolidSphere.java:62 */
+    }
+    Vec2 closestSurfacePoint(double x, double y) const {
+        if (b.type == IFL_BODY_BOX) {                  /* SolidBox.java:95 */
+            x -= b.pos_x; y -= b.pos_y;
+            Vec2 r = rotate(x, y, -1);
+            x = r.x; y = r.y;
+            double dx = std::fabs(x) - b.scale_x * 0.5;
+            double dy = std::fabs(y) - b.scale_y * 0.5;
+            if (dx > dy) x = nsgn(x) * 0.5 * b.scale_x;
+            else y = nsgn(y) * 0.5 * b.scale_y;
+            r = rotate(x, y, +1);
+            return {r.x + b.pos_x, r.y + b.pos_y};
+        }
+        /* SolidSphere.java:67 via globalToLocal / localToGlobal (A_SolidBody.java:121,138) */
+        x -= b.pos_x; y -= b.pos_y;
+        Vec2 r = rotate(x, y, -1);
+        x = r.x / b.scale_x; y = r.y / b.scale_y;
+        double rr = length(x, y);
+        if (rr < 1e-4) { x = 0.5; y = 0.0; }
+        else { x /= 2.0 * rr; y /= 2.0 * rr; }
+        x *= b.scale_x; y *= b.scale_y;
+        r = rotate(x, y, +1);
+        return {r.x + b.pos_x, r.y + b.pos_y};
+    }
+    Vec2 distanceNormal(double x, double y) const {
+        if (b.type == IFL_BODY_BOX) {                  /* SolidBox.java:118 */
+            x -= b.pos_x; y -= b.pos_y;
+            Vec2 r = rotate(x, y, -1);
+            x = r.x; y = r.y;
+            double nx, ny;
+            if (std::fabs(x) - b.scale_x * 0.5 > std::fabs(y) - b.scale_y * 0.5) { nx = nsgn(x); ny = 0.0; }
+            else { nx = 0.0; ny = nsgn(y); }
+            return rotate(nx, ny, +1);
+        }
+        x -= b.pos_x; y -= b.pos_y;                    /* SolidSphere.java:85 */
+        double rr = length(x, y);
+        if (rr < 1e-4) return {1.0, 0.0};
+        return {x / rr, y / rr};
+    }
+    double velocityX(double /*x*/, double y) const { return (b.pos_y - y) * b.vel_theta + b.vel_x; }   /* A_SolidBody.java:194 */
+    double velocityY(double x, double /*y*/) const { return (x - b.pos_x) * b.vel_theta + b.vel_y; }   /* A_SolidBody.java:205 */
+};
+
+/* F5:135 / F5:144 / F5:165 (identical in F6, F7, F8) */
+inline double triangleOccupancy(double out1, double in, double out2) { return 0.5 * in * in / ((out1 - in) * (out2 - in)); }
+inline double trapezoidOccupancy(double out1, double out2, double in1, double in2) {
+    return 0.5 * (-in1 / (out1 - in1) - in2 / (out2 - in2));
+}
+inline double occupancy(double d11, double d12, double d21, double d22) {
+    double ds[4] = {d11, d12, d22, d21};
+    int b = 0;
+    for (int i = 3; i >= 0; i--) b = (b << 1) | (ds[i] < 0.0 ? 1 : 0);
+    switch (b) {
+        case 0x0: return 0.0;
+        case 0x1: return triangleOccupancy(d21, d11, d12);
+        case 0x2: return triangleOccupancy(d11, d12, d22);
+        case 0x4: return triangleOccupancy(d12, d22, d21);
+        case 0x8: return triangleOccupancy(d22, d21, d11);
+        case 0xE: return 1.0 - triangleOccupancy(-d21, -d11, -d12);
+        case 0xD: return 1.0 - triangleOccupancy(-d11, -d12, -d22);
+        case 0xB: return 1.0 - triangleOccupancy(-d12, -d22, -d21);
+        case 0x7: return 1.0 - triangleOccupancy(-d22, -d21, -d11);
+        case 0x3: return trapezoidOccupancy(d21, d22, d11, d12);
+        case 0x6: return trapezoidOccupancy(d11, d21, d12, d22);
+        case 0x9: return trapezoidOccupancy(d12, d22, d11, d21);
+        case 0xC: return trapezoidOccupancy(d11, d12, d21, d22);
+        case 0x5: return triangleOccupancy(d11, d12, d22) + triangleOccupancy(d22, d21, d11);
+        case 0xA: return triangleOccupancy(d21, d11, d12) + triangleOccupancy(d12, d22, d21);
+        case 0xF: return 1.0;
+    }
+    return 0.0;
+}
+
 
 /* ---- FluidQuantity (F1:105, F3:114, F4:126, F5:234, F7:225) ----------------------------- */
 struct Quantity {
     std::vector<double> src, dst;
+    std::vector<double> phi, volume, normalX, normalY;     /* F4:138-153, F5:241-266 */
+    std::vector<int> cell, body, mask;
     int w = 0, h = 0;
     double ox = 0, oy = 0, hx = 0;
 
-    void init(int w_, int h_, double ox_, double oy_, double hx_) {
+    void init(int w_, int h_, double ox_, double oy_, double hx_, int variant = 0) {
         w = w_; h = h_; ox = ox_; oy = oy_; hx = hx_;
         src.assign((size_t)w * h, 0.0);
         dst.assign((size_t)w * h, 0.0);
+        if (variant >= IFL_F4_SOLID_BOUNDARIES) {
+            size_t n = (size_t)w * h;
+            phi.assign((size_t)(w + 1) * (h + 1), 0.0);
+            /* F5:313-316 initialises _cell = FLUID, _volume = 1; F4:183 leaves _cell null */
+            volume.assign(n, 1.0);
+            normalX.assign(n, 0.0); normalY.assign(n, 0.0);
+            cell.assign(n, variant == IFL_F4_SOLID_BOUNDARIES ? CELL_NULL : CELL_FLUID);
+            body.assign(n, 0); mask.assign(n, 0);
+        }
     }
+    double vol(int x, int y) const { return volume[(size_t)x + (size_t)y * w]; }
     void swap() { src.swap(dst); }                      /* F1:143 */
     double getSrc(int x, int y) const { return src[(size_t)x + (size_t)y * w]; }
     void setSrc(int x, int y, double v) { src[(size_t)x + (size_t)y * w] = v; }
@@ -180,6 +291,121 @@ struct Quantity {
         }
     }
 
+    /* F4:249 (=F5:383, F7:405) */
+    Vec2 backProject(double x, double y, const std::vector<Body>& bodies) const {
+        int rx = jmini(jmaxi(jint(x - ox), 0), w - 1);
+        int ry = jmini(jmaxi(jint(y - oy), 0), h - 1);
+        size_t c = (size_t)rx + (size_t)ry * w;
+        if (cell[c] != CELL_FLUID) {
+            x = (x - ox) * hx;
+            y = (y - oy) * hx;
+            Vec2 r = bodies[body[c]].closestSurfacePoint(x, y);
+            x = r.x / hx + ox;
+            y = r.y / hx + oy;
+        }
+        return {x, y};
+    }
+
+    /* F4:268 (=F5:402, F6:417, F7:423): only CELL_FLUID samples are written, the rest keeps stale _dst */
+    void advectMasked(double timestep, const Quantity& u, const Quantity& v, const std::vector<Body>& bodies) {
+        size_t idx = 0;
+        for (int iy = 0; iy < h; iy++) {
+            for (int ix = 0; ix < w; ix++, idx++) {
+                if (cell[idx] == CELL_FLUID) {
+                    double x = ix + ox;
+                    double y = iy + oy;
+                    Vec2 r = RungeKutta3(x, y, timestep, u, v);
+                    r = backProject(r.x, r.y, bodies);
+                    dst[idx] = cerpGrid(r.x, r.y);
+                }
+            }
+        }
+    }
+
+    /* F4:329 (voxelised) / F5:463 (=F6:478, F7:484): phi, closest body, volume, normal, cell type */
+    void fillSolidFields(int variant, const std::vector<Body>& bodies) {
+        if (bodies.empty()) return;
+        if (variant >= IFL_F5_CURVED_BOUNDARIES) {
+            size_t idx = 0;
+            for (int iy = 0; iy <= h; iy++) {
+                for (int ix = 0; ix <= w; ix++, idx++) {
+                    double x = (ix + ox - 0.5) * hx;
+                    double y = (iy + oy - 0.5) * hx;
+                    phi[idx] = bodies[0].distance(x, y);
+                    for (size_t i = 1; i < bodies.size(); i++) phi[idx] = jmin(phi[idx], bodies[i].distance(x, y));
+                }
+            }
+        }
+        size_t idx = 0;
+        for (int iy = 0; iy < h; iy++) {
+            for (int ix = 0; ix < w; ix++, idx++) {
+                double x = (ix + ox) * hx;
+                double y = (iy + oy) * hx;
+                body[idx] = 0;
+                double d = bodies[0].distance(x, y);
+                for (size_t i = 1; i < bodies.size(); i++) {
+                    double id = bodies[i].distance(x, y);
+                    if (id < d) { body[idx] = (int)i; d = id; }
+                }
+                if (variant == IFL_F4_SOLID_BOUNDARIES) {
+                    cell[idx] = d < 0.0 ? CELL_SOLID : CELL_FLUID;
+                } else {
+                    size_t idxp = (size_t)ix + (size_t)iy * (w + 1);
+                    volume[idx] = 1.0 - occupancy(phi[idxp], phi[idxp + 1], phi[idxp + w + 1], phi[idxp + w + 2]);
+                    if (volume[idx] < 0.01) volume[idx] = 0.0;
+                }
+                Vec2 n = bodies[body[idx]].distanceNormal(x, y);
+                normalX[idx] = n.x;
+                normalY[idx] = n.y;
+                if (variant != IFL_F4_SOLID_BOUNDARIES) cell[idx] = volume[idx] == 0.0 ? CELL_SOLID : CELL_FLUID;
+            }
+        }
+    }
+
+    /* F4:396 */
+    void fillSolidMask() {
+        for (int y = 1; y < h - 1; y++) {
+            for (int x = 1; x < w - 1; x++) {
+                size_t idx = (size_t)x + (size_t)y * w;
+                if (cell[idx] == CELL_FLUID) continue;
+                double nx = normalX[idx], ny = normalY[idx];
+                mask[idx] = 0;
+                if (nx != 0.0 && cell[idx + (int)jsignum(nx)] != CELL_FLUID) mask[idx] |= 1;
+                if (ny != 0.0 && cell[idx + (int)jsignum(ny) * w] != CELL_FLUID) mask[idx] |= 2;
+            }
+        }
+    }
+    /* F4:426: weights are abs((float) n) */
+    double extrapolateNormal(size_t idx) const {
+        double nx = normalX[idx], ny = normalY[idx];
+        double srcX = src[idx + (int)jsignum(nx)];
+        double srcY = src[idx + (int)jsignum(ny) * w];
+        return (jabsf(nx) * srcX + jabsf(ny) * srcY) / (jabsf(nx) + jabsf(ny));
+    }
+    void freeNeighbour(size_t idx, std::vector<size_t>& border, int m) {   /* F4:441 */
+        mask[idx] &= ~m;
+        if (cell[idx] != CELL_FLUID && mask[idx] == 0) border.push_back(idx);
+    }
+    /* F4:452 (=F5:616, F6:632, F7:632): dependency ordered fill of solid cells, LIFO stack */
+    void extrapolate() {
+        fillSolidMask();
+        std::vector<size_t> border;
+        for (int y = 1; y < h - 1; y++)
+            for (int x = 1; x < w - 1; x++) {
+                size_t idx = (size_t)x + (size_t)y * w;
+                if (cell[idx] != CELL_FLUID && mask[idx] == 0) border.push_back(idx);
+            }
+        while (!border.empty()) {
+            size_t idx = border.back();
+            border.pop_back();
+            src[idx] = extrapolateNormal(idx);
+            if (normalX[idx - 1] > 0.0) freeNeighbour(idx - 1, border, 1);
+            if (normalX[idx + 1] < 0.0) freeNeighbour(idx + 1, border, 1);
+            if (normalY[idx - w] > 0.0) freeNeighbour(idx - w, border, 2);
+            if (normalY[idx + w] < 0.0) freeNeighbour(idx + w, border, 2);
+        }
+    }
+
     /* F1:202 (hard rectangle) / F2:230 (=F3:232, F4:306, F5:440, F7:461, F8:383) smooth.
      * NOTE the inner loop bound is min(ix1, _h) -- _h, not _w -- in every copy. */
     void addInflow(int variant, double x0, double y0, double x1, double y1, double v) {
@@ -210,14 +436,22 @@ struct Solver {
     double hx, density;
     Quantity d, t, u, v;
     std::vector<double> r, p, z, s, precon, aDiag, aPlusX, aPlusY;
+    std::vector<double> uDensity, vDensity;                            /* F7:757-758 */
+    std::vector<Body> bodies;
     ifl_step_status st;
 
     explicit Solver(const ifl_config& c) : cfg(c) {
         variant = c.variant; w = c.w; h = c.h; density = c.density;
         hx = 1.0 / jmini(w, h);                                       /* F1:266 */
-        d.init(w, h, 0.5, 0.5, hx);                                   /* F1:268 */
-        u.init(w + 1, h, 0.0, 0.5, hx);                               /* F1:269 */
-        v.init(w, h + 1, 0.5, 0.0, hx);                               /* F1:270 */
+        d.init(w, h, 0.5, 0.5, hx, variant);                          /* F1:268 */
+        u.init(w + 1, h, 0.0, 0.5, hx, variant);                      /* F1:269 */
+        v.init(w, h + 1, 0.5, 0.0, hx, variant);                      /* F1:270 */
+        if (variant >= IFL_F6_HEAT) {
+            t.init(w, h, 0.5, 0.5, hx, variant);                      /* F6:792 */
+            std::fill(t.src.begin(), t.src.end(), cfg.t_ambient);     /* F6:797-799 */
+            uDensity.assign((size_t)(w + 1) * h, 0.0);
+            vDensity.assign((size_t)w * (h + 1), 0.0);
+        }
         size_t n = (size_t)w * h;
         r.assign(n, 0.0); p.assign(n, 0.0);
         z.assign(n, 0.0); s.assign(n, 0.0);
@@ -410,20 +644,297 @@ struct Solver {
         for (int x = 0; x < w; x++) { v.setSrc(x, 0, 0.0); v.setSrc(x, h, 0.0); }
     }
 
+    /* ================= F4-F7: solid boundaries, curved boundaries, heat, variable density ============ */
+    bool masksVectorOps() const { return variant >= IFL_F6_HEAT; }     /* F6:999-1064 vs F4:825-878 */
+    bool fluid(size_t i) const { return d.cell[i] == CELL_FLUID; }
+
+    /* F4:693 (masked) / F5:785 (=F6:804, F7:813) volume weighted with body velocity terms */
+    void buildRhsSolid() {
+        double scale = 1.0 / hx;
+        size_t idx = 0;
+        for (int y = 0; y < h; y++) {
+            for (int x = 0; x < w; x++, idx++) {
+                if (!fluid(idx)) { r[idx] = 0.0; continue; }
+                if (variant == IFL_F4_SOLID_BOUNDARIES) {
+                    r[idx] = -scale * (u.getSrc(x + 1, y) - u.getSrc(x, y) + v.getSrc(x, y + 1) - v.getSrc(x, y));
+                    continue;
+                }
+                r[idx] = -scale * (u.vol(x + 1, y) * u.getSrc(x + 1, y) - u.vol(x, y) * u.getSrc(x, y)
+                                   + v.vol(x, y + 1) * v.getSrc(x, y + 1) - v.vol(x, y) * v.getSrc(x, y));
+                double vol = d.vol(x, y);
+                if (bodies.empty()) continue;
+                if (x > 0)     r[idx] -= (u.vol(x, y) - vol) * bodies[d.body[idx - 1]].velocityX(x * hx, (y + 0.5) * hx);
+                if (y > 0)     r[idx] -= (v.vol(x, y) - vol) * bodies[d.body[idx - w]].velocityY((x + 0.5) * hx, y * hx);
+                if (x < w - 1) r[idx] += (u.vol(x + 1, y) - vol) * bodies[d.body[idx + 1]].velocityX((x + 1.0) * hx, (y + 0.5) * hx);
+                if (y < h - 1) r[idx] += (v.vol(x, y + 1) - vol) * bodies[d.body[idx + w]].velocityY((x + 0.5) * hx, (y + 1.0) * hx);
+            }
+        }
+    }
+
+    /* F7:854 */
+    void computeDensities() {
+        double alpha = (cfg.density_soot - density) / density;
+        std::fill(uDensity.begin(), uDensity.end(), 0.0);
+        std::fill(vDensity.begin(), vDensity.end(), 0.0);
+        for (int y = 0; y < h; y++) {
+            for (int x = 0; x < w; x++) {
+                double dens = density * cfg.t_ambient / t.getSrc(x, y) * (1.0 + alpha * d.getSrc(x, y));
+                dens = jmax(dens, 0.05 * density);
+                uDensity[(size_t)x + (size_t)y * (w + 1)] += 0.5 * dens;
+                vDensity[(size_t)x + (size_t)y * w] += 0.5 * dens;
+                uDensity[(size_t)(x + 1) + (size_t)y * (w + 1)] += 0.5 * dens;
+                vDensity[(size_t)x + (size_t)(y + 1) * w] += 0.5 * dens;
+            }
+        }
+    }
+
+    /* F4:713 (scale) / F5:825 (=F6:844; scale*volume) / F7:877 (scale*volume/density; the y factor indexes
+     * _vDensity with _u.I(x, y+1), i.e. stride w+1 -- kept) */
+    void buildPressureMatrixSolid(double timestep) {
+        double scale = variant >= IFL_F7_VARIABLE_DENSITY ? timestep / (hx * hx) : timestep / (density * hx * hx);
+        std::fill(aDiag.begin(), aDiag.end(), 0.0);
+        std::fill(aPlusX.begin(), aPlusX.end(), 0.0);
+        std::fill(aPlusY.begin(), aPlusY.end(), 0.0);
+        size_t idx = 0;
+        for (int y = 0; y < h; y++) {
+            for (int x = 0; x < w; x++, idx++) {
+                if (!fluid(idx)) continue;
+                if (x < w - 1 && fluid(idx + 1)) {
+                    double factor = scale;
+                    if (variant >= IFL_F7_VARIABLE_DENSITY) factor = scale * u.vol(x + 1, y) / uDensity[(size_t)(x + 1) + (size_t)y * (w + 1)];
+                    else if (variant >= IFL_F5_CURVED_BOUNDARIES) factor = scale * u.vol(x + 1, y);
+                    aDiag[idx] += factor; aDiag[idx + 1] += factor; aPlusX[idx] = -factor;
+                }
+                if (y < h - 1 && fluid(idx + w)) {
+                    double factor = scale;
+                    if (variant >= IFL_F7_VARIABLE_DENSITY) factor = scale * v.vol(x, y + 1) / vDensity[(size_t)x + (size_t)(y + 1) * (w + 1)];
+                    else if (variant >= IFL_F5_CURVED_BOUNDARIES) factor = scale * v.vol(x, y + 1);
+                    aDiag[idx] += factor; aDiag[idx + w] += factor; aPlusY[idx] = -factor;
+                }
+            }
+        }
+    }
+
+    /* F6:880 (=F7:913) */
+    void buildHeatDiffusionMatrix(double timestep) {
+        std::fill(aDiag.begin(), aDiag.end(), 1.0);
+        std::fill(aPlusX.begin(), aPlusX.end(), 0.0);
+        std::fill(aPlusY.begin(), aPlusY.end(), 0.0);
+        double scale = cfg.diffusion * timestep * 1.0 / (hx * hx);
+        size_t idx = 0;
+        for (int y = 0; y < h; y++) {
+            for (int x = 0; x < w; x++, idx++) {
+                if (!fluid(idx)) continue;
+                if (x < w - 1 && fluid(idx + 1)) { aDiag[idx] += scale; aDiag[idx + 1] += scale; aPlusX[idx] = -scale; }
+                if (y < h - 1 && fluid(idx + w)) { aDiag[idx] += scale; aDiag[idx + w] += scale; aPlusY[idx] = -scale; }
+            }
+        }
+    }
+
+    /* F4:744 (=F5:858, F6:918, F7:951) */
+    void buildPreconditionerSolid() {
+        const double tau = cfg.mic_tau, sigma = cfg.mic_sigma;
+        size_t idx = 0;
+        for (int y = 0; y < h; y++) {
+            for (int x = 0; x < w; x++, idx++) {
+                if (!fluid(idx)) continue;
+                double e = aDiag[idx];
+                if (x > 0 && fluid(idx - 1)) {
+                    double px = aPlusX[idx - 1] * precon[idx - 1];
+                    double py = aPlusY[idx - 1] * precon[idx - 1];
+                    e -= (px * px + tau * px * py);
+                }
+                if (y > 0 && fluid(idx - w)) {
+                    double px = aPlusX[idx - w] * precon[idx - w];
+                    double py = aPlusY[idx - w] * precon[idx - w];
+                    e -= (py * py + tau * px * py);
+                }
+                if (e < sigma * aDiag[idx]) e = aDiag[idx];
+                precon[idx] = 1.0 / std::sqrt(e);
+            }
+        }
+    }
+
+    /* F4:780 (=F5:894, F6:954, F7:987) */
+    void applyPreconditionerSolid(std::vector<double>& dst, const std::vector<double>& a) {
+        size_t idx = 0;
+        for (int y = 0; y < h; y++) {
+            for (int x = 0; x < w; x++, idx++) {
+                if (!fluid(idx)) continue;
+                double tt = a[idx];
+                if (x > 0 && fluid(idx - 1)) tt -= aPlusX[idx - 1] * precon[idx - 1] * dst[idx - 1];
+                if (y > 0 && fluid(idx - w)) tt -= aPlusY[idx - w] * precon[idx - w] * dst[idx - w];
+                dst[idx] = tt * precon[idx];
+            }
+        }
+        idx = (size_t)w * h - 1;
+        for (int y = h - 1; y >= 0; y--) {
+            for (int x = w - 1; x >= 0; x--, idx--) {
+                if (!fluid(idx)) continue;
+                double tt = dst[idx];
+                if (x < w - 1 && fluid(idx + 1)) tt -= aPlusX[idx] * precon[idx] * dst[idx + 1];
+                if (y < h - 1 && fluid(idx + w)) tt -= aPlusY[idx] * precon[idx] * dst[idx + w];
+                dst[idx] = tt * precon[idx];
+            }
+        }
+    }
+
+    double dotProductM(const std::vector<double>& a, const std::vector<double>& b) {     /* F6:999 */
+        double result = 0.0;
+        size_t n = (size_t)w * h;
+        for (size_t i = 0; i < n; i++) if (!masksVectorOps() || fluid(i)) result += a[i] * b[i];
+        return result;
+    }
+    void scaledAddM(std::vector<double>& dst, const std::vector<double>& a, const std::vector<double>& b, double sc) {   /* F6:1041 */
+        size_t n = (size_t)w * h;
+        for (size_t i = 0; i < n; i++) if (!masksVectorOps() || fluid(i)) dst[i] = a[i] + b[i] * sc;
+    }
+    double infinityNormM(const std::vector<double>& a) {                                  /* F6:1054 */
+        double maxA = 0.0;
+        size_t n = (size_t)w * h;
+        for (size_t i = 0; i < n; i++) if (!masksVectorOps() || fluid(i)) maxA = jmax(maxA, jabsf(a[i]));
+        return maxA;
+    }
+
+    /* F4:883 (=F5:997, F6:1069, F7:1102) */
+    bool projectPCGSolid(int limit, int32_t& its, double& res, int budgetBit) {
+        std::fill(p.begin(), p.end(), 0.0);
+        applyPreconditionerSolid(z, r);
+        s = z;
+        st.exceeded_budget &= ~budgetBit;
+        double maxError = infinityNormM(r);
+        its = 0; res = maxError;
+        if (maxError < cfg.tolerance) return true;
+        double sigma = dotProductM(z, r);
+        for (int iter = 0; iter < limit; iter++) {
+            matrixVectorProduct(z, s);
+            double alpha = sigma / dotProductM(z, s);
+            scaledAddM(p, p, s, alpha);
+            scaledAddM(r, r, z, -alpha);
+            maxError = infinityNormM(r);
+            its = iter + 1; res = maxError;
+            if (maxError < cfg.tolerance) return true;
+            if (maxError != maxError) { st.nan_residual = 1; return false; }
+            applyPreconditionerSolid(z, r);
+            double sigmaNew = dotProductM(z, r);
+            scaledAddM(s, z, s, sigmaNew / sigma);
+            sigma = sigmaNew;
+        }
+        st.exceeded_budget |= budgetBit;
+        return true;
+    }
+
+    /* F4:927 (=F5:1041, F6:1114) / F7:1148 (divided by the face density) */
+    void applyPressureSolid(double timestep) {
+        const bool vd = variant >= IFL_F7_VARIABLE_DENSITY;
+        double scale = vd ? timestep / hx : timestep / (density * hx);
+        size_t idx = 0;
+        for (int y = 0; y < h; y++) {
+            for (int x = 0; x < w; x++, idx++) {
+                if (!fluid(idx)) continue;
+                if (vd) {
+                    u.setSrc(x, y, u.getSrc(x, y) - scale * p[idx] / uDensity[(size_t)x + (size_t)y * (w + 1)]);
+                    v.setSrc(x, y, v.getSrc(x, y) - scale * p[idx] / vDensity[(size_t)x + (size_t)y * w]);
+                    u.setSrc(x + 1, y, u.getSrc(x + 1, y) + scale * p[idx] / uDensity[(size_t)(x + 1) + (size_t)y * (w + 1)]);
+                    v.setSrc(x, y + 1, v.getSrc(x, y + 1) + scale * p[idx] / vDensity[(size_t)x + (size_t)(y + 1) * w]);
+                } else {
+                    u.setSrc(x, y, u.getSrc(x, y) - scale * p[idx]);
+                    u.setSrc(x + 1, y, u.getSrc(x + 1, y) + scale * p[idx]);
+                    v.setSrc(x, y, v.getSrc(x, y) - scale * p[idx]);
+                    v.setSrc(x, y + 1, v.getSrc(x, y + 1) + scale * p[idx]);
+                }
+            }
+        }
+    }
+
+    /* F6:1135 (=F7:1169) */
+    void addBuoyancy(double timestep) {
+        double alpha = (cfg.density_soot - density) / density;
+        for (int y = 0; y < h; y++) {
+            for (int x = 0; x < w; x++) {
+                double buoyancy = timestep * cfg.gravity * (alpha * d.getSrc(x, y) - (t.getSrc(x, y) - cfg.t_ambient) / cfg.t_ambient);
+                v.setSrc(x, y, v.getSrc(x, y) + buoyancy * 0.5);
+                v.setSrc(x, y + 1, v.getSrc(x, y + 1) + buoyancy * 0.5);
+            }
+        }
+    }
+
+    /* F4:948 (=F5:1062, F6:1154, F7:1185): all four faces use velocityX (kept) */
+    void setBoundaryCondition() {
+        size_t idx = 0;
+        for (int y = 0; y < h; y++) {
+            for (int x = 0; x < w; x++, idx++) {
+                if (d.cell[idx] == CELL_SOLID) {
+                    const Body& b = bodies[d.body[idx]];
+                    u.setSrc(x, y, b.velocityX(x * hx, (y + 0.5) * hx));
+                    v.setSrc(x, y, b.velocityX((x + 0.5) * hx, y * hx));
+                    u.setSrc(x + 1, y, b.velocityX((x + 1.0) * hx, (y + 0.5) * hx));
+                    v.setSrc(x, y + 1, b.velocityX((x + 0.5) * hx, (y + 1.0) * hx));
+                }
+            }
+        }
+        for (int y = 0; y < h; y++) { u.setSrc(0, y, 0.0); u.setSrc(w, y, 0.0); }
+        for (int x = 0; x < w; x++) { v.setSrc(x, 0, 0.0); v.setSrc(x, h, 0.0); }
+    }
+
+    void fillSolidFieldsAll() {
+        d.fillSolidFields(variant, bodies);
+        if (variant >= IFL_F6_HEAT) t.fillSolidFields(variant, bodies);
+        u.fillSolidFields(variant, bodies);
+        v.fillSolidFields(variant, bodies);
+    }
+
+    /* F6:1190-1201 (=F7:1221-1232): r <- T; heat matrix; MIC; project; T <- p */
+    void heatSolve(double timestep) {
+        r = t.src;
+        buildHeatDiffusionMatrix(timestep);
+        buildPreconditionerSolid();
+        projectPCGSolid(cfg.solver_limit, st.iterations_heat, st.residual_heat, 2);
+        t.src = p;
+    }
+
+    /* F4:617 / F5:1089 / F6:1181 / F7:1212 */
+    void updateSolid(double timestep) {
+        fillSolidFieldsAll();
+        if (variant >= IFL_F6_HEAT) {
+            heatSolve(timestep);
+            t.extrapolate();
+            addBuoyancy(timestep);
+        }
+        setBoundaryCondition();
+        buildRhsSolid();
+        if (variant >= IFL_F7_VARIABLE_DENSITY) computeDensities();
+        buildPressureMatrixSolid(timestep);
+        buildPreconditionerSolid();
+        projectPCGSolid(cfg.solver_limit, st.iterations_pressure, st.residual_pressure, 1);
+        applyPressureSolid(timestep);
+        d.extrapolate(); u.extrapolate(); v.extrapolate();
+        setBoundaryCondition();
+        d.advectMasked(timestep, u, v, bodies);
+        if (variant >= IFL_F6_HEAT) t.advectMasked(timestep, u, v, bodies);
+        u.advectMasked(timestep, u, v, bodies);
+        v.advectMasked(timestep, u, v, bodies);
+        d.swap(); u.swap(); v.swap();
+        if (variant >= IFL_F6_HEAT) t.swap();
+    }
+
     void project(double timestep) {
+        if (variant >= IFL_F4_SOLID_BOUNDARIES) { projectPCGSolid(cfg.solver_limit, st.iterations_pressure, st.residual_pressure, 1); return; }
         if (usesPcg()) projectPCG(cfg.solver_limit, st.iterations_pressure, st.residual_pressure, 1);
         else           projectGS(cfg.solver_limit, timestep);
     }
 
     /* F1:298 / F3:385 */
-    void addInflow(double x, double y, double ww, double hh, double dv, double /*tv*/, double uv, double vv) {
+    void addInflow(double x, double y, double ww, double hh, double dv, double tv, double uv, double vv) {
         d.addInflow(variant, x, y, x + ww, y + hh, dv);
+        if (variant >= IFL_F6_HEAT) t.addInflow(variant, x, y, x + ww, y + hh, tv);       /* F6:1233 */
         u.addInflow(variant, x, y, x + ww, y + hh, uv);
         v.addInflow(variant, x, y, x + ww, y + hh, vv);
     }
 
     /* F1:276 / F2:322 / F3:361 */
     void update(double timestep) {
+        if (variant >= IFL_F4_SOLID_BOUNDARIES) { updateSolid(timestep); return; }
         buildRhs();
         if (usesPcg()) { buildPressureMatrix(timestep); buildPreconditioner(); }
         project(timestep);
@@ -449,15 +960,40 @@ struct Solver {
         return jmin(maxTimestep, 1.0);
     }
 
+    Quantity* quantity(int q) { return q == 0 ? &d : q == 1 ? &t : q == 2 ? &u : &v; }
+
     std::vector<double>* field(int f) {
+        const bool solids = variant >= IFL_F4_SOLID_BOUNDARIES, heat = variant >= IFL_F6_HEAT;
         switch (f) {
             case IFL_FIELD_D: return &d.src;   case IFL_FIELD_U: return &u.src;   case IFL_FIELD_V: return &v.src;
             case IFL_FIELD_D_DST: return &d.dst; case IFL_FIELD_U_DST: return &u.dst; case IFL_FIELD_V_DST: return &v.dst;
+            case IFL_FIELD_T: return heat ? &t.src : nullptr;
+            case IFL_FIELD_T_DST: return heat ? &t.dst : nullptr;
             case IFL_FIELD_P: return &p; case IFL_FIELD_R: return &r; case IFL_FIELD_Z: return &z; case IFL_FIELD_S: return &s;
             case IFL_FIELD_PRECON: return &precon; case IFL_FIELD_ADIAG: return &aDiag;
             case IFL_FIELD_APLUSX: return &aPlusX; case IFL_FIELD_APLUSY: return &aPlusY;
-            default: return nullptr;
+            case IFL_FIELD_UDENSITY: return variant >= IFL_F7_VARIABLE_DENSITY ? &uDensity : nullptr;
+            case IFL_FIELD_VDENSITY: return variant >= IFL_F7_VARIABLE_DENSITY ? &vDensity : nullptr;
+            default: break;
         }
+        if (!solids || f < IFL_FIELD_VOLUME_D || f > IFL_FIELD_PHI_V) return nullptr;
+        int q = (f - IFL_FIELD_VOLUME_D) % 4, grp = (f - IFL_FIELD_VOLUME_D) / 4;
+        if (q == 1 && !heat) return nullptr;
+        Quantity* Q = quantity(q);
+        switch (grp) {
+            case 0: return variant >= IFL_F5_CURVED_BOUNDARIES ? &Q->volume : nullptr;
+            case 1: return &Q->normalX;
+            case 2: return &Q->normalY;
+            case 5: return variant >= IFL_F5_CURVED_BOUNDARIES ? &Q->phi : nullptr;
+            default: return nullptr;   /* 3, 4: integer arrays, see int_field */
+        }
+    }
+    std::vector<int>* int_field(int f) {
+        if (variant < IFL_F4_SOLID_BOUNDARIES || f < IFL_FIELD_CELL_D || f > IFL_FIELD_BODY_V) return nullptr;
+        int q = (f - IFL_FIELD_CELL_D) % 4;
+        if (q == 1 && variant < IFL_F6_HEAT) return nullptr;
+        Quantity* Q = quantity(q);
+        return f < IFL_FIELD_BODY_D ? &Q->cell : &Q->body;
     }
 };
 
@@ -467,12 +1003,19 @@ extern "C" {
 
 int ifo_create(const ifl_config* cfg, void** out) {
     if (!cfg || !out || cfg->w < 2 || cfg->h < 2) return IFL_ERR_INVALID;
-    if (cfg->variant < IFL_F1_MATRIXLESS || cfg->variant > IFL_F3_CONJUGATE_GRADIENTS) return IFL_ERR_UNSUPPORTED;
+    if (cfg->variant < IFL_F1_MATRIXLESS || cfg->variant > IFL_F7_VARIABLE_DENSITY) return IFL_ERR_UNSUPPORTED;
     *out = new Solver(*cfg);
     return IFL_OK;
 }
 void ifo_destroy(void* h) { delete (Solver*)h; }
 
+int ifo_set_bodies(void* h, const ifl_body* bodies, int32_t count) {
+    Solver* s = (Solver*)h;
+    if (s->variant < IFL_F4_SOLID_BOUNDARIES) return count == 0 ? IFL_OK : IFL_ERR_UNSUPPORTED;
+    s->bodies.clear();
+    for (int i = 0; i < count; i++) s->bodies.push_back(Body{bodies[i]});
+    return IFL_OK;
+}
 int ifo_add_inflow(void* h, double x, double y, double w, double hh, double d, double t, double u, double v) {
     ((Solver*)h)->addInflow(x, y, w, hh, d, t, u, v);
     return IFL_OK;
@@ -496,18 +1039,36 @@ int ifo_run_steps(void* h, int n, double dt, double x, double y, double w, doubl
 }
 int ifo_run_stage(void* h, int stage, double dt, ifl_step_status* st) {
     Solver* s = (Solver*)h;
+    const bool solids = s->variant >= IFL_F4_SOLID_BOUNDARIES, heat = s->variant >= IFL_F6_HEAT;
+    auto adv = [&](Quantity& q) { if (solids) q.advectMasked(dt, s->u, s->v, s->bodies); else q.advect(s->variant, dt, s->u, s->v); };
     switch (stage) {
-        case IFL_STAGE_BUILD_RHS: s->buildRhs(); break;
-        case IFL_STAGE_BUILD_MATRIX: if (!s->usesPcg()) return IFL_ERR_UNSUPPORTED; s->buildPressureMatrix(dt); break;
-        case IFL_STAGE_BUILD_PRECON: if (!s->usesPcg()) return IFL_ERR_UNSUPPORTED; s->buildPreconditioner(); break;
+        case IFL_STAGE_BUILD_RHS: if (solids) s->buildRhsSolid(); else s->buildRhs(); break;
+        case IFL_STAGE_BUILD_MATRIX:
+            if (!s->usesPcg()) return IFL_ERR_UNSUPPORTED;
+            if (solids) s->buildPressureMatrixSolid(dt); else s->buildPressureMatrix(dt); break;
+        case IFL_STAGE_BUILD_PRECON:
+            if (!s->usesPcg()) return IFL_ERR_UNSUPPORTED;
+            if (solids) s->buildPreconditionerSolid(); else s->buildPreconditioner(); break;
         case IFL_STAGE_PROJECT: s->project(dt); break;
-        case IFL_STAGE_APPLY_PRESSURE: s->applyPressure(dt); break;
-        case IFL_STAGE_ADVECT_D: s->d.advect(s->variant, dt, s->u, s->v); break;
-        case IFL_STAGE_ADVECT_U: s->u.advect(s->variant, dt, s->u, s->v); break;
-        case IFL_STAGE_ADVECT_V: s->v.advect(s->variant, dt, s->u, s->v); break;
-        case IFL_STAGE_SWAP: s->d.swap(); s->u.swap(); s->v.swap(); break;
-        case IFL_STAGE_APPLY_PRECON: if (!s->usesPcg()) return IFL_ERR_UNSUPPORTED; s->applyPreconditioner(s->z, s->r); break;
+        case IFL_STAGE_APPLY_PRESSURE: if (solids) s->applyPressureSolid(dt); else s->applyPressure(dt); break;
+        case IFL_STAGE_ADVECT_D: adv(s->d); break;
+        case IFL_STAGE_ADVECT_T: if (!heat) return IFL_ERR_UNSUPPORTED; adv(s->t); break;
+        case IFL_STAGE_ADVECT_U: adv(s->u); break;
+        case IFL_STAGE_ADVECT_V: adv(s->v); break;
+        case IFL_STAGE_SWAP: s->d.swap(); s->u.swap(); s->v.swap(); if (heat) s->t.swap(); break;
+        case IFL_STAGE_APPLY_PRECON:
+            if (!s->usesPcg()) return IFL_ERR_UNSUPPORTED;
+            if (solids) s->applyPreconditionerSolid(s->z, s->r); else s->applyPreconditioner(s->z, s->r); break;
         case IFL_STAGE_MATVEC: if (!s->usesPcg()) return IFL_ERR_UNSUPPORTED; s->matrixVectorProduct(s->z, s->s); break;
+        case IFL_STAGE_FILL_SOLID_FIELDS: if (!solids) return IFL_ERR_UNSUPPORTED; s->fillSolidFieldsAll(); break;
+        case IFL_STAGE_SET_BOUNDARY: if (!solids) return IFL_ERR_UNSUPPORTED; s->setBoundaryCondition(); break;
+        case IFL_STAGE_EXTRAPOLATE_D: if (!solids) return IFL_ERR_UNSUPPORTED; s->d.extrapolate(); break;
+        case IFL_STAGE_EXTRAPOLATE_T: if (!heat) return IFL_ERR_UNSUPPORTED; s->t.extrapolate(); break;
+        case IFL_STAGE_EXTRAPOLATE_U: if (!solids) return IFL_ERR_UNSUPPORTED; s->u.extrapolate(); break;
+        case IFL_STAGE_EXTRAPOLATE_V: if (!solids) return IFL_ERR_UNSUPPORTED; s->v.extrapolate(); break;
+        case IFL_STAGE_HEAT_SOLVE: if (!heat) return IFL_ERR_UNSUPPORTED; s->heatSolve(dt); break;
+        case IFL_STAGE_ADD_BUOYANCY: if (!heat) return IFL_ERR_UNSUPPORTED; s->addBuoyancy(dt); break;
+        case IFL_STAGE_COMPUTE_DENSITIES: if (s->variant < IFL_F7_VARIABLE_DENSITY) return IFL_ERR_UNSUPPORTED; s->computeDensities(); break;
         default: return IFL_ERR_UNSUPPORTED;
     }
     if (st) *st = s->st;
@@ -516,22 +1077,38 @@ int ifo_run_stage(void* h, int stage, double dt, ifl_step_status* st) {
 int ifo_max_timestep(void* h, double* out) { *out = ((Solver*)h)->maxTimestep(); return IFL_OK; }
 
 int ifo_field_size(void* h, int f, size_t* count) {
-    auto* v = ((Solver*)h)->field(f);
-    if (!v) return IFL_ERR_INVALID;
-    *count = v->size();
-    return IFL_OK;
+    Solver* s = (Solver*)h;
+    if (auto* v = s->field(f)) { *count = v->size(); return IFL_OK; }
+    if (auto* v = s->int_field(f)) { *count = v->size(); return IFL_OK; }
+    return IFL_ERR_INVALID;
 }
 int ifo_read_field(void* h, int f, double* host, size_t count) {
-    auto* v = ((Solver*)h)->field(f);
-    if (!v || count != v->size()) return IFL_ERR_INVALID;
-    std::memcpy(host, v->data(), count * sizeof(double));
-    return IFL_OK;
+    Solver* s = (Solver*)h;
+    if (auto* v = s->field(f)) {
+        if (count != v->size()) return IFL_ERR_INVALID;
+        std::memcpy(host, v->data(), count * sizeof(double));
+        return IFL_OK;
+    }
+    if (auto* v = s->int_field(f)) {
+        if (count != v->size()) return IFL_ERR_INVALID;
+        for (size_t i = 0; i < count; i++) host[i] = (double)(*v)[i];
+        return IFL_OK;
+    }
+    return IFL_ERR_INVALID;
 }
 int ifo_write_field(void* h, int f, const double* host, size_t count) {
-    auto* v = ((Solver*)h)->field(f);
-    if (!v || count != v->size()) return IFL_ERR_INVALID;
-    std::memcpy(v->data(), host, count * sizeof(double));
-    return IFL_OK;
+    Solver* s = (Solver*)h;
+    if (auto* v = s->field(f)) {
+        if (count != v->size()) return IFL_ERR_INVALID;
+        std::memcpy(v->data(), host, count * sizeof(double));
+        return IFL_OK;
+    }
+    if (auto* v = s->int_field(f)) {
+        if (count != v->size()) return IFL_ERR_INVALID;
+        for (size_t i = 0; i < count; i++) (*v)[i] = (int)host[i];
+        return IFL_OK;
+    }
+    return IFL_ERR_INVALID;
 }
 
 /* scalar helpers exported so the tests can pin the interpolation invariants */
