@@ -178,7 +178,7 @@ def test_reference_scene_40_steps_fast_path(ifl, oracle_cls, variant_name):
             a_, b_ = g.read(n), o.read(n)
             err = np.max(np.abs(a_ - b_)) / vel_scale if n in ("u", "v") else rel_err(a_, b_)
             assert err <= tol, (step, n, err)
-    assert straddles <= 6, straddles
+    assert straddles <= 16, straddles      # F6: the 6-7 iteration heat solve sits on the threshold in ~1 step of 4
 
 
 def test_moving_bodies_timesteps(ifl, oracle_cls):
