@@ -116,3 +116,74 @@ def test_max_timestep(abi, oracle_cls):
     assert o.max_timestep() == 1.0                                # zero velocity -> inf -> min(.,1)
     o.write("u", np.full(17 * 16, 0.5)); o.write("v", np.zeros(16 * 17))
     assert o.max_timestep() == pytest.approx(2.0 * (1 / 16) / 0.5)
+
+
+# ---- F4-F7: solids, heat, variable density -----------------------------------------------------------------
+
+def make_solid(abi, oracle_cls, ifl, variant, w, h, spec, **kw):
+    o = oracle_cls(abi, abi.default_config(variant, w, h, **kw))
+    o.set_bodies(scenes.make_bodies(ifl, spec))
+    return o
+
+
+def test_sphere_volume_fractions_integrate_to_the_disc_area(abi, oracle_cls, ifl):
+    """F5 fillSolidFields: sum(1 - volume) * hx^2 approximates the area of the SolidSphere (marching squares on phi)."""
+    w = h = 128
+    o = make_solid(abi, oracle_cls, ifl, abi.F5_CURVED_BOUNDARIES, w, h, [("sphere", (0.5, 0.5, 0.4, 0.0, 0.0, 0.0, 0.0))])
+    o.run_stage("fill_solid_fields")
+    vol = o.read("volume_d")
+    cell = o.read("cell_d")
+    assert vol.min() == 0.0 and vol.max() == 1.0
+    assert np.all((cell == 1) == (vol == 0.0))                    # F5:512-517: SOLID iff volume == 0 (after the 0.01 clamp)
+    assert not np.any((vol > 0) & (vol < 0.01))
+    area = np.sum(1.0 - vol) / (w * h)
+    assert abs(area - np.pi * 0.2 ** 2) < 2e-3
+    nx, ny = o.read("normalx_d"), o.read("normaly_d")
+    assert np.allclose(nx * nx + ny * ny, 1.0)                    # SolidSphere.distanceNormal is a unit vector
+
+
+def test_box_voxelisation_f4(abi, oracle_cls, ifl):
+    """F4: cell = SOLID iff distance < 0 (cell-centre sample of the axis-aligned box)."""
+    w = h = 64
+    o = make_solid(abi, oracle_cls, ifl, abi.F4_SOLID_BOUNDARIES, w, h, [("box", (0.5, 0.5, 0.5, 0.25, 0.0, 0.0, 0.0, 0.0))])
+    assert np.all(o.read("cell_d") == 3)                          # F4:183: _cell is null until fillSolidFields runs
+    o.run_stage("fill_solid_fields")
+    cell = o.read("cell_d").reshape(h, w)
+    yc, xc = np.meshgrid((np.arange(h) + 0.5) / h, (np.arange(w) + 0.5) / w, indexing="ij")
+    inside = (np.abs(xc - 0.5) < 0.25) & (np.abs(yc - 0.5) < 0.125)
+    assert np.array_equal(cell == 1, inside)
+
+
+@pytest.mark.parametrize("variant_name", ["F4_SOLID_BOUNDARIES", "F5_CURVED_BOUNDARIES", "F7_VARIABLE_DENSITY"])
+def test_projection_makes_fluid_cells_divergence_free(abi, oracle_cls, ifl, variant_name):
+    variant = getattr(abi, variant_name)
+    w = h = 48
+    spec, rect, kw = scenes.solid_scene(abi, variant)
+    o = make_solid(abi, oracle_cls, ifl, variant, w, h, spec, **kw)
+    rng = np.random.default_rng(5)
+    o.write("u", rng.normal(size=(w + 1) * h) * 1e-2); o.write("v", rng.normal(size=w * (h + 1)) * 1e-2)
+    stages = ["fill_solid_fields", "set_boundary", "build_rhs"] + (["compute_densities"] if variant >= abi.F7_VARIABLE_DENSITY else [])
+    for st in stages + ["build_matrix", "build_precon", "project", "apply_pressure", "build_rhs"]:
+        o.run_stage(st, scenes.DT)
+    assert np.max(np.abs(o.read("r"))) < 1e-4                     # new RHS = remaining (volume-weighted) divergence
+
+
+def test_extrapolate_fills_solid_cells_from_the_fluid_side(abi, oracle_cls, ifl):
+    w = h = 64
+    o = make_solid(abi, oracle_cls, ifl, abi.F4_SOLID_BOUNDARIES, w, h, [("box", (0.5, 0.5, 0.4, 0.3, 0.0, 0.0, 0.0, 0.0))])
+    o.run_stage("fill_solid_fields")
+    cell = o.read("cell_d")
+    o.write("d", np.where(cell == 1, -7.0, 2.5))                  # constant 2.5 in the fluid, garbage in the solid
+    o.run_stage("extrapolate_d")
+    assert np.all(o.read("d") == 2.5)                             # normal-weighted average of a constant is the constant
+
+
+def test_heat_solve_conserves_a_uniform_temperature(abi, oracle_cls, ifl):
+    w = h = 32
+    spec, rect, kw = scenes.solid_scene(abi, abi.F6_HEAT)
+    o = make_solid(abi, oracle_cls, ifl, abi.F6_HEAT, w, h, spec, **kw)
+    o.run_stage("fill_solid_fields")
+    st = o.run_stage("heat_solve", scenes.DT)
+    t = o.read("t"); cell = o.read("cell_d")
+    assert np.allclose(t[cell == 0], 294.0, rtol=0, atol=1e-4)    # (I + dt*D*L) T = T for constant T (rows of L sum to 0)
+    assert np.all(t[cell == 1] == 0.0)                            # F6:1199 writes p (0 on solids) back; extrapolate() fixes it next
