@@ -154,8 +154,11 @@ def test_box_voxelisation_f4(abi, oracle_cls, ifl):
     assert np.array_equal(cell == 1, inside)
 
 
-@pytest.mark.parametrize("variant_name", ["F4_SOLID_BOUNDARIES", "F5_CURVED_BOUNDARIES", "F7_VARIABLE_DENSITY"])
+@pytest.mark.parametrize("variant_name", ["F4_SOLID_BOUNDARIES", "F5_CURVED_BOUNDARIES", "F6_HEAT"])
 def test_projection_makes_fluid_cells_divergence_free(abi, oracle_cls, ifl, variant_name):
+    # F7 is deliberately absent: its buildPressureMatrix reads _vDensity with _u's stride (F7:898) while applyPressure
+    # uses the right one (F7:1161), so the reference's own projection is not divergence free near the last rows --
+    # a port bug the oracle and the CUDA path both reproduce.
     variant = getattr(abi, variant_name)
     w = h = 48
     spec, rect, kw = scenes.solid_scene(abi, variant)
@@ -163,7 +166,8 @@ def test_projection_makes_fluid_cells_divergence_free(abi, oracle_cls, ifl, vari
     rng = np.random.default_rng(5)
     o.write("u", rng.normal(size=(w + 1) * h) * 1e-2); o.write("v", rng.normal(size=w * (h + 1)) * 1e-2)
     stages = ["fill_solid_fields", "set_boundary", "build_rhs"] + (["compute_densities"] if variant >= abi.F7_VARIABLE_DENSITY else [])
-    for st in stages + ["build_matrix", "build_precon", "project", "apply_pressure", "build_rhs"]:
+    # applyPressure only updates faces from their fluid side; setBoundaryCondition re-imposes the solid faces (F4:630-634)
+    for st in stages + ["build_matrix", "build_precon", "project", "apply_pressure", "set_boundary", "build_rhs"]:
         o.run_stage(st, scenes.DT)
     assert np.max(np.abs(o.read("r"))) < 1e-4                     # new RHS = remaining (volume-weighted) divergence
 
