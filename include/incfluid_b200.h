@@ -78,7 +78,12 @@ typedef struct ifl_config {
     int32_t particles_avg_per_cell;  /* _AvgPerCell = 4  (F8:1494) */
     int32_t particles_max_per_cell;  /* _MaxPerCell = 12 (F8:1484) */
     int32_t particles_min_per_cell;  /* _MinPerCell = 3  (F8:1489) */
-    uint64_t rng_seed;        /* replaces the unseeded Math.random() (F8:1576,1647) */
+    /* F8: the unseeded Math.random() (F8:1576,1647) is replaced by an injected counter-based stream so that runs are
+     * reproducible and a parallel implementation can consume "the k-th draw" in the reference's order:
+     *   z = rng_seed + 0x9E3779B97F4A7C15*(k+1); z = (z^(z>>30))*0xBF58476D1CE4E5B9; z = (z^(z>>27))*0x94D049BB133111EB;
+     *   z ^= z>>31;  draw_k = (float)(z >> 40) / 2^24            (splitmix64 finaliser, 24-bit float in [0,1))
+     * Draws are consumed exactly where the reference calls random(): 2 per init / seed attempt, in loop order. */
+    uint64_t rng_seed;
     int32_t device;           /* CUDA device ordinal */
     /* Slab decomposition.  world_size == 1: single GPU.
      * world_size > 1: this process owns rows [rank*h/world, (rank+1)*h/world)
@@ -94,7 +99,11 @@ typedef enum ifl_flags {
     /* Evaluate dotProduct (F3:532) in the reference's strictly sequential order instead of
      * the fixed-shape parallel tree.  Slow (one thread per reduction); makes the whole PCG
      * solve bit-identical to the Java loops.  Meant for parity tests on small grids. */
-    IFL_FLAG_SEQUENTIAL_REDUCTIONS = 1
+    IFL_FLAG_SEQUENTIAL_REDUCTIONS = 1,
+    /* F8 only: always replay FluidQuantity.extrapolate's LIFO stack (F8:651) with one device thread instead of the
+     * level-parallel sweep.  The library switches to the replay by itself whenever two CELL_EMPTY cells touch (the
+     * only case in which the reference's result depends on its stack order); the flag exists to test that path. */
+    IFL_FLAG_SEQUENTIAL_EXTRAPOLATE = 2
 } ifl_flags;
 
 /* Rigid body table entry = the fields of A_SolidBody (solidBodies/A_SolidBody.java:73-87).

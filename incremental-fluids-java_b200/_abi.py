@@ -19,6 +19,7 @@ BODY_BOX, BODY_SPHERE = 0, 1
 
 # ifl_flags
 FLAG_SEQUENTIAL_REDUCTIONS = 1
+FLAG_SEQUENTIAL_EXTRAPOLATE = 2
 
 
 class Config(C.Structure):

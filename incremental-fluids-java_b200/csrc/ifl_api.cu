@@ -68,12 +68,16 @@ struct ifl_solver {
     unsigned int* h_progress = nullptr;
     SolveScalars* sc_heat = nullptr;                /* device copy of the heat solve's final scalars */
     SolveScalars* h_sc_heat = nullptr;
+    /* F8 */
+    FlipCtx flip;
+    double inflow[8] = {0.45, 0.2, 0.2, 0.05, 1.0, 294.0, 0.0, 0.0};   /* F8:1330 */
 };
 
 static bool uses_pcg(const ifl_solver* s) { return s->cfg.variant >= IFL_F3_CONJUGATE_GRADIENTS; }
 static bool has_solids(const ifl_solver* s) { return s->cfg.variant >= IFL_F4_SOLID_BOUNDARIES; }
 static bool has_heat(const ifl_solver* s) { return s->cfg.variant >= IFL_F6_HEAT; }
 static bool has_vardens(const ifl_solver* s) { return s->cfg.variant >= IFL_F7_VARIABLE_DENSITY; }
+static bool is_flip(const ifl_solver* s) { return s->cfg.variant == IFL_F8_FLIP; }
 
 extern "C" {
 
@@ -148,6 +152,7 @@ void ifl_destroy(ifl_solver* s) {
     for (void* p : extra) if (p) cudaFree(p);
     if (s->h_progress) cudaFreeHost(s->h_progress);
     if (s->h_sc_heat) cudaFreeHost(s->h_sc_heat);
+    flip_free(s->flip);
     if (s->skew_block) cudaFree(s->skew_block);
     if (s->scratch) cudaFree(s->scratch);
     if (s->sx.pack_f) cudaFree(s->sx.pack_f);
@@ -187,6 +192,10 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     if (has_vardens(s)) {
         CU(cudaMalloc(&s->udens, sizeof(double) * s->u.count())); CU(cudaMemset(s->udens, 0, sizeof(double) * s->u.count()));
         CU(cudaMalloc(&s->vdens, sizeof(double) * s->v.count())); CU(cudaMemset(s->vdens, 0, sizeof(double) * s->v.count()));
+    }
+    if (is_flip(s)) {
+        CU(flip_alloc(s->flip, s->w, s->h, cfg->particles_max_per_cell));
+        s->inflow[5] = cfg->t_ambient;
     }
     if (has_solids(s)) {
         CU(cudaMalloc(&s->extrap_state, (size_t)(s->w + 1) * (s->h + 1)));
@@ -255,10 +264,6 @@ int ifl_create(const ifl_config* cfg, ifl_solver** out) {
     if (cfg->abi_version != IFL_ABI_VERSION) INVALID("abi_version mismatch");
     if (cfg->w < 2 || cfg->h < 2) INVALID("grid must be at least 2x2");
     if (cfg->variant < IFL_F1_MATRIXLESS || cfg->variant > IFL_F8_FLIP) INVALID("unknown variant");
-    if (cfg->variant > IFL_F7_VARIABLE_DENSITY) {
-        snprintf(g_err, sizeof g_err, "variant %d is not implemented by this build", cfg->variant);
-        return IFL_ERR_UNSUPPORTED;
-    }
     if (cfg->world_size != 1) {
         snprintf(g_err, sizeof g_err, "slab decomposition (world_size=%d) is not implemented by this build", cfg->world_size);
         return IFL_ERR_UNSUPPORTED;
@@ -301,6 +306,11 @@ int ifl_set_bodies(ifl_solver* s, const ifl_body* bodies, int32_t count) {
 
 int ifl_add_inflow(ifl_solver* s, double x, double y, double w, double h, double d, double t, double u, double v) {
     if (!s) INVALID("NULL handle");
+    if (is_flip(s)) {            /* F8 calls addInflow inside update() (F8:1330): this sets that rectangle */
+        double r[8] = {x, y, w, h, d, t, u, v};
+        memcpy(s->inflow, r, sizeof r);
+        return IFL_OK;
+    }
     CU(cudaSetDevice(s->cfg.device));
     /* FluidSolver.addInflow F1:298 / F3:385 / F6:1233 */
     launch_add_inflow(s->stream, s->cfg.variant, s->d.q, s->d.src(), s->hx, x, y, x + w, y + h, d);
@@ -348,6 +358,7 @@ static int fetch_status(ifl_solver* s, ifl_step_status* st) {
     CU(cudaMemcpyAsync(&s->h_sc[0], s->sx.sc, sizeof(SolveScalars), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     const SolveScalars& h = s->h_sc[0];
+    if (is_flip(s)) s->last.particle_count = s->flip.count;
     s->last.iterations_pressure = h.iterations;
     s->last.residual_pressure = h.max_error;
     s->last.exceeded_budget = h.exceeded ? 1 : 0;
@@ -527,7 +538,105 @@ static int update_solid(ifl_solver* s, double timestep) {
     return IFL_OK;
 }
 
+/* ---- F8 ----------------------------------------------------------------------------------------- */
+static int inflow_now(ifl_solver* s, const double* r) {
+    const double x = r[0], y = r[1], w = r[2], h = r[3];
+    launch_add_inflow(s->stream, s->cfg.variant, s->d.q, s->d.src(), s->hx, x, y, x + w, y + h, r[4]);
+    launch_add_inflow(s->stream, s->cfg.variant, s->t.q, s->t.src(), s->hx, x, y, x + w, y + h, r[5]);
+    launch_add_inflow(s->stream, s->cfg.variant, s->u.q, s->u.src(), s->hx, x, y, x + w, y + h, r[6]);
+    launch_add_inflow(s->stream, s->cfg.variant, s->v.q, s->v.src(), s->hx, x, y, x + w, y + h, r[7]);
+    s->launches += 4;
+    return IFL_OK;
+}
+/* the part of the F8 constructor that needs the body list: initParticles + gridToParticles(1.0) (F8:887-891) */
+static int flip_ensure(ifl_solver* s) {
+    FlipCtx& f = s->flip;
+    if (f.ready) return IFL_OK;
+    CU(flip_init_particles(f, s->stream, s->cfg.particles_avg_per_cell, s->cfg.rng_seed, s->d_bodies, s->nbodies, s->hx, &s->launches));
+    flip_grid_to_particles(f, s->stream, 1.0, s->d.q, s->d.src(), s->t.q, s->t.src(), s->u.q, s->u.src(), s->v.q, s->v.src(), &s->launches);
+    f.ready = true;
+    return IFL_OK;
+}
+static int flip_extrapolate_q(ifl_solver* s, Quantity& q) {
+    CU(flip_extrapolate(s->flip, s->stream, q.sq, q.src(), s->extrap_state, s->d_progress, s->h_progress,
+                        (s->cfg.flags & IFL_FLAG_SEQUENTIAL_EXTRAPOLATE) ? 1 : 0, &s->launches));
+    return IFL_OK;
+}
+/* ParticleQuantities.particlesToGrid F8:1761 */
+static int stage_particles_to_grid(ifl_solver* s) {
+    FlipCtx& f = s->flip;
+    int rc;
+    if ((rc = flip_ensure(s))) return rc;
+    Quantity* qs[4] = {&s->d, &s->t, &s->u, &s->v};
+    for (int q = 0; q < 4; q++) {
+        if (q != 1) CU(flip_bin(f, s->stream, qs[q]->q, &s->launches));        /* d and t share their sample positions */
+        flip_gather(f, s->stream, qs[q]->q, f.prop[q], qs[q]->src(), qs[q]->sq.cell, &s->launches);
+        if ((rc = flip_extrapolate_q(s, *qs[q]))) return rc;      /* leaves cell_start / vals_b (the binning) untouched */
+    }
+    CU(flip_count_prune_seed(f, s->stream, s->cfg.particles_max_per_cell, s->cfg.particles_min_per_cell, s->cfg.rng_seed,
+                             s->d_bodies, s->nbodies, s->hx, s->d.q, s->d.src(), s->t.q, s->t.src(), s->u.q, s->u.src(),
+                             s->v.q, s->v.src(), &s->launches));
+    s->last.particle_count = f.count;
+    return IFL_OK;
+}
+static int stage_grid_to_particles(ifl_solver* s) {
+    int rc;
+    if ((rc = flip_ensure(s))) return rc;
+    const double a = s->cfg.flip_alpha;
+    Quantity* qs[4] = {&s->d, &s->t, &s->u, &s->v};
+    for (Quantity* q : qs) flip_diff(s->stream, q->src(), q->dst(), q->count(), a, -1, &s->launches);          /* F8:346 */
+    flip_grid_to_particles(s->flip, s->stream, a, s->d.q, s->d.src(), s->t.q, s->t.src(), s->u.q, s->u.src(), s->v.q, s->v.src(),
+                           &s->launches);
+    for (Quantity* q : qs) flip_diff(s->stream, q->src(), q->dst(), q->count(), a, +1, &s->launches);          /* F8:355 */
+    return IFL_OK;
+}
+static int stage_advect_particles(ifl_solver* s, double timestep) {
+    int rc;
+    if ((rc = flip_ensure(s))) return rc;
+    flip_advect_particles(s->flip, s->stream, timestep, s->hx, s->u.q, s->u.src(), s->v.q, s->v.src(), s->d_bodies, s->nbodies,
+                          &s->launches);
+    return IFL_OK;
+}
+static int stage_extrapolate_any(ifl_solver* s, Quantity& q) {
+    return is_flip(s) ? flip_extrapolate_q(s, q) : stage_extrapolate(s, q);
+}
+/* FluidSolver.update F8:1306 */
+static int update_flip(ifl_solver* s, double timestep) {
+    int rc;
+    CU(cudaEventRecord(s->ev[0], s->stream));
+    if ((rc = flip_ensure(s))) return rc;
+    stage_fill_solid_fields(s);
+    if ((rc = stage_particles_to_grid(s))) return rc;
+    launch_cell_flags(s->stream, s->sx.g, s->d.sq.cell, s->sx.fl);      /* _d._cell went FLUID -> EMPTY -> FLUID meanwhile */
+    s->launches++;
+    for (Quantity* q : {&s->d, &s->t, &s->u, &s->v})                    /* copy() F8:339 */
+        CU(cudaMemcpyAsync(q->dst(), q->src(), sizeof(double) * q->count(), cudaMemcpyDeviceToDevice, s->stream));
+    inflow_now(s, s->inflow);                                            /* F8:1330 */
+    if ((rc = stage_heat_solve(s, timestep))) return rc;
+    if ((rc = flip_extrapolate_q(s, s->t))) return rc;
+    stage_add_buoyancy(s, timestep);
+    stage_set_boundary(s);
+    stage_build_rhs_solid(s);
+    stage_compute_densities(s);
+    stage_build_matrix_solid(s, timestep);
+    launch_build_precon(s->sx);
+    if ((rc = stage_project(s, timestep))) return rc;
+    stage_apply_pressure_solid(s, timestep);
+    if ((rc = flip_extrapolate_q(s, s->d))) return rc;
+    if ((rc = flip_extrapolate_q(s, s->u))) return rc;
+    if ((rc = flip_extrapolate_q(s, s->v))) return rc;
+    stage_set_boundary(s);
+    CU(cudaEventRecord(s->ev[1], s->stream));
+    if ((rc = stage_grid_to_particles(s))) return rc;
+    if ((rc = stage_advect_particles(s, timestep))) return rc;
+    CU(cudaEventRecord(s->ev[2], s->stream));
+    s->ev_valid = true;
+    CU(cudaGetLastError());
+    return IFL_OK;
+}
+
 static int update_impl(ifl_solver* s, double timestep) {
+    if (is_flip(s)) return update_flip(s, timestep);
     if (has_solids(s)) return update_solid(s, timestep);
     /* FluidSolver.update  F1:276 / F2:322 / F3:361 */
     CU(cudaEventRecord(s->ev[0], s->stream));
@@ -578,6 +687,7 @@ int ifl_run_stage(ifl_solver* s, int32_t stage, double timestep, ifl_step_status
     if (!s) INVALID("NULL handle");
     CU(cudaSetDevice(s->cfg.device));
     int rc = IFL_OK;
+    if (is_flip(s) && ((stage >= IFL_STAGE_ADVECT_D && stage <= IFL_STAGE_SWAP))) goto unsupported;
     switch (stage) {
         case IFL_STAGE_BUILD_RHS: rc = has_solids(s) ? stage_build_rhs_solid(s) : stage_build_rhs(s); break;
         case IFL_STAGE_BUILD_MATRIX:
@@ -597,12 +707,15 @@ int ifl_run_stage(ifl_solver* s, int32_t stage, double timestep, ifl_step_status
         case IFL_STAGE_SWAP: s->d.swap(); s->u.swap(); s->v.swap(); if (has_heat(s)) s->t.swap(); break;
         case IFL_STAGE_FILL_SOLID_FIELDS: if (!has_solids(s)) goto unsupported; rc = stage_fill_solid_fields(s); break;
         case IFL_STAGE_SET_BOUNDARY: if (!has_solids(s)) goto unsupported; rc = stage_set_boundary(s); break;
-        case IFL_STAGE_EXTRAPOLATE_D: if (!has_solids(s)) goto unsupported; rc = stage_extrapolate(s, s->d); break;
-        case IFL_STAGE_EXTRAPOLATE_T: if (!has_heat(s)) goto unsupported; rc = stage_extrapolate(s, s->t); break;
-        case IFL_STAGE_EXTRAPOLATE_U: if (!has_solids(s)) goto unsupported; rc = stage_extrapolate(s, s->u); break;
-        case IFL_STAGE_EXTRAPOLATE_V: if (!has_solids(s)) goto unsupported; rc = stage_extrapolate(s, s->v); break;
+        case IFL_STAGE_EXTRAPOLATE_D: if (!has_solids(s)) goto unsupported; rc = stage_extrapolate_any(s, s->d); break;
+        case IFL_STAGE_EXTRAPOLATE_T: if (!has_heat(s)) goto unsupported; rc = stage_extrapolate_any(s, s->t); break;
+        case IFL_STAGE_EXTRAPOLATE_U: if (!has_solids(s)) goto unsupported; rc = stage_extrapolate_any(s, s->u); break;
+        case IFL_STAGE_EXTRAPOLATE_V: if (!has_solids(s)) goto unsupported; rc = stage_extrapolate_any(s, s->v); break;
         case IFL_STAGE_HEAT_SOLVE: if (!has_heat(s)) goto unsupported; rc = stage_heat_solve(s, timestep); break;
         case IFL_STAGE_ADD_BUOYANCY: if (!has_heat(s)) goto unsupported; rc = stage_add_buoyancy(s, timestep); break;
+        case IFL_STAGE_PARTICLES_TO_GRID: if (!is_flip(s)) goto unsupported; rc = stage_particles_to_grid(s); break;
+        case IFL_STAGE_GRID_TO_PARTICLES: if (!is_flip(s)) goto unsupported; rc = stage_grid_to_particles(s); break;
+        case IFL_STAGE_ADVECT_PARTICLES: if (!is_flip(s)) goto unsupported; rc = stage_advect_particles(s, timestep); break;
         case IFL_STAGE_COMPUTE_DENSITIES: if (!has_vardens(s)) goto unsupported; rc = stage_compute_densities(s); break;
         case IFL_STAGE_APPLY_PRECON:
             if (!uses_pcg(s)) goto unsupported;
@@ -735,19 +848,44 @@ int ifl_write_field(ifl_solver* s, int32_t field, const double* host, size_t cou
 
 int ifl_particle_count(ifl_solver* s, int32_t* count) {
     if (!s || !count) INVALID("NULL argument");
-    snprintf(g_err, sizeof g_err, "variant %d has no particles", s->cfg.variant);
-    return IFL_ERR_UNSUPPORTED;
+    if (!is_flip(s)) { snprintf(g_err, sizeof g_err, "variant %d has no particles", s->cfg.variant); return IFL_ERR_UNSUPPORTED; }
+    CU(cudaSetDevice(s->cfg.device));
+    int rc = flip_ensure(s);
+    if (rc) return rc;
+    *count = s->flip.count;
+    return IFL_OK;
 }
-int ifl_read_particles(ifl_solver* s, double*, double*, double*, double*, double*, double*, size_t) {
+int ifl_read_particles(ifl_solver* s, double* pos_x, double* pos_y, double* prop_d, double* prop_t, double* prop_u, double* prop_v,
+                       size_t capacity) {
     if (!s) INVALID("NULL handle");
-    snprintf(g_err, sizeof g_err, "variant %d has no particles", s->cfg.variant);
-    return IFL_ERR_UNSUPPORTED;
+    if (!is_flip(s)) { snprintf(g_err, sizeof g_err, "variant %d has no particles", s->cfg.variant); return IFL_ERR_UNSUPPORTED; }
+    CU(cudaSetDevice(s->cfg.device));
+    int rc = flip_ensure(s);
+    if (rc) return rc;
+    FlipCtx& f = s->flip;
+    if (capacity < (size_t)f.count) INVALID("capacity < particle count");
+    double* host[6] = {pos_x, pos_y, prop_d, prop_t, prop_u, prop_v};
+    double* dev[6] = {f.posX, f.posY, f.prop[0], f.prop[1], f.prop[2], f.prop[3]};
+    for (int i = 0; i < 6; i++)
+        if (host[i]) CU(cudaMemcpyAsync(host[i], dev[i], sizeof(double) * f.count, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return IFL_OK;
 }
-int ifl_write_particles(ifl_solver* s, const double*, const double*, const double*, const double*, const double*,
-                        const double*, size_t) {
-    if (!s) INVALID("NULL handle");
-    snprintf(g_err, sizeof g_err, "variant %d has no particles", s->cfg.variant);
-    return IFL_ERR_UNSUPPORTED;
+int ifl_write_particles(ifl_solver* s, const double* pos_x, const double* pos_y, const double* prop_d, const double* prop_t,
+                        const double* prop_u, const double* prop_v, size_t count) {
+    if (!s || !pos_x || !pos_y || !prop_d || !prop_t || !prop_u || !prop_v) INVALID("NULL argument");
+    if (!is_flip(s)) { snprintf(g_err, sizeof g_err, "variant %d has no particles", s->cfg.variant); return IFL_ERR_UNSUPPORTED; }
+    FlipCtx& f = s->flip;
+    if (count > (size_t)f.max_particles) INVALID("count exceeds w*h*particles_max_per_cell");
+    CU(cudaSetDevice(s->cfg.device));
+    const double* host[6] = {pos_x, pos_y, prop_d, prop_t, prop_u, prop_v};
+    double* dev[6] = {f.posX, f.posY, f.prop[0], f.prop[1], f.prop[2], f.prop[3]};
+    for (int i = 0; i < 6; i++) CU(cudaMemcpyAsync(dev[i], host[i], sizeof(double) * count, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    f.count = (int)count;
+    f.ready = true;
+    s->last.particle_count = f.count;
+    return IFL_OK;
 }
 
 int ifl_synchronize(ifl_solver* s) {

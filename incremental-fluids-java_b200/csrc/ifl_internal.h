@@ -129,6 +129,39 @@ void launch_fill_u8(cudaStream_t st, unsigned char* p, size_t n, unsigned char v
 void launch_u8_to_double(cudaStream_t st, const unsigned char* a, double* out, size_t n);
 void launch_i32_to_double(cudaStream_t st, const int* a, double* out, size_t n);
 
+/* ---- F8 FLIP: ifl_flip_kernels.cu ---- */
+struct FlipCtx {
+    int w = 0, h = 0;
+    int count = 0;                    /* _particleCount (host mirror, updated at the few points it can change) */
+    int max_particles = 0;            /* _maxParticles = w*h*_MaxPerCell (F8:1549) */
+    unsigned long long rng_counter = 0;   /* draws consumed from the injected Math.random() stream */
+    double *posX = nullptr, *posY = nullptr, *prop[4] = {nullptr, nullptr, nullptr, nullptr};
+    int *counts = nullptr, *cell_start = nullptr, *cell_tmp = nullptr;
+    int *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
+    int *d_ints = nullptr, *h_ints = nullptr;
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    int sequential_extrapolations = 0;
+    bool ready = false;
+};
+cudaError_t flip_alloc(FlipCtx& f, int w, int h, int maxpc);
+void flip_free(FlipCtx& f);
+cudaError_t flip_init_particles(FlipCtx& f, cudaStream_t st, int avg, unsigned long long seed, const ifl_body* bodies, int nbodies,
+                                double hx, unsigned long long* launches);
+void flip_grid_to_particles(FlipCtx& f, cudaStream_t st, double alpha, QGeom qd, const double* d, QGeom qt, const double* t,
+                            QGeom qu, const double* u, QGeom qv, const double* v, unsigned long long* launches);
+void flip_advect_particles(FlipCtx& f, cudaStream_t st, double timestep, double hx, QGeom qu, const double* u, QGeom qv,
+                           const double* v, const ifl_body* bodies, int nbodies, unsigned long long* launches);
+cudaError_t flip_bin(FlipCtx& f, cudaStream_t st, QGeom q, unsigned long long* launches);
+void flip_gather(FlipCtx& f, cudaStream_t st, QGeom q, const double* prop, double* src, unsigned char* cell, unsigned long long* launches);
+void flip_diff(cudaStream_t st, double* src, const double* old, size_t n, double alpha, int sign, unsigned long long* launches);
+cudaError_t flip_count_prune_seed(FlipCtx& f, cudaStream_t st, int maxpc, int minpc, unsigned long long seed,
+                                  const ifl_body* bodies, int nbodies, double hx,
+                                  QGeom qd, const double* d, QGeom qt, const double* t, QGeom qu, const double* u,
+                                  QGeom qv, const double* v, unsigned long long* launches);
+cudaError_t flip_extrapolate(FlipCtx& f, cudaStream_t st, const SolidQ& q, double* src, unsigned char* state,
+                             unsigned int* d_progress, unsigned int* h_progress, int force_sequential, unsigned long long* launches);
+
 /* ---- solver kernels: ifl_solve_kernels.cu ---- */
 int  solve_partials_needed(const SkewGeom& g);
 void launch_build_precon(SolveCtx& c);

@@ -201,6 +201,22 @@ class FluidSolver:
     add_inflow = addInflow
     max_timestep = maxTimestep
 
+    # -- F8 particles (ParticleQuantities F8:1479) ------------------------------------------
+    def particle_count(self):
+        n = C.c_int32()
+        check(self._fn["ifl_particle_count"](self._h_, C.byref(n)))
+        return n.value
+
+    def read_particles(self):
+        n = self.particle_count()
+        arrs = [np.empty(n, dtype=np.float64) for _ in range(6)]
+        check(self._fn["ifl_read_particles"](self._h_, *[a.ctypes.data_as(_dp) for a in arrs], n))
+        return dict(zip(("x", "y", "d", "t", "u", "v"), arrs))
+
+    def write_particles(self, parts):
+        arrs = [np.ascontiguousarray(parts[k], dtype=np.float64) for k in ("x", "y", "d", "t", "u", "v")]
+        check(self._fn["ifl_write_particles"](self._h_, *[a.ctypes.data_as(_dp) for a in arrs], arrs[0].size))
+
     def synchronize(self):
         check(self._fn["ifl_synchronize"](self._h_))
 

@@ -89,6 +89,17 @@ inline double cubicPulse(double x) {
 
 struct Vec2 { double x, y; };
 
+/* Injected replacement of the unseeded Math.random() (F8:1576,1647): the k-th draw of the stream is a pure
+ * function of (seed, k) so that a parallel implementation can consume it in the reference's order.
+ * Returns (float) in [0, 1) exactly as `(float) random()` would deliver it to the float addition. */
+inline float rng_uniform(uint64_t seed, uint64_t k) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (k + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
 enum { CELL_FLUID = 0, CELL_SOLID = 1, CELL_EMPTY = 2, CELL_NULL = 3 /* F4: _cell entries stay null until fillSolidFields runs (F4:183) */ };
 
 /* ---- solidBodies/A_SolidBody.java, SolidBox.java, SolidSphere.java --------------------------------
@@ -406,6 +417,128 @@ struct Quantity {
         }
     }
 
+    /* ================= F8 (FLIP) grid side ================= */
+    /* F8:312 */
+    void addSample(std::vector<double>& weight, double value, double x, double y, int ix, int iy) {
+        if (ix < 0 || iy < 0 || ix >= w || iy >= h) return;
+        double k = (1.0 - std::fabs(ix - x)) * (1.0 - std::fabs(iy - y));
+        weight[(size_t)ix + (size_t)iy * w] += k;
+        src[(size_t)ix + (size_t)iy * w] += k * value;
+    }
+    /* F8:722: particle-index order; FLUID cells without weight become EMPTY */
+    void fromParticles(int count, const std::vector<double>& posX, const std::vector<double>& posY,
+                       const std::vector<double>& property) {
+        std::fill(src.begin(), src.end(), 0.0);
+        std::vector<double> weight((size_t)w * h, 0.0);
+        for (int i = 0; i < count; i++) {
+            double x = posX[i] - ox;
+            double y = posY[i] - oy;
+            x = jmax(0.5, jmin(w - 1.5, x));
+            y = jmax(0.5, jmin(h - 1.5, y));
+            int ix = jint(x), iy = jint(y);
+            addSample(weight, property[i], x, y, ix + 0, iy + 0);
+            addSample(weight, property[i], x, y, ix + 1, iy + 0);
+            addSample(weight, property[i], x, y, ix + 0, iy + 1);
+            addSample(weight, property[i], x, y, ix + 1, iy + 1);
+        }
+        size_t n = (size_t)w * h;
+        for (size_t i = 0; i < n; i++) {
+            if (weight[i] != 0.0) src[i] /= weight[i];
+            else if (cell[i] == CELL_FLUID) cell[i] = CELL_EMPTY;
+        }
+    }
+    void copyOld() { dst = src; }                                                   /* F8:339 (_old lives in dst) */
+    void diff(double alpha) { for (size_t i = 0; i < src.size(); i++) src[i] -= (1.0 - alpha) * dst[i]; }    /* F8:346 */
+    void undiff(double alpha) { for (size_t i = 0; i < src.size(); i++) src[i] += (1.0 - alpha) * dst[i]; }  /* F8:355 */
+
+    /* F8:483 */
+    void fillSolidMaskFlip() {
+        for (int x = 0; x < w; x++) mask[x] = mask[(size_t)x + (size_t)(h - 1) * w] = 0xFF;
+        for (int y = 0; y < h; y++) mask[(size_t)y * w] = mask[(size_t)y * w + w - 1] = 0xFF;
+        for (int y = 1; y < h - 1; y++) {
+            for (int x = 1; x < w - 1; x++) {
+                size_t idx = (size_t)x + (size_t)y * w;
+                mask[idx] = 0;
+                if (cell[idx] == CELL_SOLID) {
+                    double nx = normalX[idx], ny = normalY[idx];
+                    if (nx != 0.0 && cell[idx + (int)jsignum(nx)] != CELL_FLUID) mask[idx] |= 1;
+                    if (ny != 0.0 && cell[idx + (int)jsignum(ny) * w] != CELL_FLUID) mask[idx] |= 2;
+                } else if (cell[idx] == CELL_EMPTY) {
+                    mask[idx] = (cell[idx - 1] != CELL_FLUID && cell[idx + 1] != CELL_FLUID &&
+                                 cell[idx - w] != CELL_FLUID && cell[idx + w] != CELL_FLUID) ? 1 : 0;
+                }
+            }
+        }
+    }
+    double extrapolateAverage(size_t idx) const {                                    /* F8:544 */
+        double value = 0.0;
+        int count = 0;
+        if (cell[idx - 1] == CELL_FLUID) { value += src[idx - 1]; count++; }
+        if (cell[idx + 1] == CELL_FLUID) { value += src[idx + 1]; count++; }
+        if (cell[idx - w] == CELL_FLUID) { value += src[idx - w]; count++; }
+        if (cell[idx + w] == CELL_FLUID) { value += src[idx + w]; count++; }
+        return value / count;
+    }
+    void freeSolidNeighbour(size_t idx, std::vector<size_t>& border, int m) {        /* F8:567 */
+        if (cell[idx] == CELL_SOLID) {
+            mask[idx] &= ~m;
+            if (mask[idx] == 0) border.push_back(idx);
+        }
+    }
+    void freeEmptyNeighbour(size_t idx, std::vector<size_t>& border) {               /* F8:584 */
+        if (cell[idx] == CELL_EMPTY && mask[idx] == 1) {
+            mask[idx] = 0;
+            border.push_back(idx);
+        }
+    }
+    void extrapolateEmptyBorders() {                                                 /* F8:598 */
+        for (int x = 1; x < w - 1; x++) {
+            size_t idxT = x, idxB = (size_t)x + (size_t)(h - 1) * w;
+            if (cell[idxT] == CELL_EMPTY) src[idxT] = src[idxT + w];
+            if (cell[idxB] == CELL_EMPTY) src[idxB] = src[idxB - w];
+        }
+        for (int y = 1; y < h - 1; y++) {
+            size_t idxL = (size_t)y * w, idxR = (size_t)y * w + w - 1;
+            if (cell[idxL] == CELL_EMPTY) src[idxL] = src[idxL + 1];
+            if (cell[idxR] == CELL_EMPTY) src[idxR] = src[idxR - 1];
+        }
+        size_t idxTL = 0, idxTR = w - 1, idxBL = (size_t)(h - 1) * w, idxBR = (size_t)h * w - 1;
+        if (cell[idxTL] == CELL_EMPTY) src[idxTL] = 0.5 * (src[idxTL + 1] + src[idxTL + w]);
+        if (cell[idxTR] == CELL_EMPTY) src[idxTR] = 0.5 * (src[idxTR - 1] + src[idxTR + w]);
+        if (cell[idxBL] == CELL_EMPTY) src[idxBL] = 0.5 * (src[idxBL + 1] + src[idxBL - w]);
+        if (cell[idxBR] == CELL_EMPTY) src[idxBR] = 0.5 * (src[idxBR - 1] + src[idxBR - w]);
+        for (size_t i = 0; i < (size_t)w * h; i++) if (cell[i] == CELL_EMPTY) cell[i] = CELL_FLUID;
+    }
+    /* F8:651: LIFO stack; an extrapolated EMPTY cell is relabelled FLUID at once, so later averages see it */
+    void extrapolateFlip() {
+        fillSolidMaskFlip();
+        std::vector<size_t> border;
+        for (int y = 1; y < h - 1; y++)
+            for (int x = 1; x < w - 1; x++) {
+                size_t idx = (size_t)x + (size_t)y * w;
+                if (cell[idx] != CELL_FLUID && mask[idx] == 0) border.push_back(idx);
+            }
+        while (!border.empty()) {
+            size_t idx = border.back();
+            border.pop_back();
+            if (cell[idx] == CELL_EMPTY) {
+                src[idx] = extrapolateAverage(idx);
+                cell[idx] = CELL_FLUID;
+            } else {
+                src[idx] = extrapolateNormal(idx);
+            }
+            if (normalX[idx - 1] > 0.0) freeSolidNeighbour(idx - 1, border, 1);
+            if (normalX[idx + 1] < 0.0) freeSolidNeighbour(idx + 1, border, 1);
+            if (normalY[idx - w] > 0.0) freeSolidNeighbour(idx - w, border, 2);
+            if (normalY[idx + w] < 0.0) freeSolidNeighbour(idx + w, border, 2);
+            freeEmptyNeighbour(idx - 1, border);
+            freeEmptyNeighbour(idx + 1, border);
+            freeEmptyNeighbour(idx - w, border);
+            freeEmptyNeighbour(idx + w, border);
+        }
+        extrapolateEmptyBorders();
+    }
+
     /* F1:202 (hard rectangle) / F2:230 (=F3:232, F4:306, F5:440, F7:461, F8:383) smooth.
      * NOTE the inner loop bound is min(ix1, _h) -- _h, not _w -- in every copy. */
     void addInflow(int variant, double x0, double y0, double x1, double y1, double v) {
@@ -439,6 +572,13 @@ struct Solver {
     std::vector<double> uDensity, vDensity;                            /* F7:757-758 */
     std::vector<Body> bodies;
     ifl_step_status st;
+    /* F8 ParticleQuantities (F8:1479) */
+    std::vector<double> posX, posY, prop[4];
+    std::vector<int> counts;
+    int particleCount = 0, maxParticles = 0;
+    uint64_t rngCounter = 0;
+    double inflow[8] = {0.45, 0.2, 0.2, 0.05, 1.0, 0.0, 0.0, 0.0};   /* F8:1330 (t filled with tAmb in the ctor) */
+    bool particlesReady = false;
 
     explicit Solver(const ifl_config& c) : cfg(c) {
         variant = c.variant; w = c.w; h = c.h; density = c.density;
@@ -446,6 +586,13 @@ struct Solver {
         d.init(w, h, 0.5, 0.5, hx, variant);                          /* F1:268 */
         u.init(w + 1, h, 0.0, 0.5, hx, variant);                      /* F1:269 */
         v.init(w, h + 1, 0.5, 0.0, hx, variant);                      /* F1:270 */
+        if (variant == IFL_F8_FLIP) {
+            maxParticles = w * h * cfg.particles_max_per_cell;         /* F8:1549 */
+            posX.assign(maxParticles, 0.0); posY.assign(maxParticles, 0.0);
+            for (auto& pr : prop) pr.assign(maxParticles, 0.0);
+            counts.assign((size_t)w * h, 0);
+            inflow[5] = cfg.t_ambient;
+        }
         if (variant >= IFL_F6_HEAT) {
             t.init(w, h, 0.5, 0.5, hx, variant);                      /* F6:792 */
             std::fill(t.src.begin(), t.src.end(), cfg.t_ambient);     /* F6:797-799 */
@@ -918,6 +1065,157 @@ struct Solver {
         if (variant >= IFL_F6_HEAT) t.swap();
     }
 
+    /* ================= F8: FLIP / PIC (ParticleQuantities F8:1479-1790) ================= */
+    Quantity* qOf(int q) { return q == 0 ? &d : q == 1 ? &t : q == 2 ? &u : &v; }      /* addQuantity order F8:883-886 */
+    float nextRandom() { return rng_uniform(cfg.rng_seed, rngCounter++); }
+    bool pointInBody(double x, double y) const {                                       /* F8:1564 */
+        for (const Body& b : bodies) if (b.distance(x * hx, y * hx) < 0.0) return true;
+        return false;
+    }
+    /* F8:1571: _AvgPerCell tries per cell, rejected ones are dropped; x + (float) random() is a FLOAT addition */
+    void initParticles() {
+        int idx = 0;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++)
+                for (int i = 0; i < cfg.particles_avg_per_cell; i++, idx++) {
+                    posX[idx] = (double)((float)x + nextRandom());
+                    posY[idx] = (double)((float)y + nextRandom());
+                    if (pointInBody(posX[idx], posY[idx])) idx--;
+                }
+        particleCount = idx;
+    }
+    void countParticles() {                                                            /* F8:1595 */
+        std::fill(counts.begin(), counts.end(), 0);
+        for (int i = 0; i < particleCount; i++) {
+            int ix = jint(posX[i]), iy = jint(posY[i]);
+            if (ix >= 0 && iy >= 0 && ix < w && iy < h) counts[(size_t)ix + (size_t)iy * w]++;
+        }
+    }
+    void pruneParticles() {                                                            /* F8:1610 (the range guard uses && and never fires) */
+        for (int i = 0; i < particleCount; i++) {
+            int ix = jint(posX[i]), iy = jint(posY[i]);
+            size_t idx = (size_t)ix + (size_t)iy * w;
+            if (counts[idx] > cfg.particles_max_per_cell) {
+                int j = --particleCount;
+                posX[i] = posX[j]; posY[i] = posY[j];
+                for (auto& pr : prop) pr[i] = pr[j];
+                counts[idx]--;
+                i--;
+            }
+        }
+    }
+    void seedParticles() {                                                             /* F8:1637 */
+        size_t idx = 0;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++, idx++)
+                for (int i = 0; i < cfg.particles_min_per_cell - counts[idx]; i++) {
+                    if (particleCount == maxParticles) return;
+                    int j = particleCount;
+                    posX[j] = (double)((float)x + nextRandom());
+                    posY[j] = (double)((float)y + nextRandom());
+                    if (pointInBody(posX[idx], posY[idx])) continue;                   /* F8:1653: tests particle `idx`, not j (kept) */
+                    for (int q = 0; q < 4; q++) prop[q][j] = qOf(q)->lerpGrid(posX[j], posY[j]);
+                    particleCount++;
+                }
+    }
+    Vec2 particleBackProject(double x, double y) const {                               /* F8:1673: threshold d < -1.0 (kept) */
+        double dd = 1e30;
+        int closest = -1;
+        for (size_t i = 0; i < bodies.size(); i++) {
+            double id = bodies[i].distance(x * hx, y * hx);
+            if (id < dd) { dd = id; closest = (int)i; }
+        }
+        if (dd < -1.0) {
+            x *= hx; y *= hx;
+            Vec2 r = bodies[closest].closestSurfacePoint(x, y);
+            x = r.x; y = r.y;
+            Vec2 n = bodies[closest].distanceNormal(x, y);
+            x -= n.x * hx; y -= n.y * hx;
+            x /= hx; y /= hx;
+        }
+        return {x, y};
+    }
+    Vec2 particleRK3(double x, double y, double timestep) const {                      /* F8:1708: forward in time */
+        double firstU = u.lerpGrid(x, y) / hx;
+        double firstV = v.lerpGrid(x, y) / hx;
+        double midX = x + 0.5 * timestep * firstU;
+        double midY = y + 0.5 * timestep * firstV;
+        double midU = u.lerpGrid(midX, midY) / hx;
+        double midV = v.lerpGrid(midX, midY) / hx;
+        double lastX = x + 0.75 * timestep * midU;
+        double lastY = y + 0.75 * timestep * midV;
+        double lastU = u.lerpGrid(lastX, lastY);
+        double lastV = v.lerpGrid(lastX, lastY);
+        x += timestep * ((2.0 / 9.0) * firstU + (3.0 / 9.0) * midU + (4.0 / 9.0) * lastU);
+        y += timestep * ((2.0 / 9.0) * firstV + (3.0 / 9.0) * midV + (4.0 / 9.0) * lastV);
+        return {x, y};
+    }
+    void gridToParticles(double alpha) {                                               /* F8:1748 */
+        for (int q = 0; q < 4; q++)
+            for (int i = 0; i < particleCount; i++) {
+                prop[q][i] *= 1.0 - alpha;
+                prop[q][i] += qOf(q)->lerpGrid(posX[i], posY[i]);
+            }
+    }
+    void particlesToGrid() {                                                           /* F8:1761 */
+        for (int q = 0; q < 4; q++) {
+            qOf(q)->fromParticles(particleCount, posX, posY, prop[q]);
+            qOf(q)->extrapolateFlip();
+        }
+        countParticles();
+        pruneParticles();
+        seedParticles();
+        st.particle_count = particleCount;
+    }
+    void advectParticles(double timestep) {                                            /* F8:1778 */
+        for (int i = 0; i < particleCount; i++) {
+            Vec2 r = particleRK3(posX[i], posY[i], timestep);
+            r = particleBackProject(r.x, r.y);
+            posX[i] = jmax(jmin(r.x, w - 0.001), 0.0);
+            posY[i] = jmax(jmin(r.y, h - 0.001), 0.0);
+        }
+    }
+    /* the part of the F8 constructor that needs the body list: ParticleQuantities ctor + gridToParticles(1.0) (F8:887-891) */
+    void ensureParticles() {
+        if (particlesReady) return;
+        initParticles();
+        gridToParticles(1.0);
+        particlesReady = true;
+        st.particle_count = particleCount;
+    }
+    void heatSolveFlip(double timestep) {
+        r = t.src;
+        buildHeatDiffusionMatrix(timestep);
+        buildPreconditionerSolid();
+        projectPCGSolid(cfg.solver_limit, st.iterations_heat, st.residual_heat, 2);
+        t.src = p;
+    }
+    /* F8:1306 */
+    void updateFlip(double timestep) {
+        ensureParticles();
+        fillSolidFieldsAll();
+        particlesToGrid();
+        d.copyOld(); t.copyOld(); u.copyOld(); v.copyOld();
+        addInflow(inflow[0], inflow[1], inflow[2], inflow[3], inflow[4], inflow[5], inflow[6], inflow[7]);   /* F8:1330 */
+        heatSolveFlip(timestep);
+        t.extrapolateFlip();
+        addBuoyancy(timestep);
+        setBoundaryCondition();
+        buildRhsSolid();
+        computeDensities();
+        buildPressureMatrixSolid(timestep);
+        buildPreconditionerSolid();
+        projectPCGSolid(cfg.solver_limit, st.iterations_pressure, st.residual_pressure, 1);
+        applyPressureSolid(timestep);
+        d.extrapolateFlip(); u.extrapolateFlip(); v.extrapolateFlip();
+        setBoundaryCondition();
+        const double a = cfg.flip_alpha;
+        d.diff(a); t.diff(a); u.diff(a); v.diff(a);
+        gridToParticles(a);
+        d.undiff(a); t.undiff(a); u.undiff(a); v.undiff(a);
+        advectParticles(timestep);
+    }
+
     void project(double timestep) {
         if (variant >= IFL_F4_SOLID_BOUNDARIES) { projectPCGSolid(cfg.solver_limit, st.iterations_pressure, st.residual_pressure, 1); return; }
         if (usesPcg()) projectPCG(cfg.solver_limit, st.iterations_pressure, st.residual_pressure, 1);
@@ -934,6 +1232,7 @@ struct Solver {
 
     /* F1:276 / F2:322 / F3:361 */
     void update(double timestep) {
+        if (variant == IFL_F8_FLIP) { updateFlip(timestep); return; }
         if (variant >= IFL_F4_SOLID_BOUNDARIES) { updateSolid(timestep); return; }
         buildRhs();
         if (usesPcg()) { buildPressureMatrix(timestep); buildPreconditioner(); }
@@ -1003,7 +1302,7 @@ extern "C" {
 
 int ifo_create(const ifl_config* cfg, void** out) {
     if (!cfg || !out || cfg->w < 2 || cfg->h < 2) return IFL_ERR_INVALID;
-    if (cfg->variant < IFL_F1_MATRIXLESS || cfg->variant > IFL_F7_VARIABLE_DENSITY) return IFL_ERR_UNSUPPORTED;
+    if (cfg->variant < IFL_F1_MATRIXLESS || cfg->variant > IFL_F8_FLIP) return IFL_ERR_UNSUPPORTED;
     *out = new Solver(*cfg);
     return IFL_OK;
 }
@@ -1017,7 +1316,44 @@ int ifo_set_bodies(void* h, const ifl_body* bodies, int32_t count) {
     return IFL_OK;
 }
 int ifo_add_inflow(void* h, double x, double y, double w, double hh, double d, double t, double u, double v) {
-    ((Solver*)h)->addInflow(x, y, w, hh, d, t, u, v);
+    Solver* s = (Solver*)h;
+    if (s->variant == IFL_F8_FLIP) {           /* F8 calls addInflow inside update() (F8:1330): this sets that rectangle */
+        double r[8] = {x, y, w, hh, d, t, u, v};
+        std::memcpy(s->inflow, r, sizeof r);
+        return IFL_OK;
+    }
+    s->addInflow(x, y, w, hh, d, t, u, v);
+    return IFL_OK;
+}
+int ifo_particle_count(void* h, int32_t* count) {
+    Solver* s = (Solver*)h;
+    if (s->variant != IFL_F8_FLIP) return IFL_ERR_UNSUPPORTED;
+    s->ensureParticles();
+    *count = s->particleCount;
+    return IFL_OK;
+}
+int ifo_read_particles(void* h, double* px, double* py, double* pd, double* pt, double* pu, double* pv, size_t capacity) {
+    Solver* s = (Solver*)h;
+    if (s->variant != IFL_F8_FLIP) return IFL_ERR_UNSUPPORTED;
+    s->ensureParticles();
+    if (capacity < (size_t)s->particleCount) return IFL_ERR_INVALID;
+    size_t n = (size_t)s->particleCount * sizeof(double);
+    std::memcpy(px, s->posX.data(), n); std::memcpy(py, s->posY.data(), n);
+    std::memcpy(pd, s->prop[0].data(), n); std::memcpy(pt, s->prop[1].data(), n);
+    std::memcpy(pu, s->prop[2].data(), n); std::memcpy(pv, s->prop[3].data(), n);
+    return IFL_OK;
+}
+int ifo_write_particles(void* h, const double* px, const double* py, const double* pd, const double* pt, const double* pu,
+                        const double* pv, size_t count) {
+    Solver* s = (Solver*)h;
+    if (s->variant != IFL_F8_FLIP || count > (size_t)s->maxParticles) return IFL_ERR_INVALID;
+    size_t n = count * sizeof(double);
+    std::memcpy(s->posX.data(), px, n); std::memcpy(s->posY.data(), py, n);
+    std::memcpy(s->prop[0].data(), pd, n); std::memcpy(s->prop[1].data(), pt, n);
+    std::memcpy(s->prop[2].data(), pu, n); std::memcpy(s->prop[3].data(), pv, n);
+    s->particleCount = (int)count;
+    s->particlesReady = true;
+    s->st.particle_count = s->particleCount;
     return IFL_OK;
 }
 int ifo_update(void* h, double dt, ifl_step_status* st) {
@@ -1039,7 +1375,7 @@ int ifo_run_steps(void* h, int n, double dt, double x, double y, double w, doubl
 }
 int ifo_run_stage(void* h, int stage, double dt, ifl_step_status* st) {
     Solver* s = (Solver*)h;
-    const bool solids = s->variant >= IFL_F4_SOLID_BOUNDARIES, heat = s->variant >= IFL_F6_HEAT;
+    const bool solids = s->variant >= IFL_F4_SOLID_BOUNDARIES, heat = s->variant >= IFL_F6_HEAT, flip = s->variant == IFL_F8_FLIP;
     auto adv = [&](Quantity& q) { if (solids) q.advectMasked(dt, s->u, s->v, s->bodies); else q.advect(s->variant, dt, s->u, s->v); };
     switch (stage) {
         case IFL_STAGE_BUILD_RHS: if (solids) s->buildRhsSolid(); else s->buildRhs(); break;
@@ -1051,21 +1387,32 @@ int ifo_run_stage(void* h, int stage, double dt, ifl_step_status* st) {
             if (solids) s->buildPreconditionerSolid(); else s->buildPreconditioner(); break;
         case IFL_STAGE_PROJECT: s->project(dt); break;
         case IFL_STAGE_APPLY_PRESSURE: if (solids) s->applyPressureSolid(dt); else s->applyPressure(dt); break;
-        case IFL_STAGE_ADVECT_D: adv(s->d); break;
-        case IFL_STAGE_ADVECT_T: if (!heat) return IFL_ERR_UNSUPPORTED; adv(s->t); break;
-        case IFL_STAGE_ADVECT_U: adv(s->u); break;
-        case IFL_STAGE_ADVECT_V: adv(s->v); break;
-        case IFL_STAGE_SWAP: s->d.swap(); s->u.swap(); s->v.swap(); if (heat) s->t.swap(); break;
+        case IFL_STAGE_ADVECT_D: if (flip) return IFL_ERR_UNSUPPORTED; adv(s->d); break;
+        case IFL_STAGE_ADVECT_T: if (!heat || flip) return IFL_ERR_UNSUPPORTED; adv(s->t); break;
+        case IFL_STAGE_ADVECT_U: if (flip) return IFL_ERR_UNSUPPORTED; adv(s->u); break;
+        case IFL_STAGE_ADVECT_V: if (flip) return IFL_ERR_UNSUPPORTED; adv(s->v); break;
+        case IFL_STAGE_SWAP: if (flip) return IFL_ERR_UNSUPPORTED; s->d.swap(); s->u.swap(); s->v.swap(); if (heat) s->t.swap(); break;
         case IFL_STAGE_APPLY_PRECON:
             if (!s->usesPcg()) return IFL_ERR_UNSUPPORTED;
             if (solids) s->applyPreconditionerSolid(s->z, s->r); else s->applyPreconditioner(s->z, s->r); break;
         case IFL_STAGE_MATVEC: if (!s->usesPcg()) return IFL_ERR_UNSUPPORTED; s->matrixVectorProduct(s->z, s->s); break;
         case IFL_STAGE_FILL_SOLID_FIELDS: if (!solids) return IFL_ERR_UNSUPPORTED; s->fillSolidFieldsAll(); break;
         case IFL_STAGE_SET_BOUNDARY: if (!solids) return IFL_ERR_UNSUPPORTED; s->setBoundaryCondition(); break;
-        case IFL_STAGE_EXTRAPOLATE_D: if (!solids) return IFL_ERR_UNSUPPORTED; s->d.extrapolate(); break;
-        case IFL_STAGE_EXTRAPOLATE_T: if (!heat) return IFL_ERR_UNSUPPORTED; s->t.extrapolate(); break;
-        case IFL_STAGE_EXTRAPOLATE_U: if (!solids) return IFL_ERR_UNSUPPORTED; s->u.extrapolate(); break;
-        case IFL_STAGE_EXTRAPOLATE_V: if (!solids) return IFL_ERR_UNSUPPORTED; s->v.extrapolate(); break;
+        case IFL_STAGE_EXTRAPOLATE_D: if (!solids) return IFL_ERR_UNSUPPORTED; if (flip) s->d.extrapolateFlip(); else s->d.extrapolate(); break;
+        case IFL_STAGE_EXTRAPOLATE_T: if (!heat) return IFL_ERR_UNSUPPORTED; if (flip) s->t.extrapolateFlip(); else s->t.extrapolate(); break;
+        case IFL_STAGE_EXTRAPOLATE_U: if (!solids) return IFL_ERR_UNSUPPORTED; if (flip) s->u.extrapolateFlip(); else s->u.extrapolate(); break;
+        case IFL_STAGE_EXTRAPOLATE_V: if (!solids) return IFL_ERR_UNSUPPORTED; if (flip) s->v.extrapolateFlip(); else s->v.extrapolate(); break;
+        case IFL_STAGE_PARTICLES_TO_GRID: if (!flip) return IFL_ERR_UNSUPPORTED; s->ensureParticles(); s->particlesToGrid(); break;
+        case IFL_STAGE_GRID_TO_PARTICLES: {
+            if (!flip) return IFL_ERR_UNSUPPORTED;
+            s->ensureParticles();
+            const double a = s->cfg.flip_alpha;
+            s->d.diff(a); s->t.diff(a); s->u.diff(a); s->v.diff(a);
+            s->gridToParticles(a);
+            s->d.undiff(a); s->t.undiff(a); s->u.undiff(a); s->v.undiff(a);
+            break;
+        }
+        case IFL_STAGE_ADVECT_PARTICLES: if (!flip) return IFL_ERR_UNSUPPORTED; s->ensureParticles(); s->advectParticles(dt); break;
         case IFL_STAGE_HEAT_SOLVE: if (!heat) return IFL_ERR_UNSUPPORTED; s->heatSolve(dt); break;
         case IFL_STAGE_ADD_BUOYANCY: if (!heat) return IFL_ERR_UNSUPPORTED; s->addBuoyancy(dt); break;
         case IFL_STAGE_COMPUTE_DENSITIES: if (s->variant < IFL_F7_VARIABLE_DENSITY) return IFL_ERR_UNSUPPORTED; s->computeDensities(); break;

@@ -24,16 +24,23 @@ def cases(abi):
     for name, v in (("f4", abi.F4_SOLID_BOUNDARIES), ("f5", abi.F5_CURVED_BOUNDARIES), ("f6", abi.F6_HEAT), ("f7", abi.F7_VARIABLE_DENSITY)):
         spec, rect, kw = scenes.solid_scene(abi, v)
         yield name, v, spec, rect, kw
+    # F8 main() (F8:72-86): inflow lives inside update(), dt = 0.0025, soot 0.25
+    yield "f8", abi.F8_FLIP, scenes.F7_BODIES, None, {}
 
 
 def run_case(abi, variant, spec, rect, kw, solver_factory):
     s = solver_factory(variant, spec, kw)
     its = []
+    flip = variant == abi.F8_FLIP
     for _ in range(STEPS):
-        s.add_inflow(*rect)
-        st = s.update(scenes.DT)
+        if rect is not None:
+            s.add_inflow(*rect)
+        st = s.update(0.0025 if flip else scenes.DT)
         its.append((st["iterations_heat"], st["iterations_pressure"]))
     out = {"iterations": np.array(its, dtype=np.int32)}
+    if flip:
+        for k, v in s.read_particles().items():
+            out["particle_" + k] = v
     for n in ["d", "u", "v", "p"] + (["t"] if variant >= abi.F6_HEAT else []):
         out[n] = s.read(n)
     return out

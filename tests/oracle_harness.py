@@ -39,6 +39,9 @@ def _load(abi):
         "ifo_field_size": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_size_t)]),
         "ifo_read_field": (C.c_int, [C.c_void_p, C.c_int32, dp, C.c_size_t]),
         "ifo_write_field": (C.c_int, [C.c_void_p, C.c_int32, dp, C.c_size_t]),
+        "ifo_particle_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+        "ifo_read_particles": (C.c_int, [C.c_void_p] + [dp] * 6 + [C.c_size_t]),
+        "ifo_write_particles": (C.c_int, [C.c_void_p] + [dp] * 6 + [C.c_size_t]),
         "ifo_lerp": (C.c_double, [C.c_double] * 3),
         "ifo_cerp": (C.c_double, [C.c_double] * 5),
         "ifo_cubic_pulse": (C.c_double, [C.c_double]),
@@ -124,6 +127,25 @@ class OracleSolver:
         arr = np.ascontiguousarray(arr, dtype=np.float64).ravel()
         rc = self.lib.ifo_write_field(self.h, self.abi.FIELDS[name], arr.ctypes.data_as(C.POINTER(C.c_double)), arr.size)
         assert rc == 0, (name, rc)
+
+    def particle_count(self):
+        n = C.c_int32()
+        assert self.lib.ifo_particle_count(self.h, C.byref(n)) == 0
+        return n.value
+
+    def read_particles(self):
+        n = self.particle_count()
+        arrs = [np.empty(n, dtype=np.float64) for _ in range(6)]
+        dp = C.POINTER(C.c_double)
+        rc = self.lib.ifo_read_particles(self.h, *[a.ctypes.data_as(dp) for a in arrs], n)
+        assert rc == 0, rc
+        return dict(zip(("x", "y", "d", "t", "u", "v"), arrs))
+
+    def write_particles(self, parts):
+        dp = C.POINTER(C.c_double)
+        arrs = [np.ascontiguousarray(parts[k], dtype=np.float64) for k in ("x", "y", "d", "t", "u", "v")]
+        rc = self.lib.ifo_write_particles(self.h, *[a.ctypes.data_as(dp) for a in arrs], arrs[0].size)
+        assert rc == 0, rc
 
     def dot(self, a, b):
         return self.lib.ifo_dot(self.h, self.abi.FIELDS[a], self.abi.FIELDS[b])

@@ -29,7 +29,7 @@ def check(got, want, name):
         assert np.array_equal(got[k], want[k]), (name, k)
 
 
-@pytest.mark.parametrize("idx", range(7))
+@pytest.mark.parametrize("idx", range(8))
 def test_oracle_reproduces_golden(abi, oracle_cls, ifl, idx):
     name, variant, spec, rect, kw = case_list(abi)[idx]
 
@@ -42,14 +42,14 @@ def test_oracle_reproduces_golden(abi, oracle_cls, ifl, idx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("idx", range(7))
+@pytest.mark.parametrize("idx", range(8))
 def test_cuda_strict_mode_reproduces_golden(abi, ifl, idx):
     name, variant, spec, rect, kw = case_list(abi)[idx]
 
     def factory(variant, spec, kw):
         kw = dict(kw, flags=abi.FLAG_SEQUENTIAL_REDUCTIONS)
         if variant >= abi.F6_HEAT:
-            return ifl.FluidSolver(make_golden.W, make_golden.H, scenes.DENSITY, kw.pop("density_soot"), 0.01,
+            return ifl.FluidSolver(make_golden.W, make_golden.H, scenes.DENSITY, kw.pop("density_soot", 0.25), 0.01,
                                    scenes.make_bodies(ifl, spec), variant=variant, **kw)
         if variant >= abi.F4_SOLID_BOUNDARIES:
             return ifl.FluidSolver(make_golden.W, make_golden.H, scenes.DENSITY, scenes.make_bodies(ifl, spec), variant=variant, **kw)
