@@ -190,6 +190,12 @@ typedef struct ifl_solver ifl_solver;   /* opaque */
 /* Fill *cfg with the reference literals for `variant` at grid w x h. */
 int ifl_default_config(ifl_config* cfg, int32_t variant, int32_t w, int32_t h);
 
+/* Slab decomposition (the reference has no distributed path).  Rank 0 obtains a 128-byte id
+ * (an ncclUniqueId), the host program broadcasts it to the other ranks by any means, and every rank passes it in
+ * ifl_config.comm_id together with its rank / world_size.  One process per GPU.  Rank r owns the 32-row strips
+ * [r*chunk, (r+1)*chunk) of the pressure solve; everything outside the solve is computed redundantly per rank. */
+int ifl_comm_unique_id(uint8_t out[128]);
+
 /* new FluidSolver(...)  -- F1:262 F3:339 F4:594 F6:763 F7:769 F8:858 */
 int ifl_create(const ifl_config* cfg, ifl_solver** out);
 void ifl_destroy(ifl_solver* s);

@@ -106,6 +106,7 @@ PROTOTYPES = {
     "ifl_last_timing": (C.c_int, [C.c_void_p, _dp]),
     "ifl_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "ifl_kernel_timing": (C.c_int, [C.c_void_p, C.c_int32, _dp, C.POINTER(C.c_int32)]),
+    "ifl_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "ifl_wavefront_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_size_t]),
     "ifl_last_error": (C.c_char_p, []),
     "ifl_abi_version": (C.c_int, []),

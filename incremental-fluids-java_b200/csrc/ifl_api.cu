@@ -70,6 +70,7 @@ struct ifl_solver {
     SolveScalars* h_sc_heat = nullptr;
     /* F8 */
     FlipCtx flip;
+    Comm comm;
     double inflow[8] = {0.45, 0.2, 0.2, 0.05, 1.0, 294.0, 0.0, 0.0};   /* F8:1330 */
 };
 
@@ -82,6 +83,12 @@ static bool is_flip(const ifl_solver* s) { return s->cfg.variant == IFL_F8_FLIP;
 extern "C" {
 
 int ifl_abi_version(void) { return IFL_ABI_VERSION; }
+
+int ifl_comm_unique_id(uint8_t out[128]) {
+    if (!out) INVALID("NULL argument");
+    if (comm_unique_id(out)) { snprintf(g_err, sizeof g_err, "%s", comm_last_error()); return IFL_ERR_COMM; }
+    return IFL_OK;
+}
 const char* ifl_last_error(void) { return g_err; }
 
 int ifl_default_config(ifl_config* cfg, int32_t variant, int32_t w, int32_t h) {
@@ -157,10 +164,12 @@ void ifl_destroy(ifl_solver* s) {
     if (s->scratch) cudaFree(s->scratch);
     if (s->sx.pack_f) cudaFree(s->sx.pack_f);
     if (s->sx.pack_b) cudaFree(s->sx.pack_b);
+    comm_destroy(s->comm);
     if (s->sx.bnd_f) cudaFree(s->sx.bnd_f);
-    if (s->sx.bnd_b) cudaFree(s->sx.bnd_b);
+    if (s->sx.strip_part) cudaFree(s->sx.strip_part);
+    if (s->sx.rank_max) cudaFree(s->sx.rank_max);
+    if (s->sx.rowbuf) cudaFree(s->sx.rowbuf);
     if (s->sx.partials) cudaFree(s->sx.partials);
-    if (s->sx.stripdot) cudaFree(s->sx.stripdot);
     if (s->sx.sc) cudaFree(s->sx.sc);
     if (s->d_maxbits) cudaFree(s->d_maxbits);
     if (s->h_sc) cudaFreeHost(s->h_sc);
@@ -210,7 +219,13 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     g.nstrips = (s->h + 31) / 32;
     g.tl = ((s->w + 31 + 15) / 16) * 16 + 16;
     g.ss = (long long)g.tl * 32;
-    g.total = (long long)g.nstrips * g.ss;
+    /* slab decomposition: rank r owns the strips [r*chunk, min((r+1)*chunk, nstrips)); arrays hold chunk*world strips */
+    const int world = cfg->world_size;
+    const int chunk = (g.nstrips + world - 1) / world;
+    const int strips_alloc = chunk * world;
+    g.s0 = cfg->rank * chunk;
+    g.s1 = g.s0 + chunk < g.nstrips ? g.s0 + chunk : g.nstrips;
+    g.total = (long long)strips_alloc * g.ss;
     /* one all-zero strip before and after each vector: the wavefront kernels read the
      * "row above the first" / "row below the last" from there instead of branching */
     const size_t guard = (size_t)g.ss;
@@ -219,17 +234,39 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     CU(cudaMemset(s->skew_block, 0, sizeof(double) * per * 8));
     double** vecs[8] = {&s->sx.r, &s->sx.p, &s->sx.z, &s->sx.s, &s->sx.adiag, &s->sx.aplusx, &s->sx.aplusy, &s->sx.precon};
     for (int i = 0; i < 8; i++) *vecs[i] = s->skew_block + per * i + guard;
-    const size_t npack = (size_t)g.nstrips * g.tl * 32 * 3;
+    const size_t npack = (size_t)strips_alloc * g.tl * 32 * 3;
     CU(cudaMalloc(&s->sx.pack_f, sizeof(double) * npack));
     CU(cudaMalloc(&s->sx.pack_b, sizeof(double) * npack));
     CU(cudaMemset(s->sx.pack_f, 0, sizeof(double) * npack));
     CU(cudaMemset(s->sx.pack_b, 0, sizeof(double) * npack));
-    size_t nb = (size_t)g.nstrips * g.w;
-    CU(cudaMalloc(&s->sx.bnd_f, sizeof(double) * nb));
-    CU(cudaMalloc(&s->sx.bnd_b, sizeof(double) * nb));
+    /* both boundary-row sets in ONE allocation: it is the inbox the neighbour ranks map through CUDA IPC */
+    size_t nb = (size_t)strips_alloc * g.w;
+    CU(cudaMalloc(&s->sx.bnd_f, sizeof(double) * nb * 2));
+    s->sx.bnd_b = s->sx.bnd_f + nb;
+    s->sx.strips_alloc = strips_alloc;
+    CU(cudaMalloc(&s->sx.strip_part, sizeof(double) * strips_alloc));
+    CU(cudaMemset(s->sx.strip_part, 0, sizeof(double) * strips_alloc));
+    CU(cudaMalloc(&s->sx.rank_max, sizeof(unsigned long long) * (world > 16 ? world : 16) * 8));
+    CU(cudaMemset(s->sx.rank_max, 0, sizeof(unsigned long long) * (world > 16 ? world : 16) * 8));
+    CU(cudaMalloc(&s->sx.rowbuf, sizeof(double) * 4 * g.w));
+    s->sx.comm = nullptr; s->sx.peer_bnd_f_next = nullptr; s->sx.peer_bnd_b_prev = nullptr;
+    if (world > 1) {
+        if (comm_init(s->comm, cfg->rank, world, cfg->comm_id, s->stream)) {
+            snprintf(g_err, sizeof g_err, "%s", comm_last_error());
+            return IFL_ERR_COMM;
+        }
+        if (comm_map_neighbour_inboxes(s->comm, s->sx.bnd_f, s->sx.rank_max)) {
+            snprintf(g_err, sizeof g_err, "%s", comm_last_error());
+            return IFL_ERR_COMM;
+        }
+        s->sx.comm = &s->comm;
+        if (s->comm.peer_next_base) s->sx.peer_bnd_f_next = (double*)s->comm.peer_next_base;
+        if (s->comm.peer_prev_base) s->sx.peer_bnd_b_prev = (double*)s->comm.peer_prev_base + nb;
+        CU(cudaMemset(s->sx.rank_max, 0, sizeof(unsigned long long) * (world > 16 ? world : 16) * 8));
+    }
     s->sx.npartials = solve_partials_needed(g);
     CU(cudaMalloc(&s->sx.partials, sizeof(double) * s->sx.npartials));
-    CU(cudaMalloc(&s->sx.stripdot, sizeof(double) * g.nstrips));
+    s->sx.stripdot = nullptr;
     CU(cudaMalloc(&s->sx.sc, sizeof(SolveScalars)));
     CU(cudaMemset(s->sx.sc, 0, sizeof(SolveScalars)));
     CU(cudaMalloc(&s->d_maxbits, sizeof(unsigned long long)));
@@ -264,9 +301,14 @@ int ifl_create(const ifl_config* cfg, ifl_solver** out) {
     if (cfg->abi_version != IFL_ABI_VERSION) INVALID("abi_version mismatch");
     if (cfg->w < 2 || cfg->h < 2) INVALID("grid must be at least 2x2");
     if (cfg->variant < IFL_F1_MATRIXLESS || cfg->variant > IFL_F8_FLIP) INVALID("unknown variant");
-    if (cfg->world_size != 1) {
-        snprintf(g_err, sizeof g_err, "slab decomposition (world_size=%d) is not implemented by this build", cfg->world_size);
-        return IFL_ERR_UNSUPPORTED;
+    if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) INVALID("bad rank / world_size");
+    if (cfg->world_size > 1) {
+        if (cfg->variant != IFL_F3_CONJUGATE_GRADIENTS) {
+            snprintf(g_err, sizeof g_err, "slab decomposition is implemented for variant 3 (MIC(0)-PCG), not for variant %d", cfg->variant);
+            return IFL_ERR_UNSUPPORTED;
+        }
+        if (cfg->flags & IFL_FLAG_SEQUENTIAL_REDUCTIONS) INVALID("IFL_FLAG_SEQUENTIAL_REDUCTIONS is single-GPU only");
+        if ((cfg->h + 31) / 32 < cfg->world_size) INVALID("fewer 32-row strips than ranks");
     }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);

@@ -70,6 +70,7 @@ struct SkewGeom {
     int tl;             /* t-rows per strip */
     long long ss;       /* strip stride in elements = tl * 32 */
     long long total;    /* nstrips * ss */
+    int s0, s1;         /* strips owned by this rank (slab decomposition); [0, nstrips) on a single GPU */
 };
 __device__ __host__ __forceinline__ long long skew_index(const SkewGeom& g, int x, int y) {
     int l = y & 31;

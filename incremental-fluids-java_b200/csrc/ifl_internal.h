@@ -56,6 +56,22 @@ struct SolveScalars {
     int pad;
 };
 
+/* slab decomposition (ifl_comm.cu): rank r owns the strips [s0, s1) of the pressure solve */
+struct Comm {
+    int rank = 0, world = 1;
+    void* nccl = nullptr;             /* ncclComm_t */
+    cudaStream_t stream = nullptr;
+    void* peer_prev_base = nullptr;   /* IPC mapping of rank-1's / rank+1's inbox allocation (bnd_f | bnd_b) */
+    void* peer_next_base = nullptr;
+};
+const char* comm_last_error();
+int comm_unique_id(unsigned char out[128]);
+int comm_init(Comm& c, int rank, int world, const unsigned char id_bytes[128], cudaStream_t st);
+void comm_destroy(Comm& c);
+int comm_map_neighbour_inboxes(Comm& c, void* inbox_base, void* scratch_dev);
+int comm_all_gather(Comm& c, const void* send, void* recv, size_t bytes_per_rank);
+int comm_exchange_rows(Comm& c, const double* send_up, double* recv_up, const double* send_down, double* recv_down, size_t n);
+
 /* event-sampled kernel timing (ifl_set_profiling / ifl_kernel_timing) */
 struct Profiler {
     static const int NS = 128;        /* samples kept */
@@ -88,6 +104,14 @@ struct SolveCtx {
     cudaStream_t stream;
     unsigned long long* launches;
     Profiler* prof;
+    /* slab decomposition */
+    Comm* comm;              /* nullptr on a single GPU */
+    double* peer_bnd_f_next; /* rank+1's forward inbox (its bnd_f), IPC mapped */
+    double* peer_bnd_b_prev; /* rank-1's backward inbox (its bnd_b) */
+    double* rowbuf;          /* 4 packed rows of w doubles: send up, send down, recv up, recv down */
+    double* strip_part;      /* per-strip partial sums, [strips_alloc] */
+    unsigned long long* rank_max;   /* per-rank max bits, [world] */
+    int strips_alloc;        /* chunk * world >= nstrips */
     long long* trace;     /* diagnostic: per-strip timestamps of the next apply_precon, or nullptr */
 };
 

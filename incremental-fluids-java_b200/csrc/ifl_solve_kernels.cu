@@ -30,14 +30,16 @@ static constexpr int EW_TROWS = 64;    /* t-rows per element-wise block: 2048 el
 static constexpr int WF_WARPS = 4;     /* strips (warps) per wavefront block */
 static constexpr int WF_U = 8;         /* register prefetch distance in steps */
 
-static dim3 ew_grid(const SkewGeom& g) { return dim3((g.tl + EW_TROWS - 1) / EW_TROWS, g.nstrips); }
-int solve_partials_needed(const SkewGeom& g) { dim3 d = ew_grid(g); return (int)(d.x * d.y); }
+static dim3 ew_grid(const SkewGeom& g) { return dim3((g.tl + EW_TROWS - 1) / EW_TROWS, g.s1 - g.s0); }
+int solve_partials_needed(const SkewGeom& g) { return (int)(((g.tl + EW_TROWS - 1) / EW_TROWS) * g.nstrips); }
 static inline void count(SolveCtx& c, int n = 1) { if (c.launches) *c.launches += n; }
+static inline SkewGeom full_geom(const SkewGeom& g) { SkewGeom f = g; f.s0 = 0; f.s1 = g.nstrips; return f; }
+static inline int single_gpu(const SolveCtx& c) { return c.comm == nullptr; }
 
 /* iteration helper of the element-wise kernels: thread handles 8 elements, t-rows
  * t0 + e*8 + warp, lane = l.  Visits in a fixed order (e ascending). */
 #define IFL_EW_LOOP_BEGIN(g)                                                            \
-    const int k_ = blockIdx.y;                                                          \
+    const int k_ = blockIdx.y + (g).s0;                                                 \
     const long long base_ = (long long)k_ * (g).ss;                                     \
     const int l_ = threadIdx.x & 31;                                                    \
     const int y_ = k_ * 32 + l_;                                                        \
@@ -64,10 +66,13 @@ __device__ __forceinline__ void apply_dot_result(SolveScalars* sc, int mode, dou
     }
 }
 
-/* "last block" reduction of per-block partials in a fixed order */
-__device__ __forceinline__ void finish_partials(double blocksum, double* partials, int nblocks,
-                                                SolveScalars* sc, int mode, double* smem8, bool* s_last) {
+/* "last block" reduction, fixed order and independent of the slab decomposition: the partials of the blocks of one
+ * strip are added in block order (per-strip sum), then the strips are added in global strip order.  On several GPUs
+ * the second level runs in k_apply_dot after the per-strip sums of all ranks have been all-gathered. */
+__device__ __forceinline__ void finish_partials(double blocksum, double* partials, const SkewGeom& g, double* strip_part,
+                                                SolveScalars* sc, int mode, int single_gpu, bool* s_last) {
     const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    const int nblocks = gridDim.x * gridDim.y;
     if (threadIdx.x == 0) {
         partials[bid] = blocksum;
         __threadfence();
@@ -77,21 +82,49 @@ __device__ __forceinline__ void finish_partials(double blocksum, double* partial
     __syncthreads();
     if (*s_last) {
         __threadfence();
-        double v = 0.0;
-        for (int j = threadIdx.x; j < nblocks; j += EW_THREADS) v += ld_cg(partials + j);
-        double total = block_sum_256(v, smem8);
+        for (int ks = threadIdx.x; ks < (int)gridDim.y; ks += EW_THREADS) {
+            double v = 0.0;
+            for (int j = 0; j < (int)gridDim.x; j++) v += ld_cg(partials + ks * gridDim.x + j);
+            strip_part[g.s0 + ks] = v;
+        }
+        __syncthreads();
         if (threadIdx.x == 0) {
-            apply_dot_result(sc, mode, total);
+            if (single_gpu) {
+                double total = 0.0;
+                for (int kk = 0; kk < g.nstrips; kk++) total += strip_part[kk];
+                apply_dot_result(sc, mode, total);
+            }
             sc->ctr_a = 0;
         }
     }
+}
+/* second level of a distributed dot product: strips in global order (every rank computes the same bits) */
+__global__ void k_apply_dot(SkewGeom g, const double* __restrict__ strip_part, SolveScalars* sc, int mode, int check_done) {
+    if (check_done && sc->done) return;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double total = 0.0;
+    for (int kk = 0; kk < g.nstrips; kk++) total += strip_part[kk];
+    apply_dot_result(sc, mode, total);
+}
+/* convergence decision from the per-rank maxima (F3:609-619), identical on every rank */
+__global__ void k_apply_max(const unsigned long long* __restrict__ rank_max, int world, SolveScalars* sc, double tol, int init) {
+    if (!init && sc->done) return;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long mb = 0;
+    for (int r = 0; r < world; r++) mb = rank_max[r] > mb ? rank_max[r] : mb;
+    double err = (double)__uint_as_float((unsigned)mb);
+    sc->max_error = err;
+    sc->iterations = init ? 0 : sc->iterations + 1;
+    if (err < tol) sc->done = 1;
+    if (err != err) { sc->done = 1; sc->nan = 1; }
 }
 
 /* z = A s fused with the partial sums of z.s   (matrixVectorProduct F3:544, dotProduct F3:532) */
 __global__ void __launch_bounds__(EW_THREADS)
 k_matvec_dot(SkewGeom g, const double* __restrict__ adiag, const double* __restrict__ ax,
              const double* __restrict__ ay, const double* __restrict__ b, double* __restrict__ dst,
-             double* partials, SolveScalars* sc, int dot_mode, int check_done, const unsigned char* __restrict__ fl) {
+             double* partials, double* strip_part, SolveScalars* sc, int dot_mode, int check_done,
+             const unsigned char* __restrict__ fl, int single_gpu) {
     if (check_done && sc->done) return;
     __shared__ double smem8[8];
     __shared__ bool s_last;
@@ -116,7 +149,7 @@ k_matvec_dot(SkewGeom g, const double* __restrict__ adiag, const double* __restr
     IFL_EW_LOOP_END
     if (dot_mode == DOT_NONE) return;
     double bs = block_sum_256(acc, smem8);
-    finish_partials(bs, partials, gridDim.x * gridDim.y, sc, dot_mode, smem8, &s_last);
+    finish_partials(bs, partials, g, strip_part, sc, dot_mode, single_gpu, &s_last);
 }
 
 /* p += alpha s ; r -= alpha z ; maxError = infinityNorm(r)   (F3:606-608, scaledAdd F3:570,
@@ -125,7 +158,8 @@ k_matvec_dot(SkewGeom g, const double* __restrict__ adiag, const double* __restr
 __global__ void __launch_bounds__(EW_THREADS)
 k_update_pr(SkewGeom g, double* __restrict__ p, const double* __restrict__ s, double* __restrict__ r,
             const double* __restrict__ z, double* __restrict__ bnd_f, double* __restrict__ bnd_b,
-            SolveScalars* sc, double tol, const unsigned char* __restrict__ fl) {
+            SolveScalars* sc, double tol, const unsigned char* __restrict__ fl,
+            unsigned long long* rank_max, int rank, int single_gpu) {
     if (sc->done) return;
     __shared__ unsigned s_max[8];
     __shared__ bool s_last;
@@ -160,11 +194,15 @@ k_update_pr(SkewGeom g, double* __restrict__ p, const double* __restrict__ s, do
         if (s_last) {
             __threadfence();
             unsigned long long mb = atomicMax(&sc->max_bits, 0ull);
-            double err = (double)__uint_as_float((unsigned)mb);
-            sc->max_error = err;
-            sc->iterations = sc->iterations + 1;
-            if (err < tol) sc->done = 1;
-            if (err != err) { sc->done = 1; sc->nan = 1; }
+            if (single_gpu) {
+                double err = (double)__uint_as_float((unsigned)mb);
+                sc->max_error = err;
+                sc->iterations = sc->iterations + 1;
+                if (err < tol) sc->done = 1;
+                if (err != err) { sc->done = 1; sc->nan = 1; }
+            } else {
+                rank_max[rank] = mb;          /* decision after the all-gather, in k_apply_max */
+            }
             sc->max_bits = 0ull;
             sc->ctr_a = 0;
             sc->ctr_b = 0;
@@ -188,7 +226,8 @@ k_update_s(SkewGeom g, double* __restrict__ s, const double* __restrict__ z, Sol
 /* start of project(): s = z (arraycopy F3:596); maxError = infinityNorm(r) (F3:598) */
 __global__ void __launch_bounds__(EW_THREADS)
 k_init_s(SkewGeom g, double* __restrict__ s, const double* __restrict__ z, const double* __restrict__ r,
-         SolveScalars* sc, double tol, const unsigned char* __restrict__ fl) {
+         SolveScalars* sc, double tol, const unsigned char* __restrict__ fl,
+         unsigned long long* rank_max, int rank, int single_gpu) {
     __shared__ unsigned s_max[8];
     unsigned m = 0;
     IFL_EW_LOOP_BEGIN(g)
@@ -215,11 +254,15 @@ k_init_s(SkewGeom g, double* __restrict__ s, const double* __restrict__ z, const
         if (prev == gridDim.x * gridDim.y - 1u) {
             __threadfence();
             unsigned long long mb = atomicMax(&sc->max_bits, 0ull);
-            double err = (double)__uint_as_float((unsigned)mb);
-            sc->max_error = err;
-            sc->iterations = 0;
-            if (err < tol) sc->done = 1;
-            if (err != err) { sc->done = 1; sc->nan = 1; }
+            if (single_gpu) {
+                double err = (double)__uint_as_float((unsigned)mb);
+                sc->max_error = err;
+                sc->iterations = 0;
+                if (err < tol) sc->done = 1;
+                if (err != err) { sc->done = 1; sc->nan = 1; }
+            } else {
+                rank_max[rank] = mb;
+            }
             sc->max_bits = 0ull;
             sc->ctr_a = 0;
         }
@@ -354,9 +397,11 @@ struct RotFeed {
     }
     /* spin until the value of step j (column x) has arrived; re-reads all missing later ones too */
     __device__ __forceinline__ void wait(int j0, int x0, int dir) {
-        for (;;) {
-            bool ok = !is_sentinel(cur[j0]);
-            if (__all_sync(0xffffffffu, ok)) return;
+        /* bounded: a producer that never shows up (a dead peer rank) must not hang the GPU; after ~2^22 polls the
+         * strip gives up and continues with 0.0 -- the result is then wrong, which the callers' checks expose */
+        for (unsigned spins = 0;; spins++) {
+            bool ok = !is_sentinel(cur[j0]) || spins > (1u << 22);
+            if (__all_sync(0xffffffffu, ok)) { if (is_sentinel(cur[j0])) cur[j0] = 0.0; return; }
 #pragma unroll
             for (int j = 0; j < U; j++)
                 if (j >= j0 && is_sentinel(cur[j])) cur[j] = ld_volatile(row + x0 + dir * j);
@@ -494,7 +539,7 @@ __device__ __forceinline__ void sweep_steps(const double* tile_a, const double* 
 template <int DIR, bool WITH_DOT, bool MASKED>
 __global__ void __launch_bounds__(WF_WARPS * 32)
 k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restrict__ pack,
-               const double* __restrict__ rr, double* bnd, double* stripdot,
+               const double* __restrict__ rr, double* bnd, double* bnd_peer, double* stripdot,
                SolveScalars* sc, int dot_mode, int check_done, long long* trace) {
     constexpr int U = SW_U;
     constexpr int S = SW_STAGES;
@@ -502,9 +547,9 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     extern __shared__ __align__(128) unsigned char wf_smem[];
     if (check_done && sc->done) return;
     const long long tr_enter = trace ? (long long)globaltimer_ns() : 0;
-    const int slot = claim_slot(DIR > 0 ? &sc->ticket_f : &sc->ticket_b, g.nstrips);
+    const int slot = claim_slot(DIR > 0 ? &sc->ticket_f : &sc->ticket_b, g.s1 - g.s0);
     if (slot < 0) return;
-    const int k = DIR > 0 ? slot : g.nstrips - 1 - slot;
+    const int k = DIR > 0 ? g.s0 + slot : g.s1 - 1 - slot;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int y = k * 32 + lane;
@@ -541,7 +586,9 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     __syncwarp();
 
     double* pdst = dst + (long long)k * g.ss + lane + (long long)tfirst * 32;
-    double* pbnd = bnd + (long long)k * w + (tfirst - lane);   /* column x = t - lane of this strip's edge row */
+    /* outgoing edge row: the next strip's inbox -- in the neighbour GPU's memory for the last strip of a slab */
+    const bool to_peer = bnd_peer != nullptr && (DIR > 0 ? k == g.s1 - 1 : k == g.s0);
+    double* pbnd = (to_peer ? bnd_peer : bnd) + (long long)k * w + (tfirst - lane);   /* column x = t - lane */
 
     RotFeed<U> feed;
     feed.init(has_prev ? bnd + (long long)(k - DIR) * w : nullptr, w, lane == (DIR > 0 ? 31 : 0));
@@ -586,11 +633,13 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
             stripdot[k] = ws;
             __threadfence();
             unsigned prev = atomicAdd(&sc->ctr_b, 1u);
-            if (prev == (unsigned)g.nstrips - 1u) {
+            if (prev == (unsigned)(g.s1 - g.s0) - 1u) {
                 __threadfence();
-                double total = 0.0;
-                for (int kk = 0; kk < g.nstrips; kk++) total += ld_cg(stripdot + kk);
-                if (dot_mode != DOT_NONE) apply_dot_result(sc, dot_mode, total);
+                if (g.s1 - g.s0 == g.nstrips) {      /* single GPU: strips in order; otherwise k_apply_dot after the all-gather */
+                    double total = 0.0;
+                    for (int kk = 0; kk < g.nstrips; kk++) total += ld_cg(stripdot + kk);
+                    if (dot_mode != DOT_NONE) apply_dot_result(sc, dot_mode, total);
+                }
                 sc->ctr_b = 0;
             }
         }
@@ -790,6 +839,22 @@ k_gs_sweep(SkewGeom g, const double* __restrict__ r, double* p, double* bnd_use,
     }
 }
 
+/* slab decomposition: boundary rows of a skewed vector <-> packed rows.  rowbuf = [send up | send down | recv up | recv down] */
+__global__ void k_pack_rows(SkewGeom g, const double* __restrict__ vec, double* __restrict__ rowbuf) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= g.w) return;
+    rowbuf[x] = vec[skew_index(g, x, g.s0 * 32)];                                       /* my first row -> rank-1 */
+    int ylast = g.s1 * 32 - 1;
+    if (ylast > g.h - 1) ylast = g.h - 1;
+    rowbuf[g.w + x] = vec[skew_index(g, x, ylast)];                                     /* my last row -> rank+1 */
+}
+__global__ void k_unpack_rows(SkewGeom g, double* __restrict__ vec, const double* __restrict__ rowbuf, int has_up, int has_down) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= g.w) return;
+    if (has_up) vec[skew_index(g, x, g.s0 * 32 - 1)] = rowbuf[2 * g.w + x];             /* row above my slab */
+    if (has_down) vec[skew_index(g, x, g.s1 * 32)] = rowbuf[3 * g.w + x];               /* row below my slab */
+}
+
 /* ---------------------------------------------------------------------------------
  * host-side enqueue helpers
  * ------------------------------------------------------------------------------- */
@@ -804,7 +869,8 @@ void launch_build_precon(SolveCtx& c) {
     k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
     k_build_precon<<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.precon,
                                                                   c.bnd_f, c.sc, c.mic_tau, c.mic_sigma, c.fl);
-    k_precon_coeffs<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.aplusx, c.aplusy, c.precon, c.pack_f, c.pack_b, c.fl);
+    { SkewGeom fg = full_geom(c.g);   /* built redundantly for the whole grid on every rank */
+      k_precon_coeffs<<<ew_grid(fg), EW_THREADS, 0, c.stream>>>(fg, c.aplusx, c.aplusy, c.precon, c.pack_f, c.pack_b, c.fl); }
     count(c, 3);
 }
 
@@ -821,8 +887,11 @@ static void launch_sweep(SolveCtx& c, const double* src, double* dst, const doub
                              (int)sweep_smem(WITH_DOT));
         attr_done = true;
     }
-    k_precon_sweep<DIR, WITH_DOT, MASKED><<<wf_blocks(c.g), WF_WARPS * 32, sweep_smem(WITH_DOT), c.stream>>>(
-        c.g, src, dst, pack, rr, bnd, c.stripdot, c.sc, dot_mode, check_done, trace);
+    const int nown = c.g.s1 - c.g.s0;
+    double* peer = nullptr;
+    if (c.comm) peer = DIR > 0 ? c.peer_bnd_f_next : c.peer_bnd_b_prev;
+    k_precon_sweep<DIR, WITH_DOT, MASKED><<<(nown + WF_WARPS - 1) / WF_WARPS, WF_WARPS * 32, sweep_smem(WITH_DOT), c.stream>>>(
+        c.g, src, dst, pack, rr, bnd, peer, c.strip_part, c.sc, dot_mode, check_done, trace);
 }
 
 /* dst = M^-1 src: forward then backward sweep.  Boundary rows must be armed. */
@@ -857,8 +926,34 @@ void launch_apply_precon(SolveCtx& c, const double* src, double* dst, int /*with
 
 void launch_matvec(SolveCtx& c, const double* b, double* dst) {
     k_matvec_dot<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, b, dst,
-                                                           c.partials, c.sc, DOT_NONE, 0, nullptr);
+                                                           c.partials, c.strip_part, c.sc, DOT_NONE, 0, nullptr, 1);
     count(c);
+}
+
+/* ---- distributed pieces (no-ops on a single GPU) ---- */
+__global__ void k_apply_dot(SkewGeom g, const double* __restrict__ strip_part, SolveScalars* sc, int mode, int check_done);
+__global__ void k_apply_max(const unsigned long long* __restrict__ rank_max, int world, SolveScalars* sc, double tol, int init);
+static void dist_dot(SolveCtx& c, int mode, int check_done) {
+    if (single_gpu(c) || mode == DOT_NONE) return;
+    const int chunk = c.strips_alloc / c.comm->world;
+    comm_all_gather(*c.comm, c.strip_part + (size_t)c.comm->rank * chunk, c.strip_part, sizeof(double) * chunk);
+    k_apply_dot<<<1, 32, 0, c.stream>>>(c.g, c.strip_part, c.sc, mode, check_done);
+    count(c);
+}
+static void dist_max(SolveCtx& c, int init) {
+    if (single_gpu(c)) return;
+    comm_all_gather(*c.comm, c.rank_max + c.comm->rank, c.rank_max, sizeof(unsigned long long));
+    k_apply_max<<<1, 32, 0, c.stream>>>(c.rank_max, c.comm->world, c.sc, c.tolerance, init);
+    count(c);
+}
+/* the mat-vec of the next iteration reads s one row above and one row below the slab */
+static void dist_halo_rows(SolveCtx& c, double* vec) {
+    if (single_gpu(c)) return;
+    const int w = c.g.w;
+    k_pack_rows<<<(w + 255) / 256, 256, 0, c.stream>>>(c.g, vec, c.rowbuf);
+    comm_exchange_rows(*c.comm, c.rowbuf, c.rowbuf + 2 * w, c.rowbuf + w, c.rowbuf + 3 * w, (size_t)w);
+    k_unpack_rows<<<(w + 255) / 256, 256, 0, c.stream>>>(c.g, vec, c.rowbuf, c.comm->rank > 0, c.comm->rank < c.comm->world - 1);
+    count(c, 2);
 }
 
 /* project() F3:590-602: p = 0; z = M^-1 r; s = z; maxError; sigma = z.r */
@@ -866,9 +961,15 @@ void pcg_enqueue_init(SolveCtx& c) {
     cudaMemsetAsync(c.p, 0, sizeof(double) * (size_t)c.g.total, c.stream);
     k_solve_reset<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
     count(c);
+    /* every rank's inboxes must be re-armed before any neighbour starts writing into them */
+    if (!single_gpu(c)) comm_all_gather(*c.comm, c.rank_max + c.comm->rank, c.rank_max, sizeof(unsigned long long));
     enqueue_precon(c, c.r, c.z, DOT_SIGMA_INIT, 0);
-    k_init_s<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.r, c.sc, c.tolerance, c.mask_vector_ops ? c.fl : nullptr);
+    dist_dot(c, DOT_SIGMA_INIT, 0);
+    k_init_s<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.r, c.sc, c.tolerance, c.mask_vector_ops ? c.fl : nullptr,
+                                                       c.rank_max, c.comm ? c.comm->rank : 0, single_gpu(c));
     count(c);
+    dist_max(c, 1);
+    dist_halo_rows(c, c.s);
 }
 
 __global__ void k_record_done(const SolveScalars* sc, int* out) { *out = sc->done; }
@@ -891,22 +992,28 @@ static inline void prof_mark(SolveCtx& c, int slot, int e) {
 void pcg_enqueue_iterations(SolveCtx& c, int n) {
     dim3 eg = ew_grid(c.g);
     const unsigned char* mfl = c.mask_vector_ops ? c.fl : nullptr;
+    const int rank = c.comm ? c.comm->rank : 0;
     for (int it = 0; it < n; it++) {
         const int ps = (it == 0 && !c.sequential) ? prof_begin(c, 0) : -1;
-        k_matvec_dot<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.s, c.z, c.partials,
-                                                      c.sc, c.sequential ? DOT_NONE : DOT_ZS, 1, mfl);
+        k_matvec_dot<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.s, c.z, c.partials, c.strip_part,
+                                                      c.sc, c.sequential ? DOT_NONE : DOT_ZS, 1, mfl, single_gpu(c));
         count(c);
-        prof_mark(c, ps, 1);
         if (c.sequential) {
             k_dot_sequential<<<1, 32, 0, c.stream>>>(c.g, c.z, c.s, c.sc, DOT_ZS, 1, mfl);
             count(c);
         }
-        k_update_pr<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.p, c.s, c.r, c.z, c.bnd_f, c.bnd_b, c.sc, c.tolerance, mfl);
+        dist_dot(c, DOT_ZS, 1);
+        prof_mark(c, ps, 1);
+        k_update_pr<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.p, c.s, c.r, c.z, c.bnd_f, c.bnd_b, c.sc, c.tolerance, mfl,
+                                                     c.rank_max, rank, single_gpu(c));
         count(c);
+        dist_max(c, 0);
         prof_mark(c, ps, 2);
         enqueue_precon(c, c.r, c.z, DOT_SIGMA_NEW, 1, ps);
+        dist_dot(c, DOT_SIGMA_NEW, 1);
         k_update_s<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.sc, mfl);
         count(c);
+        dist_halo_rows(c, c.s);
         prof_mark(c, ps, 5);
     }
 }
@@ -914,6 +1021,11 @@ void pcg_enqueue_iterations(SolveCtx& c, int n) {
 void pcg_enqueue_finish(SolveCtx& c, int limit) {
     k_solve_finish<<<1, 1, 0, c.stream>>>(c.sc, limit);
     count(c);
+    if (!single_gpu(c)) {
+        /* every rank needs the whole pressure field for applyPressure: in-place all-gather of the slabs */
+        const size_t chunk = (size_t)(c.strips_alloc / c.comm->world) * (size_t)c.g.ss;
+        comm_all_gather(*c.comm, c.p + (size_t)c.comm->rank * chunk, c.p, sizeof(double) * chunk);
+    }
 }
 
 /* Gauss-Seidel project() F1:380: _p is warm-started, so only the control state is reset */

@@ -57,6 +57,14 @@ class SolidSphere(SolidBody):
         super().__init__(x, y, s, s, theta, velX, velY, velTheta)
 
 
+def comm_unique_id():
+    """128-byte id for a slab-decomposed solver group (rank 0 creates it, the host broadcasts it)."""
+    _, fn = load()
+    buf = (C.c_uint8 * 128)()
+    check(fn["ifl_comm_unique_id"](buf))
+    return bytes(buf)
+
+
 class FluidQuantity:
     """View of one device-resident FluidQuantity (F1:105): `_src` / `_dst` copy the buffers out."""
 
@@ -97,8 +105,11 @@ class FluidSolver:
             cfg_kw.update(density_soot=rho_soot, diffusion=diffusion)
         elif rest:
             raise TypeError("FluidSolver(w, h, density) takes no further positional arguments for F1-F3")
+        comm_id = overrides.pop("comm_id", None)
         cfg_kw.update(overrides)
         self.cfg = _abi.default_config(variant, w, h, **cfg_kw)
+        if comm_id is not None:
+            C.memmove(self.cfg.comm_id, comm_id, 128)
         self._w, self._h = w, h
         self._hx = 1.0 / min(w, h)
         self._variant = variant
