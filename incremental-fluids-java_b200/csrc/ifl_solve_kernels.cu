@@ -176,6 +176,9 @@ k_update_pr(SkewGeom g, double* __restrict__ p, const double* __restrict__ s, do
         if (l_ == 0 && t_ < g.w) {
             bnd_f[(long long)k_ * g.w + t_] = sentinel();
             bnd_b[(long long)k_ * g.w + t_] = sentinel();
+            /* slab decomposition: the rows my neighbours write into (their edge strips) are re-armed by me */
+            if (k_ == g.s0 && g.s0 > 0) bnd_f[(long long)(g.s0 - 1) * g.w + t_] = sentinel();
+            if (k_ == g.s1 - 1 && g.s1 < g.nstrips) bnd_b[(long long)g.s1 * g.w + t_] = sentinel();
         }
     IFL_EW_LOOP_END
 #pragma unroll
