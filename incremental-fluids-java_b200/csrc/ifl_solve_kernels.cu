@@ -21,6 +21,7 @@
  * Compiled with -fmad=false.
  */
 #include <cstdlib>
+#include <cooperative_groups.h>
 #include "ifl_internal.h"
 
 namespace ifl {
@@ -445,6 +446,7 @@ static constexpr int SW_U = 16;                     /* steps (t-rows) per staged
 static constexpr int SW_STAGES = 2;                 /* ring depth: block b+1 streams in while block b is computed */
 static constexpr int SW_TILE = SW_U * 32;           /* doubles per array per block (4 KB) */
 static constexpr int SW_PACK = 3 * SW_TILE;         /* packed coefficient block: 3 arrays (12 KB) */
+static constexpr int SW_FG = 8;                     /* steps per edge-feed group: granularity of the strip hand-over */
 
 /* Packed sweep coefficients.  applyPreconditioner multiplies `aPlusX[i]*precon[i]` and
  * `aPlusY[i]*precon[i]` before it touches dst (F3:500,503,514,517); those products are the same in
@@ -479,53 +481,145 @@ k_precon_coeffs(SkewGeom g, const double* __restrict__ ax, const double* __restr
     IFL_EW_LOOP_END
 }
 
-/* SW_U consecutive steps of one strip.  tile_a: staged src block [SW_U][32]; tile_c: staged
- * coefficient pack [3][SW_U][32]; tile_r: staged rr block (fused dot) */
-template <int DIR, bool WITH_DOT, bool CHECKED, bool FASTFEED, bool MASKED>
-__device__ __forceinline__ void sweep_steps(const double* tile_a, const double* tile_c, const double* tile_r,
-                                            const int t0, const int lane, const int w, const bool yok,
-                                            double* pdst, double* pbnd, RotFeed<SW_U>& feed,
+/* ---- strip hand-over inside a thread-block cluster ---------------------------------------------------
+ * Consecutive strips run on consecutive warps of a cluster (SW_CL blocks x WF_WARPS warps).  A strip hands its
+ * edge row to the next one through a small ring in the CONSUMER's shared memory, written with distributed-
+ * shared-memory stores (same block: plain shared stores through the same mapped address):
+ *   - flag-in-data again: a slot holds the sentinel until the n-th edge value is stored; the consumer polls its
+ *     own shared memory (~30 cycles a poll instead of ~300-700 for a global boundary row) and re-arms the slot;
+ *   - credit: the consumer publishes how many values it has consumed into the producer's shared memory once per
+ *     block; the producer only checks that word (local) before a block, so it can never lap the ring.
+ * Only the first strip of a cluster takes its input from a global boundary row (previous cluster / previous GPU)
+ * and only the last one writes one. */
+static constexpr int SW_CL_MAX = 8;                /* blocks per cluster (portable maximum) */
+static constexpr int SW_RB = 128;                  /* ring slots per strip inbox */
+
+/* sentinel test on the high word only (0xFFF8B200: a NaN payload no arithmetic produces) */
+__device__ __forceinline__ bool is_sentinel_hi(double v) { return __double2hiint(v) == (int)0xFFF8B200; }
+
+struct EdgeIn {
+    const double* src;        /* global boundary row, or this warp's shared-memory ring (generic address) */
+    double* ring;             /* same ring, writable (re-arm), nullptr in global mode */
+    int idx_mask;             /* SW_RB-1 for a ring, 0x7fffffff for a global row */
+    int w;
+    bool feeder;              /* this lane reads the edge values */
+    int mode;                 /* 0 none, 1 global row (index = column), 2 ring (index = sequence number) */
+    double cur[SW_FG], nxt[SW_FG];
+    __device__ __forceinline__ void init(int mode_, const double* src_, double* ring_, int w_, bool feeder_) {
+        mode = mode_; src = src_; ring = ring_; w = w_; feeder = feeder_ && mode_ != 0;
+        idx_mask = mode_ == 2 ? SW_RB - 1 : 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < SW_FG; j++) { cur[j] = 0.0; nxt[j] = 0.0; }
+    }
+    /* x0: column of the group's first step; n0: its sequence number; both advance by (dir, +1) per step */
+    __device__ __forceinline__ void prefetch(int x0, int n0, int dir) {
+#pragma unroll
+        for (int j = 0; j < SW_FG; j++) {
+            const int x = x0 + dir * j;
+            const int i = (mode == 2 ? n0 + j : x) & idx_mask;
+            nxt[j] = (feeder && x >= 0 && x < w) ? ld_volatile(src + i) : 0.0;
+        }
+    }
+    __device__ __forceinline__ void advance() {
+#pragma unroll
+        for (int j = 0; j < SW_FG; j++) cur[j] = nxt[j];
+    }
+    __device__ __forceinline__ bool ready() const {
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < SW_FG; j++) ok = ok && !is_sentinel_hi(cur[j]);
+        return __all_sync(0xffffffffu, ok);
+    }
+    /* spin (bounded) until every value of the current group has arrived */
+    __device__ __forceinline__ void wait(int x0, int n0, int dir) {
+        for (unsigned spins = 0;; spins++) {
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < SW_FG; j++) ok = ok && !is_sentinel_hi(cur[j]);
+            ok = ok || spins > (1u << 24);
+            if (__all_sync(0xffffffffu, ok)) break;
+#pragma unroll
+            for (int j = 0; j < SW_FG; j++)
+                if (is_sentinel_hi(cur[j])) {
+                    const int i = (mode == 2 ? n0 + j : x0 + dir * j) & idx_mask;
+                    cur[j] = ld_volatile(src + i);
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < SW_FG; j++) if (is_sentinel_hi(cur[j])) cur[j] = 0.0;     /* gave up: dead producer */
+    }
+    /* ring mode: re-arm the consumed slots */
+    __device__ __forceinline__ void rearm(int x0, int n0, int dir) {
+        if (mode != 2 || !feeder) return;
+#pragma unroll
+        for (int j = 0; j < SW_FG; j++) {
+            const int x = x0 + dir * j;
+            if (x >= 0 && x < w) ring[(n0 + j) & (SW_RB - 1)] = sentinel();
+        }
+    }
+};
+
+/* operands of SW_FG steps, loaded from the staged tiles one group ahead of their use: with one warp per
+ * scheduler nothing hides a shared-memory load that sits between two dependent FP64 operations */
+template <bool WITH_DOT>
+struct StepOps {
+    double a[SW_FG], cx[SW_FG], cy[SW_FG], pr[SW_FG], rr[SW_FG];
+    template <int DIR>
+    __device__ __forceinline__ void load(const double* tile_a, const double* tile_c, const double* tile_r, int j0) {
+#pragma unroll
+        for (int j = 0; j < SW_FG; j++) {
+            const int row = (DIR > 0 ? (j0 + j) : SW_U - 1 - (j0 + j)) * 32;
+            a[j] = tile_a[row];
+            cx[j] = tile_c[row];
+            cy[j] = tile_c[SW_TILE + row];
+            pr[j] = tile_c[2 * SW_TILE + row];
+            rr[j] = WITH_DOT ? tile_r[row] : 0.0;
+        }
+    }
+};
+
+/* SW_FG consecutive steps of one strip; t0 = t of the first step.  pout: where the edge lane stores the result of
+ * the first step (a global boundary row: +DIR per step; the next strip's ring: index (oi0 + j) & out_mask). */
+template <int DIR, bool WITH_DOT, bool CHECKED, bool MASKED>
+__device__ __forceinline__ void sweep_steps(const StepOps<WITH_DOT>& op, const int t0, const int lane, const int w,
+                                            const bool yok, double* pdst, double* pout_base, const int oi0,
+                                            const int out_mask, const EdgeIn& feed,
                                             double& dprev, double& cxprev, double& acc) {
-    constexpr int U = SW_U;
-    constexpr int E_IN = DIR > 0 ? 0 : 31;
     constexpr int E_OUT = DIR > 0 ? 31 : 0;
     const int srclane = (lane - DIR) & 31;          /* rotation: E_IN reads from E_OUT */
     const bool is_out = lane == E_OUT;
+    const bool ring_out = out_mask != 0x7fffffff;
 #pragma unroll
-    for (int j = 0; j < U; j++) {
-        const int row = (DIR > 0 ? j : U - 1 - j) * 32;
-        const double a = tile_a[row];
-        const double cx = tile_c[row];
-        const double cyv = tile_c[SW_TILE + row];
-        const double pr = tile_c[2 * SW_TILE + row];
-        if (!FASTFEED) feed.wait(j, t0 - E_IN, DIR);
+    for (int j = 0; j < SW_FG; j++) {
+        const double pr = op.pr[j];
         const double give = is_out ? feed.cur[j] : dprev;
         const double dn = __shfl_sync(0xffffffffu, give, srclane);
-        double v = a;
+        double v = op.a[j];
         if (DIR > 0) {
             v = v - cxprev * dprev;      /* (aPlusX[i-1]*precon[i-1]) * dst[i-1]   F3:500 */
-            v = v - cyv * dn;            /* (aPlusY[i-w]*precon[i-w]) * dst[i-w]   F3:503 */
-            cxprev = cx;
+            v = v - op.cy[j] * dn;       /* (aPlusY[i-w]*precon[i-w]) * dst[i-w]   F3:503 */
+            cxprev = op.cx[j];
         } else {
-            v = v - cx * dprev;          /* (aPlusX[i]*precon[i]) * dst[i+1]       F3:514 */
-            v = v - cyv * dn;            /* (aPlusY[i]*precon[i]) * dst[i+w]       F3:517 */
+            v = v - op.cx[j] * dprev;    /* (aPlusX[i]*precon[i]) * dst[i+1]       F3:514 */
+            v = v - op.cy[j] * dn;       /* (aPlusY[i]*precon[i]) * dst[i+w]       F3:517 */
         }
         double d = v * pr;
         const bool fluid = MASKED ? (pr == pr) : true;      /* NaN precon tags a non-fluid cell (k_precon_coeffs) */
         if (MASKED) d = fluid ? d : 0.0;                     /* skipped cell: dst stays, neighbours see +0.0 */
+        double* po = ring_out ? pout_base + ((oi0 + j) & out_mask) : pout_base + (oi0 + DIR * j);
         if (CHECKED) {
             const int x = t0 + DIR * j - lane;
             const bool active = yok && x >= 0 && x < w;
             if (active && fluid) pdst[DIR * j * 32] = d;
-            if (active && is_out) pbnd[DIR * j] = d;
+            if (x >= 0 && x < w && is_out) *po = d;          /* the edge value is published for every column */
         } else {
             /* interior block: only rows y >= h are inactive; they hold +0.0, and storing +0.0 into
              * their (zero) padding cells keeps the padding zero -- no branch needed */
             if (fluid) pdst[DIR * j * 32] = d;
-            if (is_out) pbnd[DIR * j] = d;
+            if (is_out) *po = d;
         }
         /* inactive lanes hold +0.0 and rr is zero in the padding: adding them is exact */
-        if (WITH_DOT) acc += d * tile_r[row];
+        if (WITH_DOT) acc += d * op.rr[j];
         dprev = d;
     }
 }
@@ -542,111 +636,170 @@ __device__ __forceinline__ void sweep_steps(const double* tile_a, const double* 
 template <int DIR, bool WITH_DOT, bool MASKED>
 __global__ void __launch_bounds__(WF_WARPS * 32)
 k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restrict__ pack,
-               const double* __restrict__ rr, double* bnd, double* bnd_peer, double* stripdot,
+               const double* __restrict__ rr, double* bnd, double* bnd_peer, double* strip_part,
                SolveScalars* sc, int dot_mode, int check_done, long long* trace) {
+    namespace cg = cooperative_groups;
     constexpr int U = SW_U;
     constexpr int S = SW_STAGES;
     constexpr int STAGE = (WITH_DOT ? 2 : 1) * SW_TILE + SW_PACK;     /* doubles per stage */
+    constexpr int E_IN = DIR > 0 ? 0 : 31;
+    constexpr int E_OUT = DIR > 0 ? 31 : 0;
     extern __shared__ __align__(128) unsigned char wf_smem[];
-    if (check_done && sc->done) return;
+    __shared__ double s_inbox[WF_WARPS][SW_RB];          /* edge-row rings of this block's strips */
+    __shared__ volatile int s_credit[WF_WARPS];          /* values consumed by the strip after mine */
+    __shared__ int s_ticket;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks();
+    const int crank = (int)cluster.block_rank();
+    if (check_done && sc->done) return;                  /* uniform over the whole grid */
     const long long tr_enter = trace ? (long long)globaltimer_ns() : 0;
-    const int slot = claim_slot(DIR > 0 ? &sc->ticket_f : &sc->ticket_b, g.s1 - g.s0);
-    if (slot < 0) return;
-    const int k = DIR > 0 ? g.s0 + slot : g.s1 - 1 - slot;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int y = k * 32 + lane;
-    const bool yok = y < g.h;
+    for (int i = lane; i < SW_RB; i += 32) s_inbox[warp][i] = sentinel();
+    if (lane == 0) s_credit[warp] = 0;
+    /* one ticket per cluster: a waiting cluster's predecessor has started (no reliance on launch order) */
+    if (crank == 0 && threadIdx.x == 0) {
+        int tk = (int)atomicAdd(DIR > 0 ? &sc->ticket_f : &sc->ticket_b, 1u);
+        for (int r = 0; r < csize; r++) *cluster.map_shared_rank(&s_ticket, r) = tk;
+    }
+    cluster.sync();
+    const int nown = g.s1 - g.s0;
+    const int cslot = crank * WF_WARPS + warp;                        /* position inside the cluster */
+    const int slot = s_ticket * csize * WF_WARPS + cslot;
+    const bool live = slot < nown;
+    const int k = DIR > 0 ? g.s0 + slot : g.s1 - 1 - slot;
     const int w = g.w;
-    const int nblk = (w + 31 + U - 1) / U;
-    const int tfirst = DIR > 0 ? 0 : nblk * U - 1;
-    constexpr int E_IN = DIR > 0 ? 0 : 31;
-    const bool has_prev = DIR > 0 ? (k > 0) : (k < g.nstrips - 1);
+    double acc = 0.0;
+    if (live) {
+        const int y = k * 32 + lane;
+        const bool yok = y < g.h;
+        const int nblk = (w + 31 + U - 1) / U;
+        const int tfirst = DIR > 0 ? 0 : nblk * U - 1;
+        const bool has_prev = DIR > 0 ? (k > 0) : (k < g.nstrips - 1);
 
-    /* per-warp ring of S stages: [src tile | coefficient pack | rr tile], then S mbarriers */
-    double* ring = reinterpret_cast<double*>(wf_smem) + (size_t)warp * S * STAGE;
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(
-        wf_smem + (size_t)WF_WARPS * S * STAGE * sizeof(double)) + warp * S;
-    const double* gsrc = src + (long long)k * g.ss;
-    const double* grr = WITH_DOT ? rr + (long long)k * g.ss : nullptr;
-    const double* gpack = pack + (long long)k * (g.tl / U) * SW_PACK;
-    /* block b covers t-rows [gb*U, gb*U + U) with gb = b forward, nblk-1-b backward */
-    auto issue = [&](int b) {
-        const int st = b % S;
-        const int gb = DIR > 0 ? b : nblk - 1 - b;
-        double* sdst = ring + (size_t)st * STAGE;
-        mbar_expect_tx(&bars[st], STAGE * sizeof(double));
-        bulk_g2s(sdst, gsrc + (long long)gb * SW_TILE, SW_TILE * sizeof(double), &bars[st]);
-        bulk_g2s(sdst + SW_TILE, gpack + (long long)gb * SW_PACK, SW_PACK * sizeof(double), &bars[st]);
-        if (WITH_DOT) bulk_g2s(sdst + SW_TILE + SW_PACK, grr + (long long)gb * SW_TILE, SW_TILE * sizeof(double), &bars[st]);
-    };
-    if (lane == 0) {
-        for (int i = 0; i < S; i++) mbar_init(&bars[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int b = 0; b < S && b < nblk; b++) issue(b);
-    }
-    __syncwarp();
-
-    double* pdst = dst + (long long)k * g.ss + lane + (long long)tfirst * 32;
-    /* outgoing edge row: the next strip's inbox -- in the neighbour GPU's memory for the last strip of a slab */
-    const bool to_peer = bnd_peer != nullptr && (DIR > 0 ? k == g.s1 - 1 : k == g.s0);
-    double* pbnd = (to_peer ? bnd_peer : bnd) + (long long)k * w + (tfirst - lane);   /* column x = t - lane */
-
-    RotFeed<U> feed;
-    feed.init(has_prev ? bnd + (long long)(k - DIR) * w : nullptr, w, lane == (DIR > 0 ? 31 : 0));
-    feed.prefetch(tfirst - E_IN, DIR);
-    feed.advance();
-
-    double dprev = 0.0, cxprev = 0.0, acc = 0.0;
-    long long tr_first = 0;
-    for (int b = 0; b < nblk; b++) {
-        const int t0 = tfirst + DIR * b * U;
-        const int st = b % S;
-        feed.prefetch(t0 + DIR * U - E_IN, DIR);
-        const bool fast_feed = feed.ready();
-        if (trace && b == 1) tr_first = (long long)globaltimer_ns();
-        const int tlo = DIR > 0 ? t0 : t0 - (U - 1);
-        const bool interior = (tlo - 31 >= 0) && (tlo + U - 1 < w);
-        mbar_wait(&bars[st], (unsigned)((b / S) & 1));
-        const double* tile_a = ring + (size_t)st * STAGE + lane;
-        const double* tile_c = tile_a + SW_TILE;
-        const double* tile_r = tile_a + SW_TILE + SW_PACK;
-        if (interior) {
-            if (fast_feed) sweep_steps<DIR, WITH_DOT, false, true, MASKED>(tile_a, tile_c, tile_r, t0, lane, w, yok, pdst, pbnd, feed, dprev, cxprev, acc);
-            else sweep_steps<DIR, WITH_DOT, false, false, MASKED>(tile_a, tile_c, tile_r, t0, lane, w, yok, pdst, pbnd, feed, dprev, cxprev, acc);
-        } else {
-            sweep_steps<DIR, WITH_DOT, true, false, MASKED>(tile_a, tile_c, tile_r, t0, lane, w, yok, pdst, pbnd, feed, dprev, cxprev, acc);
+        /* per-warp operand ring: S stages of [src tile | coefficient pack | rr tile], then S mbarriers */
+        double* ring = reinterpret_cast<double*>(wf_smem) + (size_t)warp * S * STAGE;
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(
+            wf_smem + (size_t)WF_WARPS * S * STAGE * sizeof(double)) + warp * S;
+        const double* gsrc = src + (long long)k * g.ss;
+        const double* grr = WITH_DOT ? rr + (long long)k * g.ss : nullptr;
+        const double* gpack = pack + (long long)k * (g.tl / U) * SW_PACK;
+        auto issue = [&](int b) {
+            const int st = b % S;
+            const int gb = DIR > 0 ? b : nblk - 1 - b;
+            double* sdst = ring + (size_t)st * STAGE;
+            mbar_expect_tx(&bars[st], STAGE * sizeof(double));
+            bulk_g2s(sdst, gsrc + (long long)gb * SW_TILE, SW_TILE * sizeof(double), &bars[st]);
+            bulk_g2s(sdst + SW_TILE, gpack + (long long)gb * SW_PACK, SW_PACK * sizeof(double), &bars[st]);
+            if (WITH_DOT) bulk_g2s(sdst + SW_TILE + SW_PACK, grr + (long long)gb * SW_TILE, SW_TILE * sizeof(double), &bars[st]);
+        };
+        if (lane == 0) {
+            for (int i = 0; i < S; i++) mbar_init(&bars[i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int b = 0; b < S && b < nblk; b++) issue(b);
         }
-        pdst += DIR * U * 32;
-        pbnd += DIR * U;
         __syncwarp();
-        if (lane == 0 && b + S < nblk) issue(b + S);
-        feed.advance();
-    }
 
-    if (trace && lane == 0) {
-        long long* tr = trace + (long long)k * 8;
-        tr[0] = tr_enter; tr[1] = tr_first; tr[2] = 0; tr[3] = (long long)globaltimer_ns();
-        tr[4] = 0; tr[5] = nblk; tr[6] = slot; tr[7] = (long long)get_smid();
+        /* incoming edge: my own ring unless I am the first strip of the cluster (then a global boundary row) */
+        const bool in_ring = cslot > 0;
+        EdgeIn feed;
+        feed.init(!has_prev ? 0 : (in_ring ? 2 : 1),
+                  in_ring ? &s_inbox[warp][0] : (has_prev ? bnd + (long long)(k - DIR) * w : nullptr),
+                  in_ring ? &s_inbox[warp][0] : nullptr, w, lane == E_OUT);
+        /* outgoing edge: the next strip's ring (mapped shared memory of its block) unless I am the last strip of
+         * the cluster / of my slab (then the global boundary row, possibly in the neighbour GPU's memory) */
+        const bool out_ring = (cslot < csize * WF_WARPS - 1) && (slot + 1 < nown);
+        const bool to_peer = bnd_peer != nullptr && (DIR > 0 ? k == g.s1 - 1 : k == g.s0);
+        double* out_base;
+        volatile int* credit_of_prev = nullptr;
+        if (out_ring) out_base = cluster.map_shared_rank(&s_inbox[(cslot + 1) % WF_WARPS][0], (cslot + 1) / WF_WARPS);
+        else out_base = (to_peer ? bnd_peer : bnd) + (long long)k * w;
+        if (in_ring) credit_of_prev = cluster.map_shared_rank((int*)&s_credit[(cslot - 1) % WF_WARPS], (cslot - 1) / WF_WARPS);
+        const int out_mask = out_ring ? SW_RB - 1 : 0x7fffffff;
+
+        /* sequence numbers: the n-th edge value is column n (forward) or w-1-n (backward) */
+        const int xin_first = tfirst - E_IN;                               /* column the E_IN lane needs at step 0 */
+        const int nin_first = DIR > 0 ? xin_first : (w - 1 - xin_first);
+        const int xout_first = tfirst - E_OUT;
+        const int nout_first = DIR > 0 ? xout_first : (w - 1 - xout_first);
+        feed.prefetch(xin_first, nin_first, DIR);
+        feed.advance();
+
+        double* pdst = dst + (long long)k * g.ss + lane + (long long)tfirst * 32;
+        double dprev = 0.0, cxprev = 0.0;
+        long long tr_first = 0, wait_cyc = 0;
+        for (int b = 0; b < nblk; b++) {
+            const int t0 = tfirst + DIR * b * U;
+            const int st = b % S;
+            if (trace && b == 1) tr_first = (long long)globaltimer_ns();
+            const int tlo = DIR > 0 ? t0 : t0 - (U - 1);
+            const bool interior = (tlo - 31 >= 0) && (tlo + U - 1 < w);
+            if (out_ring) {
+                /* credit: the last value of this block must not lap the consumer's ring */
+                const int nlast = nout_first + b * U + U - 1;
+                for (unsigned spins = 0; nlast - s_credit[warp] >= SW_RB && spins < (1u << 24); spins++) {}
+            }
+            const long long wc0 = trace ? clock64() : 0;
+            mbar_wait(&bars[st], (unsigned)((b / S) & 1));
+            if (trace) wait_cyc += clock64() - wc0;
+            const double* tile_a = ring + (size_t)st * STAGE + lane;
+            const double* tile_c = tile_a + SW_TILE;
+            const double* tile_r = tile_a + SW_TILE + SW_PACK;
+            StepOps<WITH_DOT> ops[2];
+            ops[0].template load<DIR>(tile_a, tile_c, tile_r, 0);
+#pragma unroll
+            for (int gi = 0; gi < U / SW_FG; gi++) {
+                const int sofs = b * U + gi * SW_FG;                       /* steps done before this group */
+                const int tg = t0 + DIR * gi * SW_FG;
+                const int xin = tg - E_IN, nin = nin_first + sofs;
+                if (gi + 1 < U / SW_FG) ops[(gi + 1) & 1].template load<DIR>(tile_a, tile_c, tile_r, (gi + 1) * SW_FG);
+                feed.prefetch(xin + DIR * SW_FG, nin + SW_FG, DIR);        /* next group */
+                if (!feed.ready()) feed.wait(xin, nin, DIR);
+                feed.rearm(xin, nin, DIR);
+                double* gd = pdst + DIR * gi * SW_FG * 32;
+                const int oi = out_ring ? nout_first + sofs : (tg - E_OUT);
+                if (interior)
+                    sweep_steps<DIR, WITH_DOT, false, MASKED>(ops[gi & 1], tg, lane, w, yok, gd, out_base, oi, out_mask, feed, dprev, cxprev, acc);
+                else
+                    sweep_steps<DIR, WITH_DOT, true, MASKED>(ops[gi & 1], tg, lane, w, yok, gd, out_base, oi, out_mask, feed, dprev, cxprev, acc);
+                feed.advance();
+            }
+            pdst += DIR * U * 32;
+            __syncwarp();
+            if (lane == 0) {
+                if (b + S < nblk) issue(b + S);
+                if (credit_of_prev) {                                       /* values consumed so far */
+                    int consumed = nin_first + (b + 1) * U;
+                    *credit_of_prev = consumed < 0 ? 0 : consumed;
+                }
+            }
+        }
+        if (trace && lane == 0) {
+            long long* tr = trace + (long long)k * 8;
+            tr[0] = tr_enter; tr[1] = tr_first; tr[2] = 0; tr[3] = (long long)globaltimer_ns();
+            tr[4] = wait_cyc; tr[5] = nblk; tr[6] = slot; tr[7] = (long long)get_smid();
+        }
     }
-    if (WITH_DOT) {
+    if (WITH_DOT && live) {
         double ws = warp_sum(acc);
         if (lane == 0) {
-            stripdot[k] = ws;
+            strip_part[k] = ws;
             __threadfence();
             unsigned prev = atomicAdd(&sc->ctr_b, 1u);
-            if (prev == (unsigned)(g.s1 - g.s0) - 1u) {
+            if (prev == (unsigned)nown - 1u) {
                 __threadfence();
-                if (g.s1 - g.s0 == g.nstrips) {      /* single GPU: strips in order; otherwise k_apply_dot after the all-gather */
+                if (nown == g.nstrips) {      /* single GPU: strips in order; otherwise k_apply_dot after the all-gather */
                     double total = 0.0;
-                    for (int kk = 0; kk < g.nstrips; kk++) total += ld_cg(stripdot + kk);
+                    for (int kk = 0; kk < g.nstrips; kk++) total += ld_cg(strip_part + kk);
                     if (dot_mode != DOT_NONE) apply_dot_result(sc, dot_mode, total);
                 }
                 sc->ctr_b = 0;
             }
         }
     }
+    /* nobody may leave while a neighbour can still store into its shared memory (edge values, credits) */
+    cluster.sync();
 }
 
 /* buildPreconditioner F3:464 / masked F4:744 (=F5:858, F6:918, F7:951) -- MIC(0) with tau/sigma,
@@ -893,8 +1046,20 @@ static void launch_sweep(SolveCtx& c, const double* src, double* dst, const doub
     const int nown = c.g.s1 - c.g.s0;
     double* peer = nullptr;
     if (c.comm) peer = DIR > 0 ? c.peer_bnd_f_next : c.peer_bnd_b_prev;
-    k_precon_sweep<DIR, WITH_DOT, MASKED><<<(nown + WF_WARPS - 1) / WF_WARPS, WF_WARPS * 32, sweep_smem(WITH_DOT), c.stream>>>(
-        c.g, src, dst, pack, rr, bnd, peer, c.strip_part, c.sc, dot_mode, check_done, trace);
+    const int nblocks = (nown + WF_WARPS - 1) / WF_WARPS;
+    int cl = SW_CL_MAX;
+    while (cl > 1 && cl > nblocks) cl >>= 1;                       /* cluster of 8 blocks = 32 consecutive strips */
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(((nblocks + cl - 1) / cl) * cl);
+    cfg.blockDim = dim3(WF_WARPS * 32);
+    cfg.dynamicSmemBytes = sweep_smem(WITH_DOT);
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = cl; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_precon_sweep<DIR, WITH_DOT, MASKED>, c.g, src, dst, pack, rr, bnd, peer, c.strip_part, c.sc,
+                       dot_mode, check_done, trace);
 }
 
 /* dst = M^-1 src: forward then backward sweep.  Boundary rows must be armed. */

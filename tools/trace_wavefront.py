@@ -20,4 +20,4 @@ for sw, name in ((0, "forward"), (1, "backward")):
     for k in order:
         e = t[k]
         print(f"strip {k:4d} slot {e[6]:4d} sm {e[7]:3d} enter {(e[0]-t0)/1e3:8.2f} after-block-1 {(e[1]-t0)/1e3:8.2f} "
-              f"end {(e[3]-t0)/1e3:8.2f} dur {(e[3]-e[1])/1e3:8.2f} us  blocks {e[5]}")
+              f"end {(e[3]-t0)/1e3:8.2f} dur {(e[3]-e[1])/1e3:8.2f} us  blocks {e[5]}  operand-wait {e[4]} cycles")
