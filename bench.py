@@ -185,13 +185,17 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
-    comm_kw = {}
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def comm_kw():
+        """every slab-decomposed solver group needs its own id (an ncclUniqueId), made by rank 0 and broadcast"""
+        if world == 1:
+            return {}
         ids = [ifl.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
-        comm_kw = dict(rank=rank, world_size=world, comm_id=ids[0])
+        return dict(rank=rank, world_size=world, comm_id=ids[0])
 
     def barrier():
         if dist is not None:
@@ -211,7 +215,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
     def make_solver():
-        return ifl.FluidSolver(W, H, DENSITY, variant=abi.F3_CONJUGATE_GRADIENTS, device=local_rank, **comm_kw)
+        return ifl.FluidSolver(W, H, DENSITY, variant=abi.F3_CONJUGATE_GRADIENTS, device=local_rank, **comm_kw())
 
     # ------------------------------------------------------------- resident arm
     g = make_solver()

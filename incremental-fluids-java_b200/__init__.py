@@ -8,7 +8,7 @@ or through the repo-root shim `incfluid_b200`.
 """
 from . import _abi as abi  # noqa: F401
 from ._lib import build, load, IflError, LIB_PATH  # noqa: F401
-from .solver import FluidSolver, FluidQuantity, SolidBody, SolidBox, SolidSphere, comm_unique_id  # noqa: F401
+from .solver import FluidSolver, FluidQuantity, SolidBody, SolidBox, SolidSphere, comm_unique_id, slab_partition  # noqa: F401
 
 F1_MATRIXLESS = abi.F1_MATRIXLESS
 F2_BETTER_ADVECTION = abi.F2_BETTER_ADVECTION

@@ -256,3 +256,19 @@ class FluidSolver:
         out = (C.c_double * 3)()
         check(self._fn["ifl_last_timing"](self._h_, out))
         return {"projection_ms": out[0], "advection_ms": out[1], "total_ms": out[2]}
+
+
+def slab_partition(h, world_size):
+    """Strip ranges of the slab decomposition, identical to ifl_create(): the grid's 32-row strips are dealt out in
+    contiguous chunks of ceil(nstrips / world) -- rank r owns strips [r*chunk, min((r+1)*chunk, nstrips)), i.e. rows
+    [32*s0, min(32*s1, h)).  Returns a list of (s0, s1, row0, row1) per rank."""
+    nstrips = (h + 31) // 32
+    if world_size < 1 or nstrips < world_size:
+        raise ValueError("fewer 32-row strips than ranks")
+    chunk = (nstrips + world_size - 1) // world_size
+    out = []
+    for r in range(world_size):
+        s0 = r * chunk
+        s1 = min(s0 + chunk, nstrips)
+        out.append((s0, max(s1, s0), min(32 * s0, h), min(32 * max(s1, s0), h)))
+    return out
