@@ -497,64 +497,50 @@ static constexpr int SW_RB = 128;                  /* ring slots per strip inbox
 /* sentinel test on the high word only (0xFFF8B200: a NaN payload no arithmetic produces) */
 __device__ __forceinline__ bool is_sentinel_hi(double v) { return __double2hiint(v) == (int)0xFFF8B200; }
 
-struct EdgeIn {
+/* Incoming edge values of one group of SW_FG steps.  In ring mode a value lives in slot (producer step & 127), and
+ * the producer's step is the consumer's step + 31; in global-row mode the index is the column. */
+struct EdgeSrc {
     const double* src;        /* global boundary row, or this warp's shared-memory ring (generic address) */
-    double* ring;             /* same ring, writable (re-arm), nullptr in global mode */
-    int idx_mask;             /* SW_RB-1 for a ring, 0x7fffffff for a global row */
+    double* ring;             /* the ring, writable (re-arm); nullptr in global mode */
     int w;
     bool feeder;              /* this lane reads the edge values */
-    int mode;                 /* 0 none, 1 global row (index = column), 2 ring (index = sequence number) */
-    double cur[SW_FG], nxt[SW_FG];
-    __device__ __forceinline__ void init(int mode_, const double* src_, double* ring_, int w_, bool feeder_) {
-        mode = mode_; src = src_; ring = ring_; w = w_; feeder = feeder_ && mode_ != 0;
-        idx_mask = mode_ == 2 ? SW_RB - 1 : 0x7fffffff;
-#pragma unroll
-        for (int j = 0; j < SW_FG; j++) { cur[j] = 0.0; nxt[j] = 0.0; }
-    }
-    /* x0: column of the group's first step; n0: its sequence number; both advance by (dir, +1) per step */
-    __device__ __forceinline__ void prefetch(int x0, int n0, int dir) {
+    int mode;                 /* 0 none, 1 global row, 2 ring */
+    __device__ __forceinline__ int index(int x, int sc) const { return mode == 2 ? ((sc + 31) & (SW_RB - 1)) : x; }
+    /* x0 / sc0: column and consumer step count of the group's first step; they advance by (dir, +1) per step */
+    __device__ __forceinline__ void fetch(double (&v)[SW_FG], int x0, int sc0, int dir) const {
 #pragma unroll
         for (int j = 0; j < SW_FG; j++) {
             const int x = x0 + dir * j;
-            const int i = (mode == 2 ? n0 + j : x) & idx_mask;
-            nxt[j] = (feeder && x >= 0 && x < w) ? ld_volatile(src + i) : 0.0;
+            v[j] = (feeder && x >= 0 && x < w) ? ld_volatile(src + index(x, sc0 + j)) : 0.0;
         }
     }
-    __device__ __forceinline__ void advance() {
-#pragma unroll
-        for (int j = 0; j < SW_FG; j++) cur[j] = nxt[j];
-    }
-    __device__ __forceinline__ bool ready() const {
+    __device__ __forceinline__ bool ready(const double (&v)[SW_FG]) const {
         bool ok = true;
 #pragma unroll
-        for (int j = 0; j < SW_FG; j++) ok = ok && !is_sentinel_hi(cur[j]);
+        for (int j = 0; j < SW_FG; j++) ok = ok && !is_sentinel_hi(v[j]);
         return __all_sync(0xffffffffu, ok);
     }
-    /* spin (bounded) until every value of the current group has arrived */
-    __device__ __forceinline__ void wait(int x0, int n0, int dir) {
+    /* spin (bounded) until every value of the group has arrived */
+    __device__ __forceinline__ void wait(double (&v)[SW_FG], int x0, int sc0, int dir) const {
         for (unsigned spins = 0;; spins++) {
             bool ok = true;
 #pragma unroll
-            for (int j = 0; j < SW_FG; j++) ok = ok && !is_sentinel_hi(cur[j]);
+            for (int j = 0; j < SW_FG; j++) ok = ok && !is_sentinel_hi(v[j]);
             ok = ok || spins > (1u << 24);
             if (__all_sync(0xffffffffu, ok)) break;
 #pragma unroll
             for (int j = 0; j < SW_FG; j++)
-                if (is_sentinel_hi(cur[j])) {
-                    const int i = (mode == 2 ? n0 + j : x0 + dir * j) & idx_mask;
-                    cur[j] = ld_volatile(src + i);
-                }
+                if (is_sentinel_hi(v[j])) v[j] = ld_volatile(src + index(x0 + dir * j, sc0 + j));
         }
 #pragma unroll
-        for (int j = 0; j < SW_FG; j++) if (is_sentinel_hi(cur[j])) cur[j] = 0.0;     /* gave up: dead producer */
+        for (int j = 0; j < SW_FG; j++) if (is_sentinel_hi(v[j])) v[j] = 0.0;     /* gave up: dead producer */
     }
-    /* ring mode: re-arm the consumed slots */
-    __device__ __forceinline__ void rearm(int x0, int n0, int dir) {
+    __device__ __forceinline__ void rearm(int x0, int sc0, int dir) const {
         if (mode != 2 || !feeder) return;
 #pragma unroll
         for (int j = 0; j < SW_FG; j++) {
             const int x = x0 + dir * j;
-            if (x >= 0 && x < w) ring[(n0 + j) & (SW_RB - 1)] = sentinel();
+            if (x >= 0 && x < w) ring[(sc0 + 31 + j) & (SW_RB - 1)] = sentinel();
         }
     }
 };
@@ -578,21 +564,19 @@ struct StepOps {
     }
 };
 
-/* SW_FG consecutive steps of one strip; t0 = t of the first step.  pout: where the edge lane stores the result of
- * the first step (a global boundary row: +DIR per step; the next strip's ring: index (oi0 + j) & out_mask). */
+/* SW_FG consecutive steps of one strip; t0 = t of the first step.  pdst: this lane's dst element of the first step
+ * (+DIR*32 per step); pout: where the edge lane stores its result of the first step (+ostep per step). */
 template <int DIR, bool WITH_DOT, bool CHECKED, bool MASKED>
-__device__ __forceinline__ void sweep_steps(const StepOps<WITH_DOT>& op, const int t0, const int lane, const int w,
-                                            const bool yok, double* pdst, double* pout_base, const int oi0,
-                                            const int out_mask, const EdgeIn& feed,
-                                            double& dprev, double& cxprev, double& acc) {
+__device__ __forceinline__ void sweep_steps(const StepOps<WITH_DOT>& op, const double (&edge)[SW_FG], const int t0,
+                                            const int lane, const int w, const bool yok, double* pdst, double* pout,
+                                            const int ostep, double& dprev, double& cxprev, double& acc) {
     constexpr int E_OUT = DIR > 0 ? 31 : 0;
     const int srclane = (lane - DIR) & 31;          /* rotation: E_IN reads from E_OUT */
     const bool is_out = lane == E_OUT;
-    const bool ring_out = out_mask != 0x7fffffff;
 #pragma unroll
     for (int j = 0; j < SW_FG; j++) {
         const double pr = op.pr[j];
-        const double give = is_out ? feed.cur[j] : dprev;
+        const double give = is_out ? edge[j] : dprev;
         const double dn = __shfl_sync(0xffffffffu, give, srclane);
         double v = op.a[j];
         if (DIR > 0) {
@@ -606,17 +590,16 @@ __device__ __forceinline__ void sweep_steps(const StepOps<WITH_DOT>& op, const i
         double d = v * pr;
         const bool fluid = MASKED ? (pr == pr) : true;      /* NaN precon tags a non-fluid cell (k_precon_coeffs) */
         if (MASKED) d = fluid ? d : 0.0;                     /* skipped cell: dst stays, neighbours see +0.0 */
-        double* po = ring_out ? pout_base + ((oi0 + j) & out_mask) : pout_base + (oi0 + DIR * j);
         if (CHECKED) {
             const int x = t0 + DIR * j - lane;
             const bool active = yok && x >= 0 && x < w;
             if (active && fluid) pdst[DIR * j * 32] = d;
-            if (x >= 0 && x < w && is_out) *po = d;          /* the edge value is published for every column */
+            if (x >= 0 && x < w && is_out) pout[ostep * j] = d;       /* the edge value is published for every column */
         } else {
             /* interior block: only rows y >= h are inactive; they hold +0.0, and storing +0.0 into
              * their (zero) padding cells keeps the padding zero -- no branch needed */
             if (fluid) pdst[DIR * j * 32] = d;
-            if (is_out) *po = d;
+            if (is_out) pout[ostep * j] = d;
         }
         /* inactive lanes hold +0.0 and rr is zero in the padding: adding them is exact */
         if (WITH_DOT) acc += d * op.rr[j];
@@ -641,12 +624,14 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     namespace cg = cooperative_groups;
     constexpr int U = SW_U;
     constexpr int S = SW_STAGES;
+    constexpr int NG = SW_U / SW_FG;                                  /* groups per block */
     constexpr int STAGE = (WITH_DOT ? 2 : 1) * SW_TILE + SW_PACK;     /* doubles per stage */
     constexpr int E_IN = DIR > 0 ? 0 : 31;
     constexpr int E_OUT = DIR > 0 ? 31 : 0;
+    static_assert(NG == 2, "the group ping-pong below assumes two groups per block");
     extern __shared__ __align__(128) unsigned char wf_smem[];
     __shared__ double s_inbox[WF_WARPS][SW_RB];          /* edge-row rings of this block's strips */
-    __shared__ volatile int s_credit[WF_WARPS];          /* values consumed by the strip after mine */
+    __shared__ volatile int s_credit[WF_WARPS];          /* steps of MINE the strip after me has consumed */
     __shared__ int s_ticket;
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
@@ -703,10 +688,13 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
 
         /* incoming edge: my own ring unless I am the first strip of the cluster (then a global boundary row) */
         const bool in_ring = cslot > 0;
-        EdgeIn feed;
-        feed.init(!has_prev ? 0 : (in_ring ? 2 : 1),
-                  in_ring ? &s_inbox[warp][0] : (has_prev ? bnd + (long long)(k - DIR) * w : nullptr),
-                  in_ring ? &s_inbox[warp][0] : nullptr, w, lane == E_OUT);
+        EdgeSrc feed;
+        feed.mode = !has_prev ? 0 : (in_ring ? 2 : 1);
+        feed.src = in_ring ? &s_inbox[warp][0] : (has_prev ? bnd + (long long)(k - DIR) * w : nullptr);
+        feed.ring = in_ring ? &s_inbox[warp][0] : nullptr;
+        feed.w = w;
+        feed.feeder = (lane == E_OUT) && feed.mode != 0;
+        const bool use_feed = feed.mode != 0;                             /* warp uniform */
         /* outgoing edge: the next strip's ring (mapped shared memory of its block) unless I am the last strip of
          * the cluster / of my slab (then the global boundary row, possibly in the neighbour GPU's memory) */
         const bool out_ring = (cslot < csize * WF_WARPS - 1) && (slot + 1 < nown);
@@ -716,15 +704,13 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
         if (out_ring) out_base = cluster.map_shared_rank(&s_inbox[(cslot + 1) % WF_WARPS][0], (cslot + 1) / WF_WARPS);
         else out_base = (to_peer ? bnd_peer : bnd) + (long long)k * w;
         if (in_ring) credit_of_prev = cluster.map_shared_rank((int*)&s_credit[(cslot - 1) % WF_WARPS], (cslot - 1) / WF_WARPS);
-        const int out_mask = out_ring ? SW_RB - 1 : 0x7fffffff;
+        /* per step the edge lane's store moves by +1 slot in a ring, by DIR columns in a global row */
+        const int ostep = out_ring ? 1 : DIR;
 
-        /* sequence numbers: the n-th edge value is column n (forward) or w-1-n (backward) */
-        const int xin_first = tfirst - E_IN;                               /* column the E_IN lane needs at step 0 */
-        const int nin_first = DIR > 0 ? xin_first : (w - 1 - xin_first);
-        const int xout_first = tfirst - E_OUT;
-        const int nout_first = DIR > 0 ? xout_first : (w - 1 - xout_first);
-        feed.prefetch(xin_first, nin_first, DIR);
-        feed.advance();
+        double eb[2][SW_FG];                                              /* edge values: two groups, ping-pong */
+#pragma unroll
+        for (int j = 0; j < SW_FG; j++) { eb[0][j] = 0.0; eb[1][j] = 0.0; }
+        if (use_feed) feed.fetch(eb[0], tfirst - E_IN, 0, DIR);
 
         double* pdst = dst + (long long)k * g.ss + lane + (long long)tfirst * 32;
         double dprev = 0.0, cxprev = 0.0;
@@ -736,9 +722,8 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
             const int tlo = DIR > 0 ? t0 : t0 - (U - 1);
             const bool interior = (tlo - 31 >= 0) && (tlo + U - 1 < w);
             if (out_ring) {
-                /* credit: the last value of this block must not lap the consumer's ring */
-                const int nlast = nout_first + b * U + U - 1;
-                for (unsigned spins = 0; nlast - s_credit[warp] >= SW_RB && spins < (1u << 24); spins++) {}
+                /* credit: the last step of this block must not lap the consumer's ring */
+                for (unsigned spins = 0; (b * U + U - 1) - s_credit[warp] >= SW_RB && spins < (1u << 24); spins++) {}
             }
             const long long wc0 = trace ? clock64() : 0;
             mbar_wait(&bars[st], (unsigned)((b / S) & 1));
@@ -749,30 +734,29 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
             StepOps<WITH_DOT> ops[2];
             ops[0].template load<DIR>(tile_a, tile_c, tile_r, 0);
 #pragma unroll
-            for (int gi = 0; gi < U / SW_FG; gi++) {
-                const int sofs = b * U + gi * SW_FG;                       /* steps done before this group */
+            for (int gi = 0; gi < NG; gi++) {
+                const int sc0 = b * U + gi * SW_FG;                        /* my step count at the group's first step */
                 const int tg = t0 + DIR * gi * SW_FG;
-                const int xin = tg - E_IN, nin = nin_first + sofs;
-                if (gi + 1 < U / SW_FG) ops[(gi + 1) & 1].template load<DIR>(tile_a, tile_c, tile_r, (gi + 1) * SW_FG);
-                feed.prefetch(xin + DIR * SW_FG, nin + SW_FG, DIR);        /* next group */
-                if (!feed.ready()) feed.wait(xin, nin, DIR);
-                feed.rearm(xin, nin, DIR);
+                const int xin = tg - E_IN;
+                if (gi + 1 < NG) ops[(gi + 1) & 1].template load<DIR>(tile_a, tile_c, tile_r, (gi + 1) * SW_FG);
+                if (use_feed) {
+                    feed.fetch(eb[(gi + 1) & 1], xin + DIR * SW_FG, sc0 + SW_FG, DIR);        /* next group */
+                    if (!feed.ready(eb[gi & 1])) feed.wait(eb[gi & 1], xin, sc0, DIR);
+                    feed.rearm(xin, sc0, DIR);
+                }
                 double* gd = pdst + DIR * gi * SW_FG * 32;
-                const int oi = out_ring ? nout_first + sofs : (tg - E_OUT);
+                double* po = out_ring ? out_base + (sc0 & (SW_RB - 1)) : out_base + (tg - E_OUT);
                 if (interior)
-                    sweep_steps<DIR, WITH_DOT, false, MASKED>(ops[gi & 1], tg, lane, w, yok, gd, out_base, oi, out_mask, feed, dprev, cxprev, acc);
+                    sweep_steps<DIR, WITH_DOT, false, MASKED>(ops[gi & 1], eb[gi & 1], tg, lane, w, yok, gd, po, ostep, dprev, cxprev, acc);
                 else
-                    sweep_steps<DIR, WITH_DOT, true, MASKED>(ops[gi & 1], tg, lane, w, yok, gd, out_base, oi, out_mask, feed, dprev, cxprev, acc);
-                feed.advance();
+                    sweep_steps<DIR, WITH_DOT, true, MASKED>(ops[gi & 1], eb[gi & 1], tg, lane, w, yok, gd, po, ostep, dprev, cxprev, acc);
             }
             pdst += DIR * U * 32;
             __syncwarp();
             if (lane == 0) {
                 if (b + S < nblk) issue(b + S);
-                if (credit_of_prev) {                                       /* values consumed so far */
-                    int consumed = nin_first + (b + 1) * U;
-                    *credit_of_prev = consumed < 0 ? 0 : consumed;
-                }
+                /* I have consumed my producer's steps up to (my step count + 31) */
+                if (credit_of_prev) *credit_of_prev = (b + 1) * U + 31;
             }
         }
         if (trace && lane == 0) {
