@@ -217,8 +217,8 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     SkewGeom& g = s->sx.g;
     g.w = s->w; g.h = s->h;
     g.nstrips = (s->h + 31) / 32;
-    g.tl = ((s->w + 31 + 15) / 16) * 16 + 16;
-    g.ss = (long long)g.tl * 32;
+    g.tl = (((s->w + IFL_SKB - 1) / IFL_SKB + 31 + 7) / 8) * 8 + 8;      /* m-rows: ceil(w/SKB)+31, padded to the staging block */
+    g.ss = (long long)g.tl * 32 * IFL_SKB;
     /* slab decomposition: rank r owns the strips [r*chunk, min((r+1)*chunk, nstrips)); arrays hold chunk*world strips */
     const int world = cfg->world_size;
     const int chunk = (g.nstrips + world - 1) / world;
@@ -234,7 +234,7 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     CU(cudaMemset(s->skew_block, 0, sizeof(double) * per * 8));
     double** vecs[8] = {&s->sx.r, &s->sx.p, &s->sx.z, &s->sx.s, &s->sx.adiag, &s->sx.aplusx, &s->sx.aplusy, &s->sx.precon};
     for (int i = 0; i < 8; i++) *vecs[i] = s->skew_block + per * i + guard;
-    const size_t npack = (size_t)strips_alloc * g.tl * 32 * 3;
+    const size_t npack = (size_t)strips_alloc * g.tl * 32 * IFL_SKB * 3;
     CU(cudaMalloc(&s->sx.pack_f, sizeof(double) * npack));
     CU(cudaMalloc(&s->sx.pack_b, sizeof(double) * npack));
     CU(cudaMemset(s->sx.pack_f, 0, sizeof(double) * npack));

@@ -60,21 +60,26 @@ __device__ __forceinline__ double cerp(double a, double b, double c, double d, c
 
 /* ---- strip-skewed layout ------------------------------------------------------
  * Every N-vector of the pressure solve (r p z s aDiag aPlusX aPlusY precon) lives in a
- * layout made for the lexicographic recurrences: rows are grouped in strips of 32; in
- * strip k the cell (x, y = 32k + l) is stored at  k*SS + (x + l)*32 + l.  One "t-row"
- * t = x + l is the anti-diagonal a warp (lane l = row l) processes in one step, and it
- * is 256 contiguous bytes.  tl = number of t-rows per strip (>= w + 31). */
+ * layout made for the lexicographic recurrences.  Rows are grouped in strips of 32 and
+ * columns in blocks of IFL_SKB cells; in strip k the cell (x, y = 32k + l), x = c*SKB + j,
+ * is stored at   k*SS + ((c + l)*32 + l)*SKB + j.
+ * One "m-row" m = c + l is what a warp (lane l = row l) processes in one wavefront step:
+ * every lane owns SKB consecutive cells of its row (a register-resident chain), the m-row is
+ * 32*SKB contiguous doubles, and a strip is one contiguous stream.  tl = m-rows per strip
+ * (>= ceil(w/SKB) + 31). */
+#define IFL_SKB 2
 struct SkewGeom {
     int w, h;
     int nstrips;
-    int tl;             /* t-rows per strip */
-    long long ss;       /* strip stride in elements = tl * 32 */
-    long long total;    /* nstrips * ss */
+    int tl;             /* m-rows per strip */
+    long long ss;       /* strip stride in elements = tl * 32 * SKB */
+    long long total;    /* allocated strips * ss */
     int s0, s1;         /* strips owned by this rank (slab decomposition); [0, nstrips) on a single GPU */
 };
 __device__ __host__ __forceinline__ long long skew_index(const SkewGeom& g, int x, int y) {
     int l = y & 31;
-    return (long long)(y >> 5) * g.ss + (long long)(x + l) * 32 + l;
+    int c = x / IFL_SKB, j = x - c * IFL_SKB;
+    return (long long)(y >> 5) * g.ss + ((long long)(c + l) * 32 + l) * IFL_SKB + j;
 }
 
 /* non-negative float bit patterns order like unsigned ints; NaN sorts above +inf */

@@ -156,22 +156,18 @@ void launch_add_inflow(cudaStream_t st, int variant, QGeom q, double* src, doubl
 }
 
 /* ---- row-major <-> skewed helpers ------------------------------------------------
- * Thread layout for kernels that touch both layouts: block (32, 8) over (lane l, t);
- * a warp works on one t-row (256 contiguous bytes in the skewed layout).  Row-major
- * accesses of such a warp walk an anti-diagonal; 8 consecutive t share their lines in L1. */
+ * Kernels that touch both layouts run one thread per cell (x, y) in row-major order and address the
+ * skewed side through skew_index(); they run once per step, so their strided skewed accesses are noise. */
 struct SkewPos { int x, y; long long i; bool ok; };
 __device__ __forceinline__ SkewPos skew_pos(const SkewGeom& g) {
     SkewPos s;
-    int l = threadIdx.x;
-    int t = blockIdx.x * blockDim.y + threadIdx.y;
-    int k = blockIdx.y;
-    s.x = t - l;
-    s.y = k * 32 + l;
-    s.i = (long long)k * g.ss + (long long)t * 32 + l;
-    s.ok = (t < g.tl) && s.x >= 0 && s.x < g.w && s.y < g.h;
+    s.x = blockIdx.x * blockDim.x + threadIdx.x;
+    s.y = blockIdx.y * blockDim.y + threadIdx.y;
+    s.ok = s.x < g.w && s.y < g.h;
+    s.i = s.ok ? skew_index(g, s.x, s.y) : 0;
     return s;
 }
-static dim3 skew_grid(const SkewGeom& g) { return dim3((g.tl + 7) / 8, g.nstrips); }
+static dim3 skew_grid(const SkewGeom& g) { return dim3((g.w + 31) / 32, (g.h + 7) / 8); }
 
 /* FluidSolver.buildRhs  F1:364 (=F2:379, F3:420) */
 __global__ void k_build_rhs(SkewGeom g, const double* __restrict__ u, const double* __restrict__ v,

@@ -170,16 +170,13 @@ void launch_fill_solid_fields(cudaStream_t st, const SolidQ& q, const ifl_body* 
 
 /* skewed fluid flags of the d-quantity (1 = CELL_FLUID), padding 0 */
 __global__ void k_cell_flags(SkewGeom g, const unsigned char* __restrict__ cell, unsigned char* __restrict__ fl) {
-    int l = threadIdx.x;
-    int t = blockIdx.x * blockDim.y + threadIdx.y;
-    int k = blockIdx.y;
-    if (t >= g.tl) return;
-    int x = t - l, y = k * 32 + l;
-    bool ok = x >= 0 && x < g.w && y < g.h;
-    fl[(long long)k * g.ss + (long long)t * 32 + l] = (ok && cell[(size_t)x + (size_t)y * g.w] == IFL_CELL_FLUID) ? 1 : 0;
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= g.w || y >= g.h) return;              /* padding stays 0 (allocation is zeroed, never written) */
+    fl[skew_index(g, x, y)] = cell[(size_t)x + (size_t)y * g.w] == IFL_CELL_FLUID ? 1 : 0;
 }
 void launch_cell_flags(cudaStream_t st, const SkewGeom& g, const unsigned char* cell, unsigned char* fl) {
-    k_cell_flags<<<dim3((g.tl + 7) / 8, g.nstrips), dim3(32, 8), 0, st>>>(g, cell, fl);
+    k_cell_flags<<<dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(32, 8), 0, st>>>(g, cell, fl);
 }
 
 /* ---- FluidSolver.setBoundaryCondition F4:948 (=F5:1062, F6:1154, F7:1185) --------------------
@@ -220,13 +217,11 @@ void launch_set_boundary(cudaStream_t st, int w, int h, const unsigned char* cel
 __global__ void k_build_rhs_solid(SkewGeom g, SolidView d, SolidView uq, SolidView vq, const double* __restrict__ u,
                                   const double* __restrict__ v, const ifl_body* __restrict__ bodies, int nbodies,
                                   double* __restrict__ r, double hx, int variant) {
-    int l = threadIdx.x;
-    int t = blockIdx.x * blockDim.y + threadIdx.y;
-    int k = blockIdx.y;
-    int x = t - l, y = k * 32 + l;
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
     int w = g.w, h = g.h;
-    if (t >= g.tl || x < 0 || x >= w || y >= h) return;
-    long long i = (long long)k * g.ss + (long long)t * 32 + l;
+    if (x >= w || y >= h) return;
+    long long i = skew_index(g, x, y);
     size_t idx = (size_t)x + (size_t)y * w;
     const double scale = 1.0 / hx;
     if (d.cell[idx] != IFL_CELL_FLUID) { r[i] = 0.0; return; }
@@ -248,7 +243,7 @@ __global__ void k_build_rhs_solid(SkewGeom g, SolidView d, SolidView uq, SolidVi
 }
 void launch_build_rhs_solid(cudaStream_t st, const SkewGeom& g, const SolidView& d, const SolidView& uq, const SolidView& vq,
                             const double* u, const double* v, const ifl_body* bodies, int nbodies, double* r, double hx, int variant) {
-    k_build_rhs_solid<<<dim3((g.tl + 7) / 8, g.nstrips), dim3(32, 8), 0, st>>>(g, d, uq, vq, u, v, bodies, nbodies, r, hx, variant);
+    k_build_rhs_solid<<<dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(32, 8), 0, st>>>(g, d, uq, vq, u, v, bodies, nbodies, r, hx, variant);
 }
 
 /* ---- computeDensities F7:854: faces receive 0.5*density from the cell before, then from their own cell */
@@ -304,13 +299,11 @@ __device__ __forceinline__ double fy(const MatrixArgs& a, int w, int x, int y) {
 }
 __global__ void k_build_matrix_solid(SkewGeom g, MatrixArgs a, double* __restrict__ adiag, double* __restrict__ aplusx,
                                      double* __restrict__ aplusy) {
-    int l = threadIdx.x;
-    int t = blockIdx.x * blockDim.y + threadIdx.y;
-    int k = blockIdx.y;
-    int x = t - l, y = k * 32 + l;
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
     int w = g.w, h = g.h;
-    if (t >= g.tl || x < 0 || x >= w || y >= h) return;
-    long long i = (long long)k * g.ss + (long long)t * 32 + l;
+    if (x >= w || y >= h) return;
+    long long i = skew_index(g, x, y);
     size_t idx = (size_t)x + (size_t)y * w;
     const bool fl = a.cell[idx] == IFL_CELL_FLUID;
     double dg = a.mode == 3 ? 1.0 : 0.0, px = 0.0, py = 0.0;
@@ -326,7 +319,7 @@ void launch_build_matrix_solid(cudaStream_t st, const SkewGeom& g, const unsigne
                                const double* ud, const double* vd, double scale, int mode,
                                double* adiag, double* aplusx, double* aplusy) {
     MatrixArgs a{cell, uvol, vvol, ud, vd, scale, mode};
-    k_build_matrix_solid<<<dim3((g.tl + 7) / 8, g.nstrips), dim3(32, 8), 0, st>>>(g, a, adiag, aplusx, aplusy);
+    k_build_matrix_solid<<<dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(32, 8), 0, st>>>(g, a, adiag, aplusx, aplusy);
 }
 
 /* ---- applyPressure F4:927 (=F5:1041, F6:1114) / F7:1148: only fluid cells contribute --------- */

@@ -21,15 +21,18 @@
  * Compiled with -fmad=false.
  */
 #include <cstdlib>
+#include <type_traits>
 #include <cooperative_groups.h>
 #include "ifl_internal.h"
 
 namespace ifl {
 
 static constexpr int EW_THREADS = 256;
-static constexpr int EW_TROWS = 64;    /* t-rows per element-wise block: 2048 elements, 8 per thread */
+static constexpr int EW_TROWS = 64 / IFL_SKB;   /* m-rows per element-wise block: 2048 elements, 8 per thread */
+static constexpr int EW_RPP = 8 / IFL_SKB;       /* m-rows covered by the 256 threads in one pass */
 static constexpr int WF_WARPS = 4;     /* strips (warps) per wavefront block */
-static constexpr int WF_U = 8;         /* register prefetch distance in steps */
+static constexpr int WF_U = 4;         /* register prefetch distance in macro-steps (build / Gauss-Seidel kernels) */
+static constexpr int SKB = IFL_SKB;    /* cells per lane per wavefront macro-step */
 
 static dim3 ew_grid(const SkewGeom& g) { return dim3((g.tl + EW_TROWS - 1) / EW_TROWS, g.s1 - g.s0); }
 int solve_partials_needed(const SkewGeom& g) { return (int)(((g.tl + EW_TROWS - 1) / EW_TROWS) * g.nstrips); }
@@ -37,18 +40,29 @@ static inline void count(SolveCtx& c, int n = 1) { if (c.launches) *c.launches +
 static inline SkewGeom full_geom(const SkewGeom& g) { SkewGeom f = g; f.s0 = 0; f.s1 = g.nstrips; return f; }
 static inline int single_gpu(const SolveCtx& c) { return c.comm == nullptr; }
 
-/* iteration helper of the element-wise kernels: thread handles 8 elements, t-rows
- * t0 + e*8 + warp, lane = l.  Visits in a fixed order (e ascending). */
+/* iteration helper of the element-wise kernels: a thread handles 8 elements; the 256 threads of a block cover
+ * EW_RPP consecutive m-rows per pass (element q = tid % (32*SKB) of its m-row: lane l_ = q / SKB, sub-column
+ * j_ = q % SKB), fully coalesced.  Visits in a fixed order (e ascending).  Neighbour indices of element i_:
+ * nl_/nr_ = (x-1,y)/(x+1,y), nu_/nd_ = (x,y-1)/(x,y+1) (the latter two may lie in the neighbouring strip). */
 #define IFL_EW_LOOP_BEGIN(g)                                                            \
     const int k_ = blockIdx.y + (g).s0;                                                 \
     const long long base_ = (long long)k_ * (g).ss;                                     \
-    const int l_ = threadIdx.x & 31;                                                    \
+    const int q_ = threadIdx.x % (32 * SKB);                                            \
+    const int l_ = q_ / SKB;                                                            \
+    const int j_ = q_ % SKB;                                                            \
     const int y_ = k_ * 32 + l_;                                                        \
     _Pragma("unroll") for (int e_ = 0; e_ < 8; e_++) {                                  \
-        const int t_ = blockIdx.x * EW_TROWS + e_ * 8 + (threadIdx.x >> 5);             \
-        const int x_ = t_ - l_;                                                         \
-        const long long i_ = base_ + (long long)t_ * 32 + l_;                           \
+        const int t_ = blockIdx.x * EW_TROWS + e_ * EW_RPP + threadIdx.x / (32 * SKB);  \
+        const int x_ = (t_ - l_) * SKB + j_;                                            \
+        const long long i_ = base_ + (long long)t_ * (32 * SKB) + q_;                   \
         const bool ok_ = (t_ < (g).tl) && x_ >= 0 && x_ < (g).w && y_ < (g).h;
+#define IFL_EW_NEIGHBOURS(g)                                                            \
+        const long long nl_ = (j_ > 0) ? (i_ - 1) : (i_ - 32 * SKB + (SKB - 1));        \
+        const long long nr_ = (j_ < SKB - 1) ? (i_ + 1) : (i_ + 32 * SKB - (SKB - 1));  \
+        const long long nu_ = (l_ > 0) ? (i_ - 33 * SKB)                                \
+            : (base_ - (g).ss + ((long long)(t_ + 31) * 32 + 31) * SKB + j_);           \
+        const long long nd_ = (l_ < 31) ? (i_ + 33 * SKB)                               \
+            : (base_ + (g).ss + ((long long)(t_ - 31) * 32) * SKB + j_);
 #define IFL_EW_LOOP_END }
 
 enum { DOT_NONE = 0, DOT_ZS = 1, DOT_SIGMA_INIT = 2, DOT_SIGMA_NEW = 3 };
@@ -131,19 +145,14 @@ k_matvec_dot(SkewGeom g, const double* __restrict__ adiag, const double* __restr
     __shared__ bool s_last;
     double acc = 0.0;
     IFL_EW_LOOP_BEGIN(g)
+        IFL_EW_NEIGHBOURS(g)
         if (ok_) {
             double bc = b[i_];
             double tv = adiag[i_] * bc;
-            if (x_ > 0) tv += ax[i_ - 32] * b[i_ - 32];
-            if (y_ > 0) {
-                long long j = (l_ > 0) ? (i_ - 33) : (base_ - g.ss + (long long)(t_ + 31) * 32 + 31);
-                tv += ay[j] * b[j];
-            }
-            if (x_ < g.w - 1) tv += ax[i_] * b[i_ + 32];
-            if (y_ < g.h - 1) {
-                long long j = (l_ < 31) ? (i_ + 33) : (base_ + g.ss + (long long)(t_ - 31) * 32);
-                tv += ay[i_] * b[j];
-            }
+            if (x_ > 0) tv += ax[nl_] * b[nl_];
+            if (y_ > 0) tv += ay[nu_] * b[nu_];
+            if (x_ < g.w - 1) tv += ax[i_] * b[nr_];
+            if (y_ < g.h - 1) tv += ay[i_] * b[nd_];
             dst[i_] = tv;                                   /* matrixVectorProduct is never masked (F6:1011) */
             if (fl == nullptr || fl[i_]) acc += tv * bc;    /* dotProduct: fluid cells only from F6 on (F6:999) */
         }
@@ -174,12 +183,13 @@ k_update_pr(SkewGeom g, double* __restrict__ p, const double* __restrict__ s, do
             unsigned bits = absf_bits(rv);
             m = bits > m ? bits : m;
         }
-        if (l_ == 0 && t_ < g.w) {
-            bnd_f[(long long)k_ * g.w + t_] = sentinel();
-            bnd_b[(long long)k_ * g.w + t_] = sentinel();
+        if (l_ == 0 && t_ * SKB + j_ < g.w) {
+            const int xb = t_ * SKB + j_;                  /* lane 0 works on column block t_ */
+            bnd_f[(long long)k_ * g.w + xb] = sentinel();
+            bnd_b[(long long)k_ * g.w + xb] = sentinel();
             /* slab decomposition: the rows my neighbours write into (their edge strips) are re-armed by me */
-            if (k_ == g.s0 && g.s0 > 0) bnd_f[(long long)(g.s0 - 1) * g.w + t_] = sentinel();
-            if (k_ == g.s1 - 1 && g.s1 < g.nstrips) bnd_b[(long long)g.s1 * g.w + t_] = sentinel();
+            if (k_ == g.s0 && g.s0 > 0) bnd_f[(long long)(g.s0 - 1) * g.w + xb] = sentinel();
+            if (k_ == g.s1 - 1 && g.s1 < g.nstrips) bnd_b[(long long)g.s1 * g.w + xb] = sentinel();
         }
     IFL_EW_LOOP_END
 #pragma unroll
@@ -310,9 +320,10 @@ __global__ void k_dot_sequential(SkewGeom g, const double* __restrict__ a, const
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double result = 0.0;
     for (int y = 0; y < g.h; y++) {
-        long long i = skew_index(g, 0, y);
-        for (int x = 0; x < g.w; x++, i += 32)
+        for (int x = 0; x < g.w; x++) {
+            const long long i = skew_index(g, x, y);
             if (fl == nullptr || fl[i]) result += a[i] * b[i];
+        }
     }
     apply_dot_result(sc, mode, result);
 }
@@ -330,11 +341,12 @@ __device__ __forceinline__ int claim_slot(unsigned int* ticket, int nstrips) {
     return slot < nstrips ? slot : -1;
 }
 
-/* Flag-in-data feed of the neighbouring strip's edge row.  Lane j (< U) owns the value the
- * edge lane needs at step j of the current block; `get(j)` spins (warp-uniformly) until
- * the producer has replaced the sentinel. */
+/* Flag-in-data feed of the neighbouring strip's edge row.  Lane q (< U*SKB) owns the value the edge lane needs
+ * for sub-column q % SKB of macro-step q / SKB of the current block; `get(q)` spins (warp-uniformly) until the
+ * producer has replaced the sentinel. */
 template <int U>
 struct EdgeFeed {
+    static_assert(U * SKB <= 32, "one value per lane");
     const double* row;   /* neighbour strip's boundary row or nullptr */
     int w;
     double cur, nxt;
@@ -343,73 +355,24 @@ struct EdgeFeed {
     __device__ __forceinline__ void init(const double* r, int w_) {
         row = r; w = w_; cur = 0.0; nxt = 0.0; acur = nullptr; anxt = nullptr;
     }
-    /* start fetching the values of the block whose step j needs column xin(j) */
-    __device__ __forceinline__ void prefetch(int xin_for_my_lane, int lane) {
+    /* start fetching the values of the block whose first macro-step needs column block c0 */
+    __device__ __forceinline__ void prefetch(int c0, int lane) {
         anxt = nullptr; nxt = 0.0;
-        if (row != nullptr && lane < U && xin_for_my_lane >= 0 && xin_for_my_lane < w) {
-            anxt = row + xin_for_my_lane;
+        const int x = c0 * SKB + lane;           /* (c0 + lane / SKB) * SKB + lane % SKB */
+        if (row != nullptr && lane < U * SKB && x >= 0 && x < w) {
+            anxt = row + x;
             nxt = ld_volatile(anxt);
         }
     }
     __device__ __forceinline__ void advance() { cur = nxt; acur = anxt; }
-    __device__ __forceinline__ double get(int j, int lane) {
-        double v = __shfl_sync(0xffffffffu, cur, j);
+    __device__ __forceinline__ double get(int q, int lane) {
+        double v = __shfl_sync(0xffffffffu, cur, q);
         while (is_sentinel(v)) {
             /* one round trip re-reads every value of the block that is still missing */
-            if (lane >= j && lane < U && acur != nullptr && is_sentinel(cur)) cur = ld_volatile(acur);
-            v = __shfl_sync(0xffffffffu, cur, j);
+            if (lane >= q && lane < U * SKB && acur != nullptr && is_sentinel(cur)) cur = ld_volatile(acur);
+            v = __shfl_sync(0xffffffffu, cur, q);
         }
         return v;
-    }
-};
-
-
-/* Edge feed of the two triangular sweeps.  The lane whose result leaves the strip (E_OUT: lane 31
- * forward, lane 0 backward) is also the lane that READS the neighbouring strip's edge row: it puts
- * that value into the register every lane shuffles, and the shuffle is a rotation, so the lane on
- * the other edge (E_IN) receives the boundary value with the same single shuffle that hands every
- * other lane its neighbour's result -- no second shuffle or select on the dependency chain. */
-template <int U>
-struct RotFeed {
-    const double* row;   /* neighbour strip's boundary row (only the feeder lane dereferences it) */
-    int w;
-    bool feeder;
-    double cur[U], nxt[U];
-    __device__ __forceinline__ void init(const double* r, int w_, bool feeder_) {
-        row = r; w = w_; feeder = feeder_ && (r != nullptr);
-#pragma unroll
-        for (int j = 0; j < U; j++) { cur[j] = 0.0; nxt[j] = 0.0; }
-    }
-    /* x0 = column needed at step 0 of the block, columns advance by dir per step */
-    __device__ __forceinline__ void prefetch(int x0, int dir) {
-#pragma unroll
-        for (int j = 0; j < U; j++) {
-            const int x = x0 + dir * j;
-            nxt[j] = (feeder && x >= 0 && x < w) ? ld_volatile(row + x) : 0.0;
-        }
-    }
-    __device__ __forceinline__ void advance() {
-#pragma unroll
-        for (int j = 0; j < U; j++) cur[j] = nxt[j];
-    }
-    /* warp-uniform: are all values of the current block present? */
-    __device__ __forceinline__ bool ready() const {
-        bool ok = true;
-#pragma unroll
-        for (int j = 0; j < U; j++) ok = ok && !is_sentinel(cur[j]);
-        return __all_sync(0xffffffffu, ok);
-    }
-    /* spin until the value of step j (column x) has arrived; re-reads all missing later ones too */
-    __device__ __forceinline__ void wait(int j0, int x0, int dir) {
-        /* bounded: a producer that never shows up (a dead peer rank) must not hang the GPU; after ~2^22 polls the
-         * strip gives up and continues with 0.0 -- the result is then wrong, which the callers' checks expose */
-        for (unsigned spins = 0;; spins++) {
-            bool ok = !is_sentinel(cur[j0]) || spins > (1u << 22);
-            if (__all_sync(0xffffffffu, ok)) { if (is_sentinel(cur[j0])) cur[j0] = 0.0; return; }
-#pragma unroll
-            for (int j = 0; j < U; j++)
-                if (j >= j0 && is_sentinel(cur[j])) cur[j] = ld_volatile(row + x0 + dir * j);
-        }
     }
 };
 
@@ -430,6 +393,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     asm volatile(
         "{\n"
@@ -442,17 +408,31 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-static constexpr int SW_U = 16;                     /* steps (t-rows) per staged block of the triangular sweeps */
-static constexpr int SW_STAGES = 2;                 /* ring depth: block b+1 streams in while block b is computed */
-static constexpr int SW_TILE = SW_U * 32;           /* doubles per array per block (4 KB) */
-static constexpr int SW_PACK = 3 * SW_TILE;         /* packed coefficient block: 3 arrays (12 KB) */
-static constexpr int SW_FG = 8;                     /* steps per edge-feed group: granularity of the strip hand-over */
+#ifndef IFL_SW_U
+#define IFL_SW_U 4
+#endif
+#ifndef IFL_SW_STAGES
+#define IFL_SW_STAGES 10
+#endif
+#ifndef IFL_SW_WARPS
+#define IFL_SW_WARPS 2
+#endif
+static constexpr int SW_U = IFL_SW_U;               /* macro-steps (m-rows) per staged block of the triangular sweeps */
+static constexpr int SW_STAGES = IFL_SW_STAGES;     /* shared-memory ring depth per strip */
+static constexpr int SW_WARPS = IFL_SW_WARPS;       /* strips per block of the sweep kernel: few, so that each strip's operand ring
+                                                     * (~100 KB) covers the latency of the bulk copies; a wavefront over a w-wide
+                                                     * grid only ever has ~ (w/SKB + 31) / 40 strips in flight at a time */
+static constexpr int SW_TILE = SW_U * 32 * SKB;     /* doubles per array per block (2 KB) */
+static constexpr int SW_PACK = 3 * SW_TILE;         /* packed coefficient block: 3 arrays (6 KB) */
+static constexpr int SW_FG = 8;                     /* macro-steps per block of the sweep loop (edge-feed group, hand-over granularity) */
+static constexpr int SW_GV = SW_FG * SKB;           /* edge values per block */
+static_assert(SW_FG % SW_U == 0 && SW_FG % 2 == 0, "a block is a whole, even number of staged tiles");
 
 /* Packed sweep coefficients.  applyPreconditioner multiplies `aPlusX[i]*precon[i]` and
  * `aPlusY[i]*precon[i]` before it touches dst (F3:500,503,514,517); those products are the same in
  * every PCG iteration, so they are formed once per solve -- same operands, same rounding -- and
- * stored per strip in blocks of SW_U t-rows, [3][SW_U][32] doubles, so that ONE bulk copy fetches
- * every static operand of SW_U wavefront steps:
+ * stored per strip in blocks of SW_U m-rows, [3][SW_U][32][SKB] doubles, so that ONE bulk copy fetches
+ * every static operand of SW_U wavefront macro-steps:
  *     forward pack : cx = aPlusX*precon (own cell), cy = (aPlusY*precon) of the cell above, precon
  *     backward pack: cx = aPlusX*precon,            cy = aPlusY*precon (own cell),          precon */
 __global__ void __launch_bounds__(EW_THREADS)
@@ -461,28 +441,29 @@ k_precon_coeffs(SkewGeom g, const double* __restrict__ ax, const double* __restr
                 const unsigned char* __restrict__ fl) {
     const long long pstrip = (long long)(g.tl / SW_U) * SW_PACK;
     IFL_EW_LOOP_BEGIN(g)
+        IFL_EW_NEIGHBOURS(g)
         if (ok_) {
-            const long long j = (l_ > 0) ? (i_ - 33) : (base_ - g.ss + (long long)(t_ + 31) * 32 + 31);
             double pr = pre[i_];
             double cx = ax[i_] * pr;
             double cy = ay[i_] * pr;
-            double cyu = ay[j] * pre[j];
+            double cyu = ay[nu_] * pre[nu_];
             if (fl != nullptr) {
                 /* F4+: non-fluid cells are skipped by applyPreconditioner and never used as neighbours
                  * (F4:783-807).  They are tagged with a NaN precon (the sweep then neither computes nor
                  * stores them and hands +0.0 to its neighbours) and exact +0.0 products. */
-                if (!fl[j]) cyu = 0.0;
+                if (!fl[nu_]) cyu = 0.0;
                 if (!fl[i_]) { cx = 0.0; cy = 0.0; pr = __longlong_as_double(0x7ff8000000000b20ll); }
             }
-            const long long o = (long long)k_ * pstrip + (long long)(t_ / SW_U) * SW_PACK + (t_ % SW_U) * 32 + l_;
+            const long long o = (long long)k_ * pstrip + (long long)(t_ / SW_U) * SW_PACK + (t_ % SW_U) * (32 * SKB) + q_;
             pack_f[o] = cx; pack_f[o + SW_TILE] = cyu; pack_f[o + 2 * SW_TILE] = pr;
             pack_b[o] = cx; pack_b[o + SW_TILE] = cy;  pack_b[o + 2 * SW_TILE] = pr;
+            (void)nl_; (void)nr_; (void)nd_;
         }
     IFL_EW_LOOP_END
 }
 
 /* ---- strip hand-over inside a thread-block cluster ---------------------------------------------------
- * Consecutive strips run on consecutive warps of a cluster (SW_CL blocks x WF_WARPS warps).  A strip hands its
+ * Consecutive strips run on consecutive warps of a cluster (SW_CL blocks x SW_WARPS warps).  A strip hands its
  * edge row to the next one through a small ring in the CONSUMER's shared memory, written with distributed-
  * shared-memory stores (same block: plain shared stores through the same mapped address):
  *   - flag-in-data again: a slot holds the sentinel until the n-th edge value is stored; the consumer polls its
@@ -497,113 +478,216 @@ static constexpr int SW_RB = 128;                  /* ring slots per strip inbox
 /* sentinel test on the high word only (0xFFF8B200: a NaN payload no arithmetic produces) */
 __device__ __forceinline__ bool is_sentinel_hi(double v) { return __double2hiint(v) == (int)0xFFF8B200; }
 
-/* Incoming edge values of one group of SW_FG steps.  In ring mode a value lives in slot (producer step & 127), and
- * the producer's step is the consumer's step + 31; in global-row mode the index is the column. */
+/* Incoming edge values of one group of SW_FG macro-steps (SKB values each).  In ring mode the values of a producer
+ * macro-step live in slots (producer step & 127)*SKB + j, and the producer's step is the consumer's step + 31; in
+ * global-row mode the index is the column. */
 struct EdgeSrc {
     const double* src;        /* global boundary row, or this warp's shared-memory ring (generic address) */
     double* ring;             /* the ring, writable (re-arm); nullptr in global mode */
     int w;
     bool feeder;              /* this lane reads the edge values */
     int mode;                 /* 0 none, 1 global row, 2 ring */
-    __device__ __forceinline__ int index(int x, int sc) const { return mode == 2 ? ((sc + 31) & (SW_RB - 1)) : x; }
-    /* x0 / sc0: column and consumer step count of the group's first step; they advance by (dir, +1) per step */
-    __device__ __forceinline__ void fetch(double (&v)[SW_FG], int x0, int sc0, int dir) const {
+    __device__ __forceinline__ int index(int x, int sc, int j) const {
+        return mode == 2 ? (((sc + 31) & (SW_RB - 1)) * SKB + j) : x;
+    }
+    /* c0 / sc0: column block and consumer step count of the group's first macro-step; they advance by (dir, +1) */
+    __device__ __forceinline__ void fetch(double (&v)[SW_GV], int c0, int sc0, int dir) const {
 #pragma unroll
-        for (int j = 0; j < SW_FG; j++) {
-            const int x = x0 + dir * j;
-            v[j] = (feeder && x >= 0 && x < w) ? ld_volatile(src + index(x, sc0 + j)) : 0.0;
+        for (int s = 0; s < SW_FG; s++)
+#pragma unroll
+            for (int j = 0; j < SKB; j++) {
+                const int x = (c0 + dir * s) * SKB + j;
+                v[s * SKB + j] = (feeder && x >= 0 && x < w) ? ld_volatile(src + index(x, sc0 + s, j)) : 0.0;
+            }
+    }
+    /* ring mode, every column of the block valid: the SW_GV values are consecutive, 16-byte aligned slots */
+    __device__ __forceinline__ void fetch_ring(double (&v)[SW_GV], int sc0) const {
+        const double* p = src + ((sc0 + 31) & (SW_RB - 1)) * SKB;
+#pragma unroll
+        for (int i = 0; i < SW_GV; i += 2) {
+            double2 t;
+            asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(smem_u32(p + i)));
+            v[i] = t.x; v[i + 1] = t.y;
         }
     }
-    __device__ __forceinline__ bool ready(const double (&v)[SW_FG]) const {
+    /* tight poll on the value that is stored last, then the whole block again (the caller re-checks every value:
+     * stores of one thread to different addresses need not become visible in order) */
+    __device__ __forceinline__ void wait_ring(double (&v)[SW_GV], int sc0) const {
+        const unsigned last_hi = smem_u32(src + ((sc0 + 31) & (SW_RB - 1)) * SKB + (SW_GV - 1)) + 4u;
+        unsigned hi, spins = 0;
+        do {
+            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(hi) : "r"(last_hi));
+        } while (hi == 0xFFF8B200u && ++spins < (1u << 24));
+        fetch_ring(v, sc0);
+    }
+    __device__ __forceinline__ void rearm_ring(int sc0) const {
+        double* p = ring + ((sc0 + 31) & (SW_RB - 1)) * SKB;
+        const double sv = sentinel();
+#pragma unroll
+        for (int i = 0; i < SW_GV; i += 2) *reinterpret_cast<double2*>(p + i) = make_double2(sv, sv);
+    }
+    __device__ __forceinline__ bool ready(const double (&v)[SW_GV]) const {
         bool ok = true;
 #pragma unroll
-        for (int j = 0; j < SW_FG; j++) ok = ok && !is_sentinel_hi(v[j]);
+        for (int i = 0; i < SW_GV; i++) ok = ok && !is_sentinel_hi(v[i]);
         return __all_sync(0xffffffffu, ok);
     }
     /* spin (bounded) until every value of the group has arrived */
-    __device__ __forceinline__ void wait(double (&v)[SW_FG], int x0, int sc0, int dir) const {
+    __device__ __forceinline__ void wait(double (&v)[SW_GV], int c0, int sc0, int dir) const {
         for (unsigned spins = 0;; spins++) {
             bool ok = true;
 #pragma unroll
-            for (int j = 0; j < SW_FG; j++) ok = ok && !is_sentinel_hi(v[j]);
+            for (int i = 0; i < SW_GV; i++) ok = ok && !is_sentinel_hi(v[i]);
             ok = ok || spins > (1u << 24);
             if (__all_sync(0xffffffffu, ok)) break;
 #pragma unroll
-            for (int j = 0; j < SW_FG; j++)
-                if (is_sentinel_hi(v[j])) v[j] = ld_volatile(src + index(x0 + dir * j, sc0 + j));
+            for (int s = 0; s < SW_FG; s++)
+#pragma unroll
+                for (int j = 0; j < SKB; j++)
+                    if (is_sentinel_hi(v[s * SKB + j]))
+                        v[s * SKB + j] = ld_volatile(src + index((c0 + dir * s) * SKB + j, sc0 + s, j));
         }
 #pragma unroll
-        for (int j = 0; j < SW_FG; j++) if (is_sentinel_hi(v[j])) v[j] = 0.0;     /* gave up: dead producer */
+        for (int i = 0; i < SW_GV; i++) if (is_sentinel_hi(v[i])) v[i] = 0.0;     /* gave up: dead producer */
     }
-    __device__ __forceinline__ void rearm(int x0, int sc0, int dir) const {
+    __device__ __forceinline__ void rearm(int c0, int sc0, int dir) const {
         if (mode != 2 || !feeder) return;
 #pragma unroll
-        for (int j = 0; j < SW_FG; j++) {
-            const int x = x0 + dir * j;
-            if (x >= 0 && x < w) ring[(sc0 + 31 + j) & (SW_RB - 1)] = sentinel();
-        }
-    }
-};
-
-/* operands of SW_FG steps, loaded from the staged tiles one group ahead of their use: with one warp per
- * scheduler nothing hides a shared-memory load that sits between two dependent FP64 operations */
-template <bool WITH_DOT>
-struct StepOps {
-    double a[SW_FG], cx[SW_FG], cy[SW_FG], pr[SW_FG], rr[SW_FG];
-    template <int DIR>
-    __device__ __forceinline__ void load(const double* tile_a, const double* tile_c, const double* tile_r, int j0) {
+        for (int s = 0; s < SW_FG; s++)
 #pragma unroll
-        for (int j = 0; j < SW_FG; j++) {
-            const int row = (DIR > 0 ? (j0 + j) : SW_U - 1 - (j0 + j)) * 32;
-            a[j] = tile_a[row];
-            cx[j] = tile_c[row];
-            cy[j] = tile_c[SW_TILE + row];
-            pr[j] = tile_c[2 * SW_TILE + row];
-            rr[j] = WITH_DOT ? tile_r[row] : 0.0;
-        }
+            for (int j = 0; j < SKB; j++) {
+                const int x = (c0 + dir * s) * SKB + j;
+                if (x >= 0 && x < w) ring[((sc0 + 31 + s) & (SW_RB - 1)) * SKB + j] = sentinel();
+            }
     }
 };
 
-/* SW_FG consecutive steps of one strip; t0 = t of the first step.  pdst: this lane's dst element of the first step
- * (+DIR*32 per step); pout: where the edge lane stores its result of the first step (+ostep per step). */
+/* the SKB adjacent cells of one lane and macro-step (16-byte aligned in every skewed array and staged tile) */
+__device__ __forceinline__ void load_cells(const double* p, double* out) {
+    if (SKB == 2) { const double2 t = *reinterpret_cast<const double2*>(p); out[0] = t.x; out[SKB - 1] = t.y; }
+    else {
+#pragma unroll
+        for (int j = 0; j < SKB; j++) out[j] = p[j];
+    }
+}
+__device__ __forceinline__ void store_cells(double* p, const double (&d)[SKB]) {
+    if (SKB == 2) *reinterpret_cast<double2*>(p) = make_double2(d[0], d[SKB - 1]);
+    else {
+#pragma unroll
+        for (int j = 0; j < SKB; j++) p[j] = d[j];
+    }
+}
+
+/* operands of one macro-step of one lane: SKB adjacent cells of every staged array (one 16-byte shared-memory load
+ * per array for SKB = 2).  They are fetched one macro-step ahead of their use: with one warp per scheduler nothing
+ * else hides a shared-memory load that sits between two dependent FP64 operations. */
+struct CellOps {
+    double a[SKB], cx[SKB], cy[SKB], pr[SKB], rr[SKB];
+};
+__device__ __forceinline__ void lds_cells(unsigned addr, double* out) {
+    static_assert(SKB == 2, "one 16-byte shared-memory load per array and macro-step");
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(out[0]), "=d"(out[1]) : "r"(addr));
+}
+/* stage layout: [src tile | cx | cy | pr | rr tile]; `tile` = shared address of this lane's cells of the tile's first row */
+template <int DIR, bool WITH_DOT>
+__device__ __forceinline__ void load_step(CellOps& o, unsigned tile, int row) {
+    const unsigned p = tile + (unsigned)((DIR > 0 ? row : SW_U - 1 - row) * (32 * SKB) * sizeof(double));
+    lds_cells(p, o.a);
+    lds_cells(p + SW_TILE * (unsigned)sizeof(double), o.cx);
+    lds_cells(p + 2 * SW_TILE * (unsigned)sizeof(double), o.cy);
+    lds_cells(p + 3 * SW_TILE * (unsigned)sizeof(double), o.pr);
+    if (WITH_DOT) lds_cells(p + (SW_TILE + SW_PACK) * (unsigned)sizeof(double), o.rr);
+}
+
+/* predicated stores without a branch (a divergent branch plus reconvergence costs more than a macro-step's arithmetic) */
+__device__ __forceinline__ void st_if(bool p, double* addr, double v) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.f64 [%1], %2;\n}" ::"r"((unsigned)p), "l"(addr), "d"(v));
+}
+__device__ __forceinline__ void st_int_if(bool p, volatile int* addr, int v) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.volatile.s32 [%1], %2;\n}" ::"r"((unsigned)p), "l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_if(bool p, unsigned bar) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q mbarrier.arrive.shared::cta.b64 _, [%1];\n}" ::"r"((unsigned)p), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "IFL_WAITU:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra IFL_DONEU;\n"
+        "bra IFL_WAITU;\n"
+        "IFL_DONEU:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+/* keeps a value in a register: the compiler would otherwise re-derive shared-memory addresses from the thread id on
+ * every use, which costs issue slots on a one-warp-per-scheduler critical path */
+__device__ __forceinline__ unsigned pin_u32(unsigned v) { asm volatile("mov.u32 %0, %0;" : "+r"(v)); return v; }
+
+/* One macro-step of one lane: the SKB cells x = (m - lane)*SKB + j of its row, in the sweep's direction.  The left/right
+ * neighbour is the previous cell of the same lane (a register); the upper/lower neighbours `dn` are the SKB results of
+ * the adjacent lane's PREVIOUS macro-step.  Each result is shuffled to the adjacent lane as soon as it exists (dn_next),
+ * so the shuffle latency overlaps the rest of the lane's own dependency chain; `edge_next` is what the edge lane
+ * injects into that rotation (the neighbouring strip's values for the NEXT macro-step), nullptr = no early shuffle. */
 template <int DIR, bool WITH_DOT, bool CHECKED, bool MASKED>
-__device__ __forceinline__ void sweep_steps(const StepOps<WITH_DOT>& op, const double (&edge)[SW_FG], const int t0,
-                                            const int lane, const int w, const bool yok, double* pdst, double* pout,
-                                            const int ostep, double& dprev, double& cxprev, double& acc) {
-    constexpr int E_OUT = DIR > 0 ? 31 : 0;
-    const int srclane = (lane - DIR) & 31;          /* rotation: E_IN reads from E_OUT */
-    const bool is_out = lane == E_OUT;
+__device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB], const double* edge_next, const int m,
+                                           const int lane, const int srclane, const bool is_out, const int w, const bool yok,
+                                           double* pd, double* po, double* dummy, double (&dprev)[SKB], double& cxprev,
+                                           double& acc) {
+    double dl = DIR > 0 ? dprev[SKB - 1] : dprev[0];
+    bool fl[SKB];
+    double dnn[SKB];
 #pragma unroll
-    for (int j = 0; j < SW_FG; j++) {
+    for (int jj = 0; jj < SKB; jj++) {
+        const int j = DIR > 0 ? jj : SKB - 1 - jj;
         const double pr = op.pr[j];
-        const double give = is_out ? edge[j] : dprev;
-        const double dn = __shfl_sync(0xffffffffu, give, srclane);
         double v = op.a[j];
         if (DIR > 0) {
-            v = v - cxprev * dprev;      /* (aPlusX[i-1]*precon[i-1]) * dst[i-1]   F3:500 */
-            v = v - op.cy[j] * dn;       /* (aPlusY[i-w]*precon[i-w]) * dst[i-w]   F3:503 */
+            v = v - cxprev * dl;         /* (aPlusX[i-1]*precon[i-1]) * dst[i-1]   F3:500 */
+            v = v - op.cy[j] * dn[j];    /* (aPlusY[i-w]*precon[i-w]) * dst[i-w]   F3:503 */
             cxprev = op.cx[j];
         } else {
-            v = v - op.cx[j] * dprev;    /* (aPlusX[i]*precon[i]) * dst[i+1]       F3:514 */
-            v = v - op.cy[j] * dn;       /* (aPlusY[i]*precon[i]) * dst[i+w]       F3:517 */
+            v = v - op.cx[j] * dl;       /* (aPlusX[i]*precon[i]) * dst[i+1]       F3:514 */
+            v = v - op.cy[j] * dn[j];    /* (aPlusY[i]*precon[i]) * dst[i+w]       F3:517 */
         }
         double d = v * pr;
-        const bool fluid = MASKED ? (pr == pr) : true;      /* NaN precon tags a non-fluid cell (k_precon_coeffs) */
-        if (MASKED) d = fluid ? d : 0.0;                     /* skipped cell: dst stays, neighbours see +0.0 */
-        if (CHECKED) {
-            const int x = t0 + DIR * j - lane;
-            const bool active = yok && x >= 0 && x < w;
-            if (active && fluid) pdst[DIR * j * 32] = d;
-            if (x >= 0 && x < w && is_out) pout[ostep * j] = d;       /* the edge value is published for every column */
-        } else {
-            /* interior block: only rows y >= h are inactive; they hold +0.0, and storing +0.0 into
-             * their (zero) padding cells keeps the padding zero -- no branch needed */
-            if (fluid) pdst[DIR * j * 32] = d;
-            if (is_out) pout[ostep * j] = d;
+        fl[j] = MASKED ? (pr == pr) : true;              /* NaN precon tags a non-fluid cell (k_precon_coeffs) */
+        if (MASKED) d = fl[j] ? d : 0.0;                 /* skipped cell: dst stays, neighbours see +0.0 */
+        if (edge_next != nullptr) {                      /* hand the result to the adjacent lane right away */
+            const double give = is_out ? edge_next[j] : d;
+            dnn[j] = __shfl_sync(0xffffffffu, give, srclane);
         }
         /* inactive lanes hold +0.0 and rr is zero in the padding: adding them is exact */
         if (WITH_DOT) acc += d * op.rr[j];
-        dprev = d;
+        dprev[j] = d;
+        dl = d;
+    }
+    if (CHECKED) {
+        const int xb = (m - lane) * SKB;
+#pragma unroll
+        for (int j = 0; j < SKB; j++) {
+            const int x = xb + j;
+            const bool inx = x >= 0 && x < w;
+            st_if(yok && inx && fl[j], pd + j, dprev[j]);
+            st_if(inx && is_out, po + j, dprev[j]);           /* the edge value is published for every column */
+        }
+    } else {
+        /* interior block: only rows y >= h are inactive; they hold +0.0, and storing +0.0 into
+         * their (zero) padding cells keeps the padding zero -- no predicate needed.  Lanes that have nothing to
+         * store (not the edge lane; a non-fluid cell) store into a per-lane dummy slot instead: an unconditional
+         * store with a selected address, because a predicated store is turned into a divergent branch. */
+        if (MASKED) {
+#pragma unroll
+            for (int j = 0; j < SKB; j++) *(fl[j] ? pd + j : dummy + j) = dprev[j];
+        } else {
+            store_cells(pd, dprev);
+        }
+#pragma unroll
+        for (int j = 0; j < SKB; j++) po[j] = dprev[j];       /* po: the edge lane's slot, the dummy slot for the others */
+    }
+    if (edge_next != nullptr) {
+#pragma unroll
+        for (int j = 0; j < SKB; j++) dn[j] = dnn[j];
     }
 }
 
@@ -615,23 +699,27 @@ __device__ __forceinline__ void sweep_steps(const StepOps<WITH_DOT>& op, const d
  * guards are implicit: every skewed array is zero outside the grid (padding cells, plus one
  * all-zero strip before and after), and inactive lanes provably carry +0.0, so the guarded
  * products are +0.0 and `v - (+0.0)` returns v bit-for-bit (also for v = -0.0).  For the
- * backward sweep aPlusX(w-1,y) and aPlusY(x,h-1) are +0.0 by construction (F3:447,454). */
+ * backward sweep aPlusX(w-1,y) and aPlusY(x,h-1) are +0.0 by construction (F3:447,454).
+ *
+ * Block layout: SW_WARPS strip warps (0..SW_WARPS-1) and as many loader warps; loader warp SW_WARPS+i streams the
+ * operands of strip warp i into that warp's shared-memory ring with bulk copies (full/empty mbarrier pair per stage),
+ * so that no copy bookkeeping sits on the strip warp's dependency chain. */
 template <int DIR, bool WITH_DOT, bool MASKED>
-__global__ void __launch_bounds__(WF_WARPS * 32)
+__global__ void __launch_bounds__(2 * SW_WARPS * 32)
 k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restrict__ pack,
                const double* __restrict__ rr, double* bnd, double* bnd_peer, double* strip_part,
                SolveScalars* sc, int dot_mode, int check_done, long long* trace) {
     namespace cg = cooperative_groups;
-    constexpr int U = SW_U;
+    constexpr int U = SW_U;                                           /* macro-steps per staged tile */
+    constexpr int UB = SW_FG;                                         /* macro-steps per block of the loop */
     constexpr int S = SW_STAGES;
-    constexpr int NG = SW_U / SW_FG;                                  /* groups per block */
     constexpr int STAGE = (WITH_DOT ? 2 : 1) * SW_TILE + SW_PACK;     /* doubles per stage */
     constexpr int E_IN = DIR > 0 ? 0 : 31;
     constexpr int E_OUT = DIR > 0 ? 31 : 0;
-    static_assert(NG == 2, "the group ping-pong below assumes two groups per block");
     extern __shared__ __align__(128) unsigned char wf_smem[];
-    __shared__ double s_inbox[WF_WARPS][SW_RB];          /* edge-row rings of this block's strips */
-    __shared__ volatile int s_credit[WF_WARPS];          /* steps of MINE the strip after me has consumed */
+    __shared__ __align__(16) double s_inbox[SW_WARPS][SW_RB * SKB];   /* edge-row rings of this block's strips */
+    __shared__ volatile int s_credit[SW_WARPS];          /* steps of MINE the strip after me has consumed */
+    __shared__ __align__(16) double s_dummy[SW_WARPS][32][SKB];       /* where lanes with nothing to publish store */
     __shared__ int s_ticket;
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
@@ -639,9 +727,22 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     if (check_done && sc->done) return;                  /* uniform over the whole grid */
     const long long tr_enter = trace ? (long long)globaltimer_ns() : 0;
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    for (int i = lane; i < SW_RB; i += 32) s_inbox[warp][i] = sentinel();
-    if (lane == 0) s_credit[warp] = 0;
+    const bool loader = threadIdx.x >= SW_WARPS * 32;
+    const int warp = (threadIdx.x >> 5) - (loader ? SW_WARPS : 0);    /* strip warp index (own, or the one served) */
+    /* per-strip operand ring: S stages of [src tile | coefficient pack | rr tile]; then per strip S full + S empty mbarriers */
+    double* ring = reinterpret_cast<double*>(wf_smem) + (size_t)warp * S * STAGE;
+    unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(
+        wf_smem + (size_t)SW_WARPS * S * STAGE * sizeof(double)) + warp * 2 * S;
+    unsigned long long* bar_empty = bar_full + S;
+    if (!loader) {
+        for (int i = lane; i < SW_RB * SKB; i += 32) s_inbox[warp][i] = sentinel();
+        if (lane == 0) {
+            s_credit[warp] = 0;
+            for (int i = 0; i < S; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+    }
     /* one ticket per cluster: a waiting cluster's predecessor has started (no reliance on launch order) */
     if (crank == 0 && threadIdx.x == 0) {
         int tk = (int)atomicAdd(DIR > 0 ? &sc->ticket_f : &sc->ticket_b, 1u);
@@ -649,42 +750,53 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     }
     cluster.sync();
     const int nown = g.s1 - g.s0;
-    const int cslot = crank * WF_WARPS + warp;                        /* position inside the cluster */
-    const int slot = s_ticket * csize * WF_WARPS + cslot;
+    const int cslot = crank * SW_WARPS + warp;                        /* position inside the cluster */
+    const int slot = s_ticket * csize * SW_WARPS + cslot;
     const bool live = slot < nown;
     const int k = DIR > 0 ? g.s0 + slot : g.s1 - 1 - slot;
     const int w = g.w;
+    const int cw = (w + SKB - 1) / SKB;                               /* column blocks per row */
+    const int nblk = (cw + 31 + UB - 1) / UB;
+    const int ntile = nblk * (UB / U);
     double acc = 0.0;
-    if (live) {
+    if (live && loader) {
+        if (lane == 0) {
+            /* running pointers / shared addresses: this loop has to issue a tile faster than the strip warp consumes one */
+            const long long dtile = DIR > 0 ? SW_TILE : -SW_TILE;
+            const long long dpack = DIR > 0 ? SW_PACK : -SW_PACK;
+            const long long first = DIR > 0 ? 0 : ntile - 1;
+            const double* gsrc = src + (long long)k * g.ss + first * SW_TILE;
+            const double* grr = WITH_DOT ? rr + (long long)k * g.ss + first * SW_TILE : nullptr;
+            const double* gpack = pack + (long long)k * (g.tl / U) * SW_PACK + first * SW_PACK;
+            const unsigned ring0 = smem_u32(ring), full0 = smem_u32(bar_full), empty0 = smem_u32(bar_empty);
+            unsigned sdst = ring0, fb = full0, eb = empty0;
+            int st = 0;
+            unsigned ph = 1;                             /* parity of the completion that frees a stage; first lap: free */
+            /* one tile more than the strip has: the strip warp prefetches across every tile boundary without a test */
+            for (int b = 0; b <= ntile; b++) {
+                if (b >= S) mbar_wait_u32(eb, ph);
+                if (b == ntile && DIR < 0) { gsrc -= dtile; gpack -= dpack; if (WITH_DOT) grr -= dtile; }   /* stay inside */
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((unsigned)(STAGE * sizeof(double))) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sdst), "l"(gsrc), "r"((unsigned)(SW_TILE * sizeof(double))), "r"(fb) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sdst + (unsigned)(SW_TILE * sizeof(double))), "l"(gpack), "r"((unsigned)(SW_PACK * sizeof(double))), "r"(fb) : "memory");
+                if (WITH_DOT)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(sdst + (unsigned)((SW_TILE + SW_PACK) * sizeof(double))), "l"(grr), "r"((unsigned)(SW_TILE * sizeof(double))), "r"(fb) : "memory");
+                gsrc += dtile; gpack += dpack; if (WITH_DOT) grr += dtile;
+                sdst += (unsigned)(STAGE * sizeof(double)); fb += 8u; eb += 8u;
+                if (++st == S) { st = 0; ph ^= 1u; sdst = ring0; fb = full0; eb = empty0; }
+            }
+        }
+    } else if (live) {
         const int y = k * 32 + lane;
         const bool yok = y < g.h;
-        const int nblk = (w + 31 + U - 1) / U;
-        const int tfirst = DIR > 0 ? 0 : nblk * U - 1;
+        const int tfirst = DIR > 0 ? 0 : nblk * UB - 1;
         const bool has_prev = DIR > 0 ? (k > 0) : (k < g.nstrips - 1);
-
-        /* per-warp operand ring: S stages of [src tile | coefficient pack | rr tile], then S mbarriers */
-        double* ring = reinterpret_cast<double*>(wf_smem) + (size_t)warp * S * STAGE;
-        unsigned long long* bars = reinterpret_cast<unsigned long long*>(
-            wf_smem + (size_t)WF_WARPS * S * STAGE * sizeof(double)) + warp * S;
-        const double* gsrc = src + (long long)k * g.ss;
-        const double* grr = WITH_DOT ? rr + (long long)k * g.ss : nullptr;
-        const double* gpack = pack + (long long)k * (g.tl / U) * SW_PACK;
-        auto issue = [&](int b) {
-            const int st = b % S;
-            const int gb = DIR > 0 ? b : nblk - 1 - b;
-            double* sdst = ring + (size_t)st * STAGE;
-            mbar_expect_tx(&bars[st], STAGE * sizeof(double));
-            bulk_g2s(sdst, gsrc + (long long)gb * SW_TILE, SW_TILE * sizeof(double), &bars[st]);
-            bulk_g2s(sdst + SW_TILE, gpack + (long long)gb * SW_PACK, SW_PACK * sizeof(double), &bars[st]);
-            if (WITH_DOT) bulk_g2s(sdst + SW_TILE + SW_PACK, grr + (long long)gb * SW_TILE, SW_TILE * sizeof(double), &bars[st]);
-        };
-        if (lane == 0) {
-            for (int i = 0; i < S; i++) mbar_init(&bars[i], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            for (int b = 0; b < S && b < nblk; b++) issue(b);
-        }
-        __syncwarp();
+        const int srclane = (lane - DIR) & 31;                            /* rotation: E_IN reads from E_OUT */
+        const bool is_out = lane == E_OUT;
+        const bool lane0 = lane == 0;
 
         /* incoming edge: my own ring unless I am the first strip of the cluster (then a global boundary row) */
         const bool in_ring = cslot > 0;
@@ -693,79 +805,133 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
         feed.src = in_ring ? &s_inbox[warp][0] : (has_prev ? bnd + (long long)(k - DIR) * w : nullptr);
         feed.ring = in_ring ? &s_inbox[warp][0] : nullptr;
         feed.w = w;
-        feed.feeder = (lane == E_OUT) && feed.mode != 0;
+        feed.feeder = is_out && feed.mode != 0;
         const bool use_feed = feed.mode != 0;                             /* warp uniform */
+        const bool ring_feed = feed.mode == 2;
         /* outgoing edge: the next strip's ring (mapped shared memory of its block) unless I am the last strip of
          * the cluster / of my slab (then the global boundary row, possibly in the neighbour GPU's memory) */
-        const bool out_ring = (cslot < csize * WF_WARPS - 1) && (slot + 1 < nown);
+        const bool out_ring = (cslot < csize * SW_WARPS - 1) && (slot + 1 < nown);
         const bool to_peer = bnd_peer != nullptr && (DIR > 0 ? k == g.s1 - 1 : k == g.s0);
         double* out_base;
         volatile int* credit_of_prev = nullptr;
-        if (out_ring) out_base = cluster.map_shared_rank(&s_inbox[(cslot + 1) % WF_WARPS][0], (cslot + 1) / WF_WARPS);
+        if (out_ring) out_base = cluster.map_shared_rank(&s_inbox[(cslot + 1) % SW_WARPS][0], (cslot + 1) / SW_WARPS);
         else out_base = (to_peer ? bnd_peer : bnd) + (long long)k * w;
-        if (in_ring) credit_of_prev = cluster.map_shared_rank((int*)&s_credit[(cslot - 1) % WF_WARPS], (cslot - 1) / WF_WARPS);
-        /* per step the edge lane's store moves by +1 slot in a ring, by DIR columns in a global row */
-        const int ostep = out_ring ? 1 : DIR;
+        if (in_ring) credit_of_prev = cluster.map_shared_rank((int*)&s_credit[(cslot - 1) % SW_WARPS], (cslot - 1) / SW_WARPS);
+        const bool pub_credit = lane0 && credit_of_prev != nullptr;
+        /* per macro-step the edge lane's store moves by +1 slot group in a ring, by DIR column blocks in a global row */
+        const int ostep = out_ring ? SKB : DIR * SKB;
 
-        double eb[2][SW_FG];                                              /* edge values: two groups, ping-pong */
+        double* pdst = dst + (long long)k * g.ss + ((long long)tfirst * 32 + lane) * SKB;
+        double dprev[SKB];
 #pragma unroll
-        for (int j = 0; j < SW_FG; j++) { eb[0][j] = 0.0; eb[1][j] = 0.0; }
-        if (use_feed) feed.fetch(eb[0], tfirst - E_IN, 0, DIR);
+        for (int j = 0; j < SKB; j++) dprev[j] = 0.0;
+        double cxprev = 0.0;
+        long long tr_first = 0;
 
-        double* pdst = dst + (long long)k * g.ss + lane + (long long)tfirst * 32;
-        double dprev = 0.0, cxprev = 0.0;
-        long long tr_first = 0, wait_cyc = 0;
-        for (int b = 0; b < nblk; b++) {
-            const int t0 = tfirst + DIR * b * U;
-            const int st = b % S;
-            if (trace && b == 1) tr_first = (long long)globaltimer_ns();
-            const int tlo = DIR > 0 ? t0 : t0 - (U - 1);
-            const bool interior = (tlo - 31 >= 0) && (tlo + U - 1 < w);
-            if (out_ring) {
-                /* credit: the last step of this block must not lap the consumer's ring */
-                for (unsigned spins = 0; (b * U + U - 1) - s_credit[warp] >= SW_RB && spins < (1u << 24); spins++) {}
+        /* tile cursor: stage st holds the tile the operand loads currently read; shared addresses kept in registers */
+        const unsigned ring_lane = pin_u32(smem_u32(ring + lane * SKB));
+        const unsigned full0 = pin_u32(smem_u32(bar_full));
+        const unsigned empty0 = pin_u32(smem_u32(bar_empty));
+        int st = 0;
+        unsigned ph = 0;
+        unsigned tile = ring_lane;
+        /* edge-out stores are unconditional: the edge lane's pointer walks the ring / boundary row, every other lane
+         * keeps storing into its own dummy slot */
+        double* const dummy = &s_dummy[warp][lane][0];
+        const int ostep_lane = is_out ? ostep : 0;
+
+        CellOps ops[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < SKB; j++) { ops[i].a[j] = 0.0; ops[i].cx[j] = 0.0; ops[i].cy[j] = 0.0; ops[i].pr[j] = 0.0; ops[i].rr[j] = 0.0; }
+        mbar_wait_u32(full0, 0);
+        load_step<DIR, WITH_DOT>(ops[0], tile, 0);
+
+        /* UB macro-steps, fully unrolled and branch-free: operands of macro-step s+1 are fetched before macro-step s
+         * is computed; at a tile boundary the next stage is awaited first and the finished one handed back after */
+        auto run_block = [&](auto checked_tag, const int t0, const double (&ecur)[SW_GV], double* po_lane) {
+            constexpr bool CHECKED = decltype(checked_tag)::value;
+            double dn[SKB];
+#pragma unroll
+            for (int j = 0; j < SKB; j++) {
+                const double give = is_out ? ecur[j] : dprev[j];
+                dn[j] = __shfl_sync(0xffffffffu, give, srclane);
             }
-            const long long wc0 = trace ? clock64() : 0;
-            mbar_wait(&bars[st], (unsigned)((b / S) & 1));
-            if (trace) wait_cyc += clock64() - wc0;
-            const double* tile_a = ring + (size_t)st * STAGE + lane;
-            const double* tile_c = tile_a + SW_TILE;
-            const double* tile_r = tile_a + SW_TILE + SW_PACK;
-            StepOps<WITH_DOT> ops[2];
-            ops[0].template load<DIR>(tile_a, tile_c, tile_r, 0);
 #pragma unroll
-            for (int gi = 0; gi < NG; gi++) {
-                const int sc0 = b * U + gi * SW_FG;                        /* my step count at the group's first step */
-                const int tg = t0 + DIR * gi * SW_FG;
-                const int xin = tg - E_IN;
-                if (gi + 1 < NG) ops[(gi + 1) & 1].template load<DIR>(tile_a, tile_c, tile_r, (gi + 1) * SW_FG);
-                if (use_feed) {
-                    feed.fetch(eb[(gi + 1) & 1], xin + DIR * SW_FG, sc0 + SW_FG, DIR);        /* next group */
-                    if (!feed.ready(eb[gi & 1])) feed.wait(eb[gi & 1], xin, sc0, DIR);
-                    feed.rearm(xin, sc0, DIR);
+            for (int s = 0; s < UB; s++) {
+                const int r = (s + 1) % U;
+                unsigned done_bar = 0;
+                if (r == 0) {
+                    done_bar = empty0 + 8u * st;
+                    const bool wrap = st == S - 1;
+                    st = wrap ? 0 : st + 1;
+                    ph ^= wrap ? 1u : 0u;
+                    tile = ring_lane + (unsigned)(st * STAGE * (int)sizeof(double));
+                    mbar_wait_u32(full0 + 8u * st, ph);
                 }
-                double* gd = pdst + DIR * gi * SW_FG * 32;
-                double* po = out_ring ? out_base + (sc0 & (SW_RB - 1)) : out_base + (tg - E_OUT);
-                if (interior)
-                    sweep_steps<DIR, WITH_DOT, false, MASKED>(ops[gi & 1], eb[gi & 1], tg, lane, w, yok, gd, po, ostep, dprev, cxprev, acc);
-                else
-                    sweep_steps<DIR, WITH_DOT, true, MASKED>(ops[gi & 1], eb[gi & 1], tg, lane, w, yok, gd, po, ostep, dprev, cxprev, acc);
+                load_step<DIR, WITH_DOT>(ops[(s + 1) & 1], tile, r);
+                const double* en = (s + 1 < UB) ? &ecur[(s + 1) * SKB] : nullptr;
+                sweep_step<DIR, WITH_DOT, CHECKED, MASKED>(ops[s & 1], dn, en, t0 + DIR * s, lane, srclane, is_out, w, yok,
+                                                           pdst + DIR * s * (32 * SKB), po_lane + ostep_lane * s, dummy,
+                                                           dprev, cxprev, acc);
+                /* every row of the finished tile is in registers (the loads are warp-wide instructions issued, in
+                 * order, before this arrive): hand the stage back to the loader warp */
+                if (r == 0) mbar_arrive_if(lane0, done_bar);
             }
-            pdst += DIR * U * 32;
-            __syncwarp();
-            if (lane == 0) {
-                if (b + S < nblk) issue(b + S);
-                /* I have consumed my producer's steps up to (my step count + 31) */
-                if (credit_of_prev) *credit_of_prev = (b + 1) * U + 31;
+        };
+
+        auto do_block = [&](const int b, double (&ecur)[SW_GV], double (&enext)[SW_GV]) {
+            const int t0 = tfirst + DIR * b * UB;
+            if (trace && b == 1) tr_first = (long long)globaltimer_ns();
+            const int tlo = DIR > 0 ? t0 : t0 - (UB - 1);
+            const bool interior = (tlo - 31 >= 0) && ((tlo + UB - 1) * SKB + SKB - 1 < w);
+            if (out_ring && (b & 1) == 0) {
+                /* credit: the last step of the next two blocks must not lap the consumer's ring */
+                for (unsigned spins = 0; (b * UB + 2 * UB - 1) - s_credit[warp] >= SW_RB && spins < (1u << 24); spins++) {}
             }
+            const int sc0 = b * UB;                                        /* my step count at the block's first step */
+            const int cin = t0 - E_IN;                                     /* column block the edge lane needs first */
+            if (use_feed) {
+                /* ring fast path: all columns of the block exist and its slots do not wrap */
+                const int clo = DIR > 0 ? cin : cin - (UB - 1);
+                const bool allcols = clo >= 0 && (clo + UB - 1) * SKB + SKB - 1 < w;
+                const int cnl = clo + DIR * UB;
+                const bool allcols_next = cnl >= 0 && (cnl + UB - 1) * SKB + SKB - 1 < w;
+                if (ring_feed && allcols_next && ((sc0 + UB + 31) & (SW_RB - 1)) + UB <= SW_RB) feed.fetch_ring(enext, sc0 + UB);
+                else feed.fetch(enext, cin + DIR * UB, sc0 + UB, DIR);     /* next block */
+                const bool fast = ring_feed && allcols && ((sc0 + 31) & (SW_RB - 1)) + UB <= SW_RB;
+                if (!feed.ready(ecur)) {
+                    if (fast) feed.wait_ring(ecur, sc0);
+                    if (!feed.ready(ecur)) feed.wait(ecur, cin, sc0, DIR);
+                }
+                if (fast) feed.rearm_ring(sc0);
+                else feed.rearm(cin, sc0, DIR);
+            }
+            double* po = out_ring ? out_base + (sc0 & (SW_RB - 1)) * SKB : out_base + (t0 - E_OUT) * SKB;
+            double* po_lane = is_out ? po : dummy;
+            if (interior) run_block(std::false_type{}, t0, ecur, po_lane);
+            else          run_block(std::true_type{}, t0, ecur, po_lane);
+            pdst += DIR * UB * (32 * SKB);
+            /* I have consumed my producer's steps up to (my step count + 31) */
+            st_int_if(pub_credit, credit_of_prev, (b + 1) * UB + 31);
+        };
+
+        double eb0[SW_GV], eb1[SW_GV];                                     /* edge values: two blocks, ping-pong */
+#pragma unroll
+        for (int j = 0; j < SW_GV; j++) { eb0[j] = 0.0; eb1[j] = 0.0; }
+        if (use_feed) feed.fetch(eb0, tfirst - E_IN, 0, DIR);
+        for (int b = 0; b < nblk; b += 2) {
+            do_block(b, eb0, eb1);
+            if (b + 1 < nblk) do_block(b + 1, eb1, eb0);
         }
         if (trace && lane == 0) {
             long long* tr = trace + (long long)k * 8;
             tr[0] = tr_enter; tr[1] = tr_first; tr[2] = 0; tr[3] = (long long)globaltimer_ns();
-            tr[4] = wait_cyc; tr[5] = nblk; tr[6] = slot; tr[7] = (long long)get_smid();
+            tr[4] = 0; tr[5] = nblk; tr[6] = slot; tr[7] = (long long)get_smid();
         }
     }
-    if (WITH_DOT && live) {
+    if (WITH_DOT && live && !loader) {
         double ws = warp_sum(acc);
         if (lane == 0) {
             strip_part[k] = ws;
@@ -794,6 +960,7 @@ k_build_precon(SkewGeom g, const double* __restrict__ adiag, const double* __res
                const double* __restrict__ ay, double* pre, double* bnd, SolveScalars* sc,
                double tau, double sigma, const unsigned char* __restrict__ fl) {
     constexpr int U = WF_U;
+    constexpr int RS = 32 * SKB;                     /* doubles per m-row */
     const int slot = claim_slot(&sc->ticket_f, g.nstrips);
     if (slot < 0) return;
     const int k = slot;
@@ -801,76 +968,83 @@ k_build_precon(SkewGeom g, const double* __restrict__ adiag, const double* __res
     const int y = k * 32 + lane;
     const bool yok = y < g.h;
     const int w = g.w;
-    const long long base = (long long)k * g.ss + lane;
-    const int nblk = (w + 31 + U - 1) / U;
-    long long upbase = base - 33;
-    if (lane == 0) upbase = (long long)(k - 1) * g.ss + 31LL * 32 + 31;
+    const int cw = (w + SKB - 1) / SKB;
+    const long long base = (long long)k * g.ss + lane * SKB;
+    const int nblk = (cw + 31 + U - 1) / U;
+    long long upbase = base - 33 * SKB;
+    if (lane == 0) upbase = (long long)(k - 1) * g.ss + (31LL * 32 + 31) * SKB;
     const bool has_up = y > 0;
     const bool masked = fl != nullptr;
 
-    double AD[U], AX[U], AY[U], AXU[U], AYU[U];
-    unsigned char FL[U], FLU[U];
+    double AD[U][SKB], AX[U][SKB], AY[U][SKB], AXU[U][SKB], AYU[U][SKB];
+    unsigned char FL[U][SKB], FLU[U][SKB];
+    auto fetch = [&](int u, int m) {
 #pragma unroll
-    for (int j = 0; j < U; j++) {
-        int t = j;
-        AD[j] = adiag[base + (long long)t * 32];
-        AX[j] = ax[base + (long long)t * 32];
-        AY[j] = ay[base + (long long)t * 32];
-        bool okup = has_up && (t - lane) >= 0 && (t - lane) < w;
-        AXU[j] = okup ? ax[upbase + (long long)t * 32] : 0.0;
-        AYU[j] = okup ? ay[upbase + (long long)t * 32] : 0.0;
-        FL[j] = masked ? fl[base + (long long)t * 32] : 1;
-        FLU[j] = (masked && okup) ? fl[upbase + (long long)t * 32] : 1;
-    }
+        for (int j = 0; j < SKB; j++) {
+            const long long i = base + (long long)m * RS + j;
+            const long long iu = upbase + (long long)m * RS + j;
+            const int x = (m - lane) * SKB + j;
+            AD[u][j] = adiag[i];
+            AX[u][j] = ax[i];
+            AY[u][j] = ay[i];
+            const bool okup = has_up && x >= 0 && x < w;
+            AXU[u][j] = okup ? ax[iu] : 0.0;
+            AYU[u][j] = okup ? ay[iu] : 0.0;
+            FL[u][j] = masked ? fl[i] : 1;
+            FLU[u][j] = (masked && okup) ? fl[iu] : 1;
+        }
+    };
+#pragma unroll
+    for (int u = 0; u < U; u++) fetch(u, u);
     EdgeFeed<U> feed;
     feed.init(k > 0 ? bnd + (long long)(k - 1) * w : nullptr, w);
-    feed.prefetch(lane, lane);
+    feed.prefetch(0, lane);
     feed.advance();
 
-    double pprev = 0.0, axprev = 0.0, ayprev = 0.0;
+    double pprev[SKB];
+#pragma unroll
+    for (int j = 0; j < SKB; j++) pprev[j] = 0.0;
+    double pl = 0.0, axprev = 0.0, ayprev = 0.0;
     bool flprev = false;
     for (int b = 0; b < nblk; b++) {
-        const int t0 = b * U;
-        feed.prefetch(t0 + U + lane, lane);
+        const int m0 = b * U;
+        feed.prefetch(m0 + U, lane);
 #pragma unroll
-        for (int j = 0; j < U; j++) {
-            const int t = t0 + j;
-            const int x = t - lane;
-            double pu = __shfl_up_sync(0xffffffffu, pprev, 1);
-            const double bv = feed.get(j, lane);
-            if (lane == 0) pu = bv;
-            const double ad = AD[j];
-            const bool fself = FL[j] != 0;
-            double e = ad;
-            if (x > 0 && flprev) {
-                double px = axprev * pprev;
-                double py = ayprev * pprev;
-                e -= (px * px + tau * px * py);
+        for (int u = 0; u < U; u++) {
+            const int m = m0 + u;
+            double pu[SKB];
+#pragma unroll
+            for (int j = 0; j < SKB; j++) {
+                pu[j] = __shfl_up_sync(0xffffffffu, pprev[j], 1);
+                const double bv = feed.get(u * SKB + j, lane);
+                if (lane == 0) pu[j] = bv;
             }
-            if (y > 0 && FLU[j]) {
-                double px = AXU[j] * pu;
-                double py = AYU[j] * pu;
-                e -= (py * py + tau * px * py);
+#pragma unroll
+            for (int j = 0; j < SKB; j++) {
+                const int x = (m - lane) * SKB + j;
+                const double ad = AD[u][j];
+                const bool fself = FL[u][j] != 0;
+                double e = ad;
+                if (x > 0 && flprev) {
+                    double px = axprev * pl;
+                    double py = ayprev * pl;
+                    e -= (px * px + tau * px * py);
+                }
+                if (y > 0 && FLU[u][j]) {
+                    double px = AXU[u][j] * pu[j];
+                    double py = AYU[u][j] * pu[j];
+                    e -= (py * py + tau * px * py);
+                }
+                if (e < sigma * ad) e = ad;
+                const double pc = 1.0 / sqrt(e);
+                const bool active = yok && x >= 0 && x < w;
+                if (active) {
+                    if (fself) pre[base + (long long)m * RS + j] = pc;
+                    if (lane == 31) bnd[(long long)k * w + x] = fself ? pc : 0.0;   /* flag-in-data: always publish */
+                }
+                pprev[j] = pc; pl = pc; axprev = AX[u][j]; ayprev = AY[u][j]; flprev = fself;
             }
-            if (e < sigma * ad) e = ad;
-            const double pc = 1.0 / sqrt(e);
-            const bool active = yok && x >= 0 && x < w;
-            if (active) {
-                if (fself) pre[base + (long long)t * 32] = pc;
-                if (lane == 31) bnd[(long long)k * w + x] = fself ? pc : 0.0;   /* flag-in-data: always publish */
-            }
-            pprev = pc; axprev = AX[j]; ayprev = AY[j]; flprev = fself;
-            const int tn = t + U;
-            if (tn < g.tl) {
-                AD[j] = adiag[base + (long long)tn * 32];
-                AX[j] = ax[base + (long long)tn * 32];
-                AY[j] = ay[base + (long long)tn * 32];
-                bool okup = has_up && (tn - lane) >= 0 && (tn - lane) < w;
-                AXU[j] = okup ? ax[upbase + (long long)tn * 32] : 0.0;
-                AYU[j] = okup ? ay[upbase + (long long)tn * 32] : 0.0;
-                FL[j] = masked ? fl[base + (long long)tn * 32] : 1;
-                FLU[j] = (masked && okup) ? fl[upbase + (long long)tn * 32] : 1;
-            }
+            if (m + U < g.tl) fetch(u, m + U);
         }
         feed.advance();
     }
@@ -883,6 +1057,7 @@ __global__ void __launch_bounds__(WF_WARPS * 32)
 k_gs_sweep(SkewGeom g, const double* __restrict__ r, double* p, double* bnd_use, double* bnd_rearm,
            SolveScalars* sc, double scale, double tol) {
     constexpr int U = WF_U;
+    constexpr int RS = 32 * SKB;
     if (sc->done) return;
     const int slot = claim_slot(&sc->ticket_f, g.nstrips);
     if (slot < 0) return;
@@ -891,68 +1066,77 @@ k_gs_sweep(SkewGeom g, const double* __restrict__ r, double* p, double* bnd_use,
     const int y = k * 32 + lane;
     const bool yok = y < g.h;
     const int w = g.w, h = g.h;
-    const long long base = (long long)k * g.ss + lane;
-    const int nblk = (w + 31 + U - 1) / U;
+    const int cw = (w + SKB - 1) / SKB;
+    const long long base = (long long)k * g.ss + lane * SKB;
+    const int nblk = (cw + 31 + U - 1) / U;
     for (int x = lane; x < w; x += 32) bnd_rearm[(long long)k * w + x] = sentinel();
 
-    /* old value of the cell below: (x, y+1) is at i+33, or in the next strip's lane 0 */
-    long long dnbase = base + 33;
-    if (lane == 31) dnbase = (long long)(k + 1) * g.ss - 31LL * 32;
+    /* old value of the cell below: (x, y+1) is 33 lanes-slots further, or in the next strip's lane 0 */
+    long long dnbase = base + 33 * SKB;
+    if (lane == 31) dnbase = (long long)(k + 1) * g.ss - 31LL * RS;
     const bool has_dn = y < h - 1;
 
-    double R[U], PO[U], PD[U];
+    double R[U][SKB], PO[U][SKB], PD[U][SKB];
+    auto fetch = [&](int u, int m) {
 #pragma unroll
-    for (int j = 0; j < U; j++) {
-        int t = j;
-        R[j] = r[base + (long long)t * 32];
-        PO[j] = __ldcg(p + base + (long long)t * 32);
-        bool okdn = has_dn && (t - lane) >= 0 && (t - lane) < w;
-        PD[j] = okdn ? __ldcg(p + dnbase + (long long)t * 32) : 0.0;
-    }
+        for (int j = 0; j < SKB; j++) {
+            const int x = (m - lane) * SKB + j;
+            R[u][j] = r[base + (long long)m * RS + j];
+            PO[u][j] = __ldcg(p + base + (long long)m * RS + j);
+            const bool okdn = has_dn && x >= 0 && x < w;
+            PD[u][j] = okdn ? __ldcg(p + dnbase + (long long)m * RS + j) : 0.0;
+        }
+    };
+#pragma unroll
+    for (int u = 0; u < U; u++) fetch(u, u);
     EdgeFeed<U> feed;
     feed.init(k > 0 ? bnd_use + (long long)(k - 1) * w : nullptr, w);
-    feed.prefetch(lane, lane);
+    feed.prefetch(0, lane);
     feed.advance();
 
-    double pprev = 0.0;
+    double pprev[SKB];
+#pragma unroll
+    for (int j = 0; j < SKB; j++) pprev[j] = 0.0;
+    double pl = 0.0;
     unsigned long long mbits = 0ull;
     for (int b = 0; b < nblk; b++) {
-        const int t0 = b * U;
-        feed.prefetch(t0 + U + lane, lane);
+        const int m0 = b * U;
+        feed.prefetch(m0 + U, lane);
 #pragma unroll
-        for (int j = 0; j < U; j++) {
-            const int t = t0 + j;
-            const int x = t - lane;
-            double pu = __shfl_up_sync(0xffffffffu, pprev, 1);
-            const double bv = feed.get(j, lane);
-            if (lane == 0) pu = bv;
-            const double pold = PO[j];
-            /* fetch p(x+1, y) = own old value of the next step before it is needed; the
-             * register of step j+1 still holds it (rotation happens after use) */
-            const int tn = t + U;
-            const double pright = PO[(j + 1) % U];
-            double diag = 0.0, offDiag = 0.0;
-            if (x > 0)     { diag += scale; offDiag -= scale * pprev; }
-            if (y > 0)     { diag += scale; offDiag -= scale * pu; }
-            if (x < w - 1) { diag += scale; offDiag -= scale * pright; }
-            if (y < h - 1) { diag += scale; offDiag -= scale * PD[j]; }
-            const double newP = (R[j] - offDiag) / diag;
-            const bool active = yok && x >= 0 && x < w;
-            if (active) {
-                /* F1:414: old p rounded through float, difference taken in double */
-                double delta = fabs(jfloat(pold) - newP);
-                unsigned long long db = (unsigned long long)__double_as_longlong(delta);
-                mbits = db > mbits ? db : mbits;
-                p[base + (long long)t * 32] = newP;
-                if (lane == 31) bnd_use[(long long)k * w + x] = newP;
+        for (int u = 0; u < U; u++) {
+            const int m = m0 + u;
+            double pu[SKB];
+#pragma unroll
+            for (int j = 0; j < SKB; j++) {
+                pu[j] = __shfl_up_sync(0xffffffffu, pprev[j], 1);
+                const double bv = feed.get(u * SKB + j, lane);
+                if (lane == 0) pu[j] = bv;
             }
-            pprev = newP;
-            if (tn < g.tl) {
-                R[j] = r[base + (long long)tn * 32];
-                PO[j] = __ldcg(p + base + (long long)tn * 32);
-                bool okdn = has_dn && (tn - lane) >= 0 && (tn - lane) < w;
-                PD[j] = okdn ? __ldcg(p + dnbase + (long long)tn * 32) : 0.0;
+#pragma unroll
+            for (int j = 0; j < SKB; j++) {
+                const int x = (m - lane) * SKB + j;
+                const double pold = PO[u][j];
+                /* p(x+1, y) = own old value of the next cell; the registers of the next macro-step still
+                 * hold it (they are refilled only after their own use) */
+                const double pright = (j < SKB - 1) ? PO[u][(j + 1) % SKB] : PO[(u + 1) % U][0];
+                double diag = 0.0, offDiag = 0.0;
+                if (x > 0)     { diag += scale; offDiag -= scale * pl; }
+                if (y > 0)     { diag += scale; offDiag -= scale * pu[j]; }
+                if (x < w - 1) { diag += scale; offDiag -= scale * pright; }
+                if (y < h - 1) { diag += scale; offDiag -= scale * PD[u][j]; }
+                const double newP = (R[u][j] - offDiag) / diag;
+                const bool active = yok && x >= 0 && x < w;
+                if (active) {
+                    /* F1:414: old p rounded through float, difference taken in double */
+                    double delta = fabs(jfloat(pold) - newP);
+                    unsigned long long db = (unsigned long long)__double_as_longlong(delta);
+                    mbits = db > mbits ? db : mbits;
+                    p[base + (long long)m * RS + j] = newP;
+                    if (lane == 31) bnd_use[(long long)k * w + x] = newP;
+                }
+                pprev[j] = newP; pl = newP;
             }
+            if (m + U < g.tl) fetch(u, m + U);
         }
         feed.advance();
     }
@@ -1016,7 +1200,7 @@ void launch_build_precon(SolveCtx& c) {
 
 static size_t sweep_smem(bool with_dot) {
     size_t stage = ((with_dot ? 2 : 1) * SW_TILE + SW_PACK) * sizeof(double);
-    return (size_t)WF_WARPS * SW_STAGES * stage + (size_t)WF_WARPS * SW_STAGES * 8;
+    return (size_t)SW_WARPS * SW_STAGES * stage + (size_t)SW_WARPS * 2 * SW_STAGES * 8;
 }
 template <int DIR, bool WITH_DOT, bool MASKED>
 static void launch_sweep(SolveCtx& c, const double* src, double* dst, const double* pack, const double* rr, double* bnd,
@@ -1030,12 +1214,12 @@ static void launch_sweep(SolveCtx& c, const double* src, double* dst, const doub
     const int nown = c.g.s1 - c.g.s0;
     double* peer = nullptr;
     if (c.comm) peer = DIR > 0 ? c.peer_bnd_f_next : c.peer_bnd_b_prev;
-    const int nblocks = (nown + WF_WARPS - 1) / WF_WARPS;
+    const int nblocks = (nown + SW_WARPS - 1) / SW_WARPS;
     int cl = SW_CL_MAX;
-    while (cl > 1 && cl > nblocks) cl >>= 1;                       /* cluster of 8 blocks = 32 consecutive strips */
+    while (cl > 1 && cl > nblocks) cl >>= 1;                       /* cluster of 8 blocks = 8 * SW_WARPS consecutive strips */
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(((nblocks + cl - 1) / cl) * cl);
-    cfg.blockDim = dim3(WF_WARPS * 32);
+    cfg.blockDim = dim3(2 * SW_WARPS * 32);                        /* strip warps + loader warps */
     cfg.dynamicSmemBytes = sweep_smem(WITH_DOT);
     cfg.stream = c.stream;
     cudaLaunchAttribute attr;
