@@ -409,10 +409,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 
 #ifndef IFL_SW_U
-#define IFL_SW_U 4
+#define IFL_SW_U 8
 #endif
 #ifndef IFL_SW_STAGES
-#define IFL_SW_STAGES 10
+#define IFL_SW_STAGES 5
 #endif
 #ifndef IFL_SW_WARPS
 #define IFL_SW_WARPS 2
