@@ -624,6 +624,36 @@ __device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity) {
  * every use, which costs issue slots on a one-warp-per-scheduler critical path */
 __device__ __forceinline__ unsigned pin_u32(unsigned v) { asm volatile("mov.u32 %0, %0;" : "+r"(v)); return v; }
 
+/* ---- per-macro-step edge feed from this strip's shared-memory ring ------------------------------------------------
+ * Every lane reads the same slot pair (a broadcast), so the flag-in-data test is warp uniform: no vote, no divergence.
+ * The pair is requested one macro-step before it is tested; when it has not arrived the warp re-reads it (bounded).
+ * Re-arming stores the sentinel's high word over both values (every lane, same address, same data). */
+__device__ __forceinline__ void ring_peek(unsigned slot_addr, double (&v)[SKB]) {
+    static_assert(SKB == 2, "one 16-byte slot pair per macro-step");
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(slot_addr) : "memory");
+}
+__device__ __forceinline__ void ring_rearm(unsigned slot_addr, unsigned sent_hi) {
+    asm volatile("st.volatile.shared.u32 [%0+4], %1;\n\tst.volatile.shared.u32 [%0+12], %1;" ::"r"(slot_addr), "r"(sent_hi) : "memory");
+}
+/* need0 / need1: which of the two values exist (a column block can straddle the right edge of the grid) */
+#ifdef IFL_SW_TRACE_WAITS
+#define IFL_TW_ARGS , long long& tw_nstarved, long long& tw_nspins
+#define IFL_TW_PASS , tw_nstarved, tw_nspins
+#else
+#define IFL_TW_ARGS
+#define IFL_TW_PASS
+#endif
+__device__ __forceinline__ void ring_wait(unsigned slot_addr, double (&v)[SKB], bool need0, bool need1 IFL_TW_ARGS) {
+    if ((need0 && is_sentinel_hi(v[0])) || (need1 && is_sentinel_hi(v[SKB - 1]))) {
+        unsigned spins = 0;
+        do { ring_peek(slot_addr, v); }
+        while (((need0 && is_sentinel_hi(v[0])) || (need1 && is_sentinel_hi(v[SKB - 1]))) && ++spins < (1u << 22));
+#ifdef IFL_SW_TRACE_WAITS
+        tw_nstarved++; tw_nspins += spins + 1;
+#endif
+    }
+}
+
 /* One macro-step of one lane: the SKB cells x = (m - lane)*SKB + j of its row, in the sweep's direction.  The left/right
  * neighbour is the previous cell of the same lane (a register); the upper/lower neighbours `dn` are the SKB results of
  * the adjacent lane's PREVIOUS macro-step.  Each result is shuffled to the adjacent lane as soon as it exists (dn_next),
@@ -819,7 +849,6 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
         if (in_ring) credit_of_prev = cluster.map_shared_rank((int*)&s_credit[(cslot - 1) % SW_WARPS], (cslot - 1) / SW_WARPS);
         const bool pub_credit = lane0 && credit_of_prev != nullptr;
         /* per macro-step the edge lane's store moves by +1 slot group in a ring, by DIR column blocks in a global row */
-        const int ostep = out_ring ? SKB : DIR * SKB;
 
         double* pdst = dst + (long long)k * g.ss + ((long long)tfirst * 32 + lane) * SKB;
         double dprev[SKB];
@@ -827,18 +856,27 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
         for (int j = 0; j < SKB; j++) dprev[j] = 0.0;
         double cxprev = 0.0;
         long long tr_first = 0;
+#ifdef IFL_SW_TRACE_WAITS
+        long long tw_edge = 0, tw_op = 0, tw_credit = 0;      /* clocks spent waiting: incoming edge, operand tiles, ring credit */
+        long long tw_nstarved = 0, tw_nspins = 0, tw_t4 = 0;  /* macro-steps that found no edge value yet; re-reads; time at block 4 */
+#define IFL_TW_BEGIN const long long tw_c0_ = clock64();
+#define IFL_TW_END(acc) acc += clock64() - tw_c0_;
+#else
+#define IFL_TW_BEGIN
+#define IFL_TW_END(acc)
+#endif
 
         /* tile cursor: stage st holds the tile the operand loads currently read; shared addresses kept in registers */
         const unsigned ring_lane = pin_u32(smem_u32(ring + lane * SKB));
         const unsigned full0 = pin_u32(smem_u32(bar_full));
         const unsigned empty0 = pin_u32(smem_u32(bar_empty));
+        const unsigned inbox0 = pin_u32(smem_u32(&s_inbox[warp][0]));
         int st = 0;
         unsigned ph = 0;
         unsigned tile = ring_lane;
         /* edge-out stores are unconditional: the edge lane's pointer walks the ring / boundary row, every other lane
          * keeps storing into its own dummy slot */
         double* const dummy = &s_dummy[warp][lane][0];
-        const int ostep_lane = is_out ? ostep : 0;
 
         CellOps ops[2];
 #pragma unroll
@@ -850,17 +888,59 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
 
         /* UB macro-steps, fully unrolled and branch-free: operands of macro-step s+1 are fetched before macro-step s
          * is computed; at a tile boundary the next stage is awaited first and the finished one handed back after */
-        auto run_block = [&](auto checked_tag, const int t0, const double (&ecur)[SW_GV], double* po_lane) {
-            constexpr bool CHECKED = decltype(checked_tag)::value;
-            double dn[SKB];
+        /* RINGFEED: the incoming edge values come from this strip's ring, macro-step by macro-step.  Consumer step c
+         * reads slot (c + 31) & 127; while computing macro-step s of the block the values of macro-step s+1 are taken, so
+         * a block takes the slots of its steps 1..8 (8 consecutive slots, the group does not wrap), and the rotation
+         * registers dn are carried from block to block.  Otherwise the values are in ecur (none / global boundary row). */
+        double dn[SKB], epk[2][SKB];          /* epk[q & 1]: edge values of macro-step q of the block (requested a step ahead) */
 #pragma unroll
-            for (int j = 0; j < SKB; j++) {
-                const double give = is_out ? ecur[j] : dprev[j];
-                dn[j] = __shfl_sync(0xffffffffu, give, srclane);
+        for (int j = 0; j < SKB; j++) { dn[j] = 0.0; epk[0][j] = 0.0; epk[1][j] = 0.0; }
+        const unsigned sent_hi = pin_u32(0xFFF8B200u);
+        /* Blocks of UB macro-steps.  Hand-over protocol of a ring (the same for every producer / consumer pair):
+         *   - the producer publishes every macro-step from its 24th on (block 3 onwards; steps 24..30 carry the +0.0 of
+         *     cells left of the grid) into slot (step & 127), and 8 more zero pairs after its last macro-step;
+         *   - the consumer first waits for slots 24..31, re-arms them and starts from slot 31 (its macro-step c uses the
+         *     producer's macro-step c + 31); it then takes one slot per macro-step up to block nblk-4 and feeds zeros
+         *     afterwards (those columns lie right of the grid).
+         * So there is no per-step "does this edge value exist" decision, and the first and last blocks of a strip run
+         * the SAME code as the interior ones: cells outside the grid are zero padding, they provably produce +0.0, and
+         * storing +0.0 into padding keeps it zero.  (The first 31 macro-steps of every strip are on the critical path of
+         * the whole sweep.)  CHECKED blocks (per-cell predicates) remain only where the edge row goes to a global
+         * boundary row, which has no padding: the last strip of a cluster / slab. */
+        auto run_block = [&](auto checked_tag, auto ringfeed_tag, const int t0, const int sc0, const double (&ecur)[SW_GV],
+                             double* po_lane, const int ostep_l) {
+            constexpr bool CHECKED = decltype(checked_tag)::value;
+            constexpr bool RINGFEED = decltype(ringfeed_tag)::value;
+            const unsigned in_rest = inbox0 + (unsigned)(((sc0 + 32) & (SW_RB - 1)) * SKB * (int)sizeof(double));
+            const unsigned in_next = inbox0 + (unsigned)(((sc0 + UB + 32) & (SW_RB - 1)) * SKB * (int)sizeof(double));
+            const int cin0 = t0 - E_IN;                                    /* column block the edge lane needs at step 0 */
+            double ecar[SKB];
+            if (!RINGFEED) {
+#pragma unroll
+                for (int j = 0; j < SKB; j++) {
+                    const double give = is_out ? ecur[j] : dprev[j];
+                    dn[j] = __shfl_sync(0xffffffffu, give, srclane);
+                }
             }
 #pragma unroll
             for (int s = 0; s < UB; s++) {
                 const int r = (s + 1) % U;
+                if (RINGFEED) {
+                    /* values of macro-step s+1: requested one macro-step ago into epk[(s+1)&1]; request those of s+2 */
+                    const unsigned a = in_rest + (unsigned)(s * SKB * (int)sizeof(double));
+                    double (&e)[SKB] = epk[(s + 1) & 1];
+                    ring_wait(a, e, true, true IFL_TW_PASS);
+                    ring_rearm(a, sent_hi);
+                    if (CHECKED) {                                          /* the producer's padding cells hold +0.0 anyway */
+                        const int c = cin0 + DIR * (s + 1);
+#pragma unroll
+                        for (int j = 0; j < SKB; j++) if (c < 0 || c * SKB + j >= w) e[j] = 0.0;
+                    }
+                    ring_peek(s + 1 < UB ? a + (unsigned)(SKB * sizeof(double)) : in_next, epk[s & 1]);
+                } else if (s + 1 < UB) {
+#pragma unroll
+                    for (int j = 0; j < SKB; j++) ecar[j] = ecur[(s + 1) * SKB + j];
+                }
                 unsigned done_bar = 0;
                 if (r == 0) {
                     done_bar = empty0 + 8u * st;
@@ -868,12 +948,12 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
                     st = wrap ? 0 : st + 1;
                     ph ^= wrap ? 1u : 0u;
                     tile = ring_lane + (unsigned)(st * STAGE * (int)sizeof(double));
-                    mbar_wait_u32(full0 + 8u * st, ph);
+                    { IFL_TW_BEGIN mbar_wait_u32(full0 + 8u * st, ph); IFL_TW_END(tw_op) }
                 }
                 load_step<DIR, WITH_DOT>(ops[(s + 1) & 1], tile, r);
-                const double* en = (s + 1 < UB) ? &ecur[(s + 1) * SKB] : nullptr;
+                const double* en = RINGFEED ? &epk[(s + 1) & 1][0] : (s + 1 < UB ? &ecar[0] : nullptr);
                 sweep_step<DIR, WITH_DOT, CHECKED, MASKED>(ops[s & 1], dn, en, t0 + DIR * s, lane, srclane, is_out, w, yok,
-                                                           pdst + DIR * s * (32 * SKB), po_lane + ostep_lane * s, dummy,
+                                                           pdst + DIR * s * (32 * SKB), po_lane + ostep_l * s, dummy,
                                                            dprev, cxprev, acc);
                 /* every row of the finished tile is in registers (the loads are warp-wide instructions issued, in
                  * order, before this arrive): hand the stage back to the loader warp */
@@ -881,54 +961,118 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
             }
         };
 
-        auto do_block = [&](const int b, double (&ecur)[SW_GV], double (&enext)[SW_GV]) {
-            const int t0 = tfirst + DIR * b * UB;
-            if (trace && b == 1) tr_first = (long long)globaltimer_ns();
-            const int tlo = DIR > 0 ? t0 : t0 - (UB - 1);
-            const bool interior = (tlo - 31 >= 0) && ((tlo + UB - 1) * SKB + SKB - 1 < w);
-            if (out_ring && (b & 1) == 0) {
-                /* credit: the last step of the next two blocks must not lap the consumer's ring */
-                for (unsigned spins = 0; (b * UB + 2 * UB - 1) - s_credit[warp] >= SW_RB && spins < (1u << 24); spins++) {}
-            }
-            const int sc0 = b * UB;                                        /* my step count at the block's first step */
-            const int cin = t0 - E_IN;                                     /* column block the edge lane needs first */
-            if (use_feed) {
-                /* ring fast path: all columns of the block exist and its slots do not wrap */
-                const int clo = DIR > 0 ? cin : cin - (UB - 1);
-                const bool allcols = clo >= 0 && (clo + UB - 1) * SKB + SKB - 1 < w;
-                const int cnl = clo + DIR * UB;
-                const bool allcols_next = cnl >= 0 && (cnl + UB - 1) * SKB + SKB - 1 < w;
-                if (ring_feed && allcols_next && ((sc0 + UB + 31) & (SW_RB - 1)) + UB <= SW_RB) feed.fetch_ring(enext, sc0 + UB);
-                else feed.fetch(enext, cin + DIR * UB, sc0 + UB, DIR);     /* next block */
-                const bool fast = ring_feed && allcols && ((sc0 + 31) & (SW_RB - 1)) + UB <= SW_RB;
-                if (!feed.ready(ecur)) {
-                    if (fast) feed.wait_ring(ecur, sc0);
-                    if (!feed.ready(ecur)) feed.wait(ecur, cin, sc0, DIR);
-                }
-                if (fast) feed.rearm_ring(sc0);
-                else feed.rearm(cin, sc0, DIR);
-            }
-            double* po = out_ring ? out_base + (sc0 & (SW_RB - 1)) * SKB : out_base + (t0 - E_OUT) * SKB;
-            double* po_lane = is_out ? po : dummy;
-            if (interior) run_block(std::false_type{}, t0, ecur, po_lane);
-            else          run_block(std::true_type{}, t0, ecur, po_lane);
-            pdst += DIR * UB * (32 * SKB);
-            /* I have consumed my producer's steps up to (my step count + 31) */
-            st_int_if(pub_credit, credit_of_prev, (b + 1) * UB + 31);
-        };
-
-        double eb0[SW_GV], eb1[SW_GV];                                     /* edge values: two blocks, ping-pong */
+        double eb0[SW_GV], eb1[SW_GV];                                     /* edge values from a global row: two blocks, ping-pong */
 #pragma unroll
         for (int j = 0; j < SW_GV; j++) { eb0[j] = 0.0; eb1[j] = 0.0; }
-        if (use_feed) feed.fetch(eb0, tfirst - E_IN, 0, DIR);
-        for (int b = 0; b < nblk; b += 2) {
-            do_block(b, eb0, eb1);
-            if (b + 1 < nblk) do_block(b + 1, eb1, eb0);
+        constexpr std::false_type F{}; constexpr std::true_type T{};
+        const int nsteps = nblk * UB;
+
+        /* credit: the last step of the next two blocks must not lap the consumer's ring */
+        auto credit_wait = [&](const int last_step) {
+            IFL_TW_BEGIN
+            for (unsigned spins = 0; last_step - s_credit[warp] >= SW_RB && spins < (1u << 24); spins++) {}
+            IFL_TW_END(tw_credit)
+        };
+        if (ring_feed) {
+            /* prologue: the producer's macro-steps 24..31 (one slot group); only the last one carries a column of mine */
+            const unsigned a = inbox0 + (unsigned)(24 * SKB * (int)sizeof(double));
+            double e0[SKB];
+            for (int i = 0; i < 8; i++) {
+                ring_peek(a + (unsigned)(i * SKB * (int)sizeof(double)), e0);
+                ring_wait(a + (unsigned)(i * SKB * (int)sizeof(double)), e0, true, true IFL_TW_PASS);
+                ring_rearm(a + (unsigned)(i * SKB * (int)sizeof(double)), sent_hi);
+            }
+            if (!out_ring) {                                             /* CHECKED strip: do not rely on the padding */
+                const int c = tfirst - E_IN;
+#pragma unroll
+                for (int j = 0; j < SKB; j++) if (c < 0 || c * SKB + j >= w) e0[j] = 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < SKB; j++) {
+                const double give = is_out ? e0[j] : 0.0;
+                dn[j] = __shfl_sync(0xffffffffu, give, srclane);
+            }
+            ring_peek(inbox0 + (unsigned)(32 * SKB * (int)sizeof(double)), epk[1]);            /* macro-step 1 */
+        }
+        const int last_ring_block = nblk - 4;                             /* the producer's last real macro-step is taken in this block */
+        if (out_ring && !(use_feed && !ring_feed)) {
+            /* both hand-overs through rings (or no incoming edge at all): one code path for every block */
+            for (int b = 0; b < nblk; b++) {
+                const int t0 = tfirst + DIR * b * UB, sc0 = b * UB;
+                if (trace && b == 1) tr_first = (long long)globaltimer_ns();
+#ifdef IFL_SW_TRACE_WAITS
+                if (trace && b == 4) tw_t4 = (long long)globaltimer_ns();
+#endif
+                if ((b & 1) == 0) credit_wait(sc0 + 2 * UB - 1);
+                const bool pub = is_out && b >= 3;
+                double* po_lane = pub ? out_base + (sc0 & (SW_RB - 1)) * SKB : dummy;
+                const int ostep_l = pub ? SKB : 0;
+                if (ring_feed && b <= last_ring_block) run_block(F, T, t0, sc0, eb0, po_lane, ostep_l);
+                else                                   run_block(F, F, t0, sc0, eb0, po_lane, ostep_l);
+                pdst += DIR * UB * (32 * SKB);
+                /* I have consumed my producer's steps up to (my step count + 31) */
+                st_int_if(pub_credit, credit_of_prev, (b + 1) * UB + 31);
+            }
+        } else {
+            auto do_block = [&](const int b, double (&ecur)[SW_GV], double (&enext)[SW_GV]) {
+                const int t0 = tfirst + DIR * b * UB;
+                if (trace && b == 1) tr_first = (long long)globaltimer_ns();
+#ifdef IFL_SW_TRACE_WAITS
+                if (trace && b == 4) tw_t4 = (long long)globaltimer_ns();
+#endif
+                const int tlo = DIR > 0 ? t0 : t0 - (UB - 1);
+                const bool interior = (tlo - 31 >= 0) && ((tlo + UB - 1) * SKB + SKB - 1 < w);
+                const int sc0 = b * UB;                                    /* my step count at the block's first step */
+                const int cin = t0 - E_IN;                                 /* column block the edge lane needs first */
+                if (out_ring && (b & 1) == 0) credit_wait(sc0 + 2 * UB - 1);
+                if (use_feed && !ring_feed) {                              /* global boundary row: block by block */
+                    IFL_TW_BEGIN
+                    feed.fetch(enext, cin + DIR * UB, sc0 + UB, DIR);      /* next block */
+                    if (!feed.ready(ecur)) feed.wait(ecur, cin, sc0, DIR);
+                    IFL_TW_END(tw_edge)
+                }
+                const bool rf = ring_feed && b <= last_ring_block;
+                if (out_ring) {
+                    /* ring out, global row in: plain arithmetic and stores in every block (see above) */
+                    const bool pub = is_out && b >= 3;
+                    double* po_lane = pub ? out_base + (sc0 & (SW_RB - 1)) * SKB : dummy;
+                    run_block(F, F, t0, sc0, ecur, po_lane, pub ? SKB : 0);
+                } else {
+                    /* global row out: per-cell predicates in the first and last blocks */
+                    double* po_lane = is_out ? out_base + (t0 - E_OUT) * SKB : dummy;
+                    const int ostep_l = is_out ? DIR * SKB : 0;
+                    if (rf) {
+                        if (interior) run_block(F, T, t0, sc0, ecur, po_lane, ostep_l);
+                        else          run_block(T, T, t0, sc0, ecur, po_lane, ostep_l);
+                    } else {
+                        if (interior) run_block(F, F, t0, sc0, ecur, po_lane, ostep_l);
+                        else          run_block(T, F, t0, sc0, ecur, po_lane, ostep_l);
+                    }
+                }
+                pdst += DIR * UB * (32 * SKB);
+                st_int_if(pub_credit, credit_of_prev, (b + 1) * UB + 31);
+            };
+            if (use_feed && !ring_feed) feed.fetch(eb0, tfirst - E_IN, 0, DIR);
+            for (int b = 0; b < nblk; b += 2) {
+                do_block(b, eb0, eb1);
+                if (b + 1 < nblk) do_block(b + 1, eb1, eb0);
+            }
+        }
+        if (out_ring) {
+            /* 8 more zero pairs: the consumer takes one slot per macro-step through its block nblk-4 */
+            credit_wait(nsteps + UB - 1);
+            if (is_out) {
+                double* p = out_base + (nsteps & (SW_RB - 1)) * SKB;
+                for (int i = 0; i < UB * SKB; i++) p[i] = 0.0;
+            }
         }
         if (trace && lane == 0) {
             long long* tr = trace + (long long)k * 8;
             tr[0] = tr_enter; tr[1] = tr_first; tr[2] = 0; tr[3] = (long long)globaltimer_ns();
             tr[4] = 0; tr[5] = nblk; tr[6] = slot; tr[7] = (long long)get_smid();
+#ifdef IFL_SW_TRACE_WAITS
+            tr[2] = tw_nstarved * 1000000 + tw_nspins; tr[4] = tw_t4 - tr_first; tr[5] = tw_credit + tw_edge;
+#endif
         }
     }
     if (WITH_DOT && live && !loader) {

@@ -24,4 +24,4 @@ for sw, name in ((0, "forward"), (1, "backward")):
     for k in order:
         e = t[k]
         print(f"strip {k:4d} slot {e[6]:4d} sm {e[7]:3d} enter {(e[0]-t0)/1e3:8.2f} after-block-1 {(e[1]-t0)/1e3:8.2f} "
-              f"end {(e[3]-t0)/1e3:8.2f} dur {(e[3]-e[1])/1e3:8.2f} us  blocks {e[5]}  operand-wait {e[4]} cycles")
+              f"end {(e[3]-t0)/1e3:8.2f} dur {(e[3]-e[1])/1e3:8.2f} us  [IFL_SW_TRACE_WAITS builds] starved steps {e[2]//1000000} re-reads {e[2]%1000000} blocks1-3 {e[4]/1e3:.2f} us credit+edge clocks {e[5]}")
