@@ -179,6 +179,9 @@ void ifl_destroy(ifl_solver* s) {
     }
     for (auto& e : s->ev_chunk) if (e) cudaEventDestroy(e);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    if (s->sx.ev_r) cudaEventDestroy(s->sx.ev_r);
+    if (s->sx.ev_p) cudaEventDestroy(s->sx.ev_p);
+    if (s->sx.side) cudaStreamDestroy(s->sx.side);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -287,6 +290,12 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
         s->sx.fl += guard;
     }
     s->sx.stream = s->stream;
+    s->sx.side = nullptr; s->sx.ev_r = nullptr; s->sx.ev_p = nullptr;
+    if (uses_pcg(s) && !getenv("IFL_NO_SIDE_STREAM")) {
+        CU(cudaStreamCreateWithFlags(&s->sx.side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s->sx.ev_r, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->sx.ev_p, cudaEventDisableTiming));
+    }
     s->sx.launches = &s->launches;
     s->sx.prof = &s->prof;
     s->sx.trace = nullptr;

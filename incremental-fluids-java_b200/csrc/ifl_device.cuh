@@ -135,4 +135,18 @@ __device__ __forceinline__ double ld_volatile(const double* p) {
     return *reinterpret_cast<const volatile double*>(p);
 }
 
+
+/* `v / _hx` (Euler F1:220, RungeKutta3 F2:253, backProject F4:249): when _hx = 1/min(w,h) is a power of two its reciprocal
+ * is exact and v * (1/_hx) is bit-identical to the IEEE quotient (scaling by a power of two never rounds; overflow and
+ * subnormal results coincide too), which spares the ~25-instruction division sequence.  Any other _hx divides. */
+struct HxDiv { double hx, inv; bool pow2; };
+__device__ __forceinline__ HxDiv make_hxdiv(double hx) {
+    const long long b = __double_as_longlong(hx);
+    HxDiv d;
+    d.hx = hx;
+    d.pow2 = b > 0 && (b & 0x000FFFFFFFFFFFFFll) == 0 && (b >> 52) >= 2 && (b >> 52) <= 0x7FC;
+    d.inv = __longlong_as_double((0x7FEll << 52) - b);
+    return d;
+}
+__device__ __forceinline__ double div_hx(double v, const HxDiv& d) { return d.pow2 ? v * d.inv : v / d.hx; }
 } // namespace ifl

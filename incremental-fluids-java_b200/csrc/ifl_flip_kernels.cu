@@ -157,15 +157,16 @@ __global__ void k_grid_to_particles(int n, double alpha, const double* __restric
 __global__ void k_advect_particles(int n, double timestep, double hx, int w, int h, GridView gu, GridView gv,
                                    const ifl_body* __restrict__ bodies, int nbodies,
                                    double* __restrict__ posX, double* __restrict__ posY) {
+    const HxDiv hd = make_hxdiv(hx);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double x = posX[i], y = posY[i];
-    double firstU = g_lerp_grid(gu, x, y) / hx;
-    double firstV = g_lerp_grid(gv, x, y) / hx;
+    double firstU = div_hx(g_lerp_grid(gu, x, y), hd);
+    double firstV = div_hx(g_lerp_grid(gv, x, y), hd);
     double midX = x + 0.5 * timestep * firstU;
     double midY = y + 0.5 * timestep * firstV;
-    double midU = g_lerp_grid(gu, midX, midY) / hx;
-    double midV = g_lerp_grid(gv, midX, midY) / hx;
+    double midU = div_hx(g_lerp_grid(gu, midX, midY), hd);
+    double midV = div_hx(g_lerp_grid(gv, midX, midY), hd);
     double lastX = x + 0.75 * timestep * midU;
     double lastY = y + 0.75 * timestep * midV;
     double lastU = g_lerp_grid(gu, lastX, lastY);

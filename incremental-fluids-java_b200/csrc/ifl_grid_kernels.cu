@@ -68,6 +68,7 @@ __device__ __forceinline__ double cerp_grid(const FieldView& f, double x, double
 template <bool RK3>
 __global__ void __launch_bounds__(256)
 k_advect(FieldView q, FieldView u, FieldView v, double* __restrict__ dst, double timestep, double hx) {
+    const HxDiv hd = make_hxdiv(hx);
     int ix = blockIdx.x * blockDim.x + threadIdx.x;
     int iy = blockIdx.y * blockDim.y + threadIdx.y;
     if (ix >= q.w || iy >= q.h) return;
@@ -75,18 +76,18 @@ k_advect(FieldView q, FieldView u, FieldView v, double* __restrict__ dst, double
     double y = iy + q.oy;
     double out;
     if (!RK3) {
-        double uVel = lerp_grid(u, x, y) / hx;
-        double vVel = lerp_grid(v, x, y) / hx;
+        double uVel = div_hx(lerp_grid(u, x, y), hd);
+        double vVel = div_hx(lerp_grid(v, x, y), hd);
         x -= uVel * timestep;
         y -= vVel * timestep;
         out = lerp_grid(q, x, y);
     } else {
-        double firstU = lerp_grid(u, x, y) / hx;
-        double firstV = lerp_grid(v, x, y) / hx;
+        double firstU = div_hx(lerp_grid(u, x, y), hd);
+        double firstV = div_hx(lerp_grid(v, x, y), hd);
         double midX = x - 0.5 * timestep * firstU;
         double midY = y - 0.5 * timestep * firstV;
-        double midU = lerp_grid(u, midX, midY) / hx;
-        double midV = lerp_grid(v, midX, midY) / hx;
+        double midU = div_hx(lerp_grid(u, midX, midY), hd);
+        double midV = div_hx(lerp_grid(v, midX, midY), hd);
         double lastX = x - 0.75 * timestep * midU;
         double lastY = y - 0.75 * timestep * midV;
         /* F2:266-267: the third sample is NOT divided by _hx (port quirk, kept) */

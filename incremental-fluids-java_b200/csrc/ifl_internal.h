@@ -53,7 +53,7 @@ struct SolveScalars {
     unsigned int ctr_b;
     unsigned int ticket_f;  /* strip tickets of the forward / backward wavefront */
     unsigned int ticket_b;
-    int pad;
+    int p_go;            /* 1: the p += alpha*s of this iteration has to be applied (k_update_p, side stream) */
 };
 
 /* slab decomposition (ifl_comm.cu): rank r owns the strips [s0, s1) of the pressure solve */
@@ -102,6 +102,8 @@ struct SolveCtx {
     unsigned char* fl;    /* skewed fluid flags of _d._cell (F4+), nullptr for F1-F3 */
     int mask_vector_ops;  /* F6+: dotProduct/scaledAdd/infinityNorm only over fluid cells (F6:999-1064) */
     cudaStream_t stream;
+    cudaStream_t side;    /* p += alpha*s runs here, next to the triangular sweeps (which leave half the bandwidth idle) */
+    cudaEvent_t ev_r, ev_p;
     unsigned long long* launches;
     Profiler* prof;
     /* slab decomposition */

@@ -484,6 +484,7 @@ __device__ __forceinline__ double adv_cerp_grid(const AdvView& f, double x, doub
 __global__ void __launch_bounds__(256)
 k_advect_solid(AdvView q, AdvView u, AdvView v, const unsigned char* __restrict__ cell, const int* __restrict__ body,
                const ifl_body* __restrict__ bodies, double* __restrict__ dst, double timestep, double hx) {
+    const HxDiv hd = make_hxdiv(hx);
     int ix = blockIdx.x * blockDim.x + threadIdx.x;
     int iy = blockIdx.y * blockDim.y + threadIdx.y;
     if (ix >= q.w || iy >= q.h) return;
@@ -491,12 +492,12 @@ k_advect_solid(AdvView q, AdvView u, AdvView v, const unsigned char* __restrict_
     if (cell[idx] != IFL_CELL_FLUID) return;      /* stale _dst is kept (F4:273) */
     double x = ix + q.ox;
     double y = iy + q.oy;
-    double firstU = adv_lerp_grid(u, x, y) / hx;
-    double firstV = adv_lerp_grid(v, x, y) / hx;
+    double firstU = div_hx(adv_lerp_grid(u, x, y), hd);
+    double firstV = div_hx(adv_lerp_grid(v, x, y), hd);
     double midX = x - 0.5 * timestep * firstU;
     double midY = y - 0.5 * timestep * firstV;
-    double midU = adv_lerp_grid(u, midX, midY) / hx;
-    double midV = adv_lerp_grid(v, midX, midY) / hx;
+    double midU = div_hx(adv_lerp_grid(u, midX, midY), hd);
+    double midV = div_hx(adv_lerp_grid(v, midX, midY), hd);
     double lastX = x - 0.75 * timestep * midU;
     double lastY = y - 0.75 * timestep * midV;
     double lastU = adv_lerp_grid(u, lastX, lastY);
@@ -511,8 +512,8 @@ k_advect_solid(AdvView q, AdvView u, AdvView v, const unsigned char* __restrict_
         x = (x - q.ox) * hx;
         y = (y - q.oy) * hx;
         V2 r = body_closest_surface_point(bodies[body[c]], x, y);
-        x = r.x / hx + q.ox;
-        y = r.y / hx + q.oy;
+        x = div_hx(r.x, hd) + q.ox;
+        y = div_hx(r.y, hd) + q.oy;
     }
     dst[idx] = adv_cerp_grid(q, x, y);
 }

@@ -44,15 +44,16 @@ static inline int single_gpu(const SolveCtx& c) { return c.comm == nullptr; }
  * EW_RPP consecutive m-rows per pass (element q = tid % (32*SKB) of its m-row: lane l_ = q / SKB, sub-column
  * j_ = q % SKB), fully coalesced.  Visits in a fixed order (e ascending).  Neighbour indices of element i_:
  * nl_/nr_ = (x-1,y)/(x+1,y), nu_/nd_ = (x,y-1)/(x,y+1) (the latter two may lie in the neighbouring strip). */
-#define IFL_EW_LOOP_BEGIN(g)                                                            \
-    const int k_ = blockIdx.y + (g).s0;                                                 \
+#define IFL_EW_LOOP_BEGIN(g) IFL_EW_LOOP_BEGIN_AT(g, blockIdx.x, blockIdx.y)
+#define IFL_EW_LOOP_BEGIN_AT(g, bx_, by_)                                               \
+    const int k_ = (by_) + (g).s0;                                                      \
     const long long base_ = (long long)k_ * (g).ss;                                     \
     const int q_ = threadIdx.x % (32 * SKB);                                            \
     const int l_ = q_ / SKB;                                                            \
     const int j_ = q_ % SKB;                                                            \
     const int y_ = k_ * 32 + l_;                                                        \
     _Pragma("unroll") for (int e_ = 0; e_ < 8; e_++) {                                  \
-        const int t_ = blockIdx.x * EW_TROWS + e_ * EW_RPP + threadIdx.x / (32 * SKB);  \
+        const int t_ = (bx_) * EW_TROWS + e_ * EW_RPP + threadIdx.x / (32 * SKB);       \
         const int x_ = (t_ - l_) * SKB + j_;                                            \
         const long long i_ = base_ + (long long)t_ * (32 * SKB) + q_;                   \
         const bool ok_ = (t_ < (g).tl) && x_ >= 0 && x_ < (g).w && y_ < (g).h;
@@ -162,6 +163,20 @@ k_matvec_dot(SkewGeom g, const double* __restrict__ adiag, const double* __restr
     finish_partials(bs, partials, g, strip_part, sc, dot_mode, single_gpu, &s_last);
 }
 
+/* scaledAdd(_p, _p, _s, alpha) F3:607 (masked F6:1041) on its own: see k_update_pr(with_p = 0) */
+__global__ void __launch_bounds__(EW_THREADS)
+k_update_p(SkewGeom g, double* __restrict__ p, const double* __restrict__ s, const SolveScalars* sc,
+           const unsigned char* __restrict__ fl, int nvx, int nvy) {
+    if (!sc->p_go) return;
+    const double alpha = sc->alpha;
+    /* the grid walks the (nvx, nvy) blocks of the usual element-wise decomposition (one each by default) */
+    for (int vb = blockIdx.x; vb < nvx * nvy; vb += gridDim.x) {
+        IFL_EW_LOOP_BEGIN_AT(g, vb % nvx, vb / nvx)
+            if (ok_ && (fl == nullptr || fl[i_])) p[i_] = p[i_] + s[i_] * alpha;
+        IFL_EW_LOOP_END
+    }
+}
+
 /* p += alpha s ; r -= alpha z ; maxError = infinityNorm(r)   (F3:606-608, scaledAdd F3:570,
  * infinityNorm F3:579).  Also re-arms the boundary rows and tickets of the two sweeps
  * that follow.  The last block decides convergence (F3:609-619). */
@@ -169,15 +184,19 @@ __global__ void __launch_bounds__(EW_THREADS)
 k_update_pr(SkewGeom g, double* __restrict__ p, const double* __restrict__ s, double* __restrict__ r,
             const double* __restrict__ z, double* __restrict__ bnd_f, double* __restrict__ bnd_b,
             SolveScalars* sc, double tol, const unsigned char* __restrict__ fl,
-            unsigned long long* rank_max, int rank, int single_gpu) {
-    if (sc->done) return;
+            unsigned long long* rank_max, int rank, int single_gpu, int with_p) {
+    /* with_p == 0: p is updated by k_update_p on the side stream; it has to know whether THIS iteration runs (`done`
+     * may be set by this very kernel's last block, after every block has passed this point) */
+    const bool first = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+    if (sc->done) { if (!with_p && first) sc->p_go = 0; return; }
+    if (!with_p && first) sc->p_go = 1;
     __shared__ unsigned s_max[8];
     __shared__ bool s_last;
     const double alpha = sc->alpha, nalpha = sc->neg_alpha;
     unsigned m = 0;
     IFL_EW_LOOP_BEGIN(g)
         if (ok_ && (fl == nullptr || fl[i_])) {
-            p[i_] = p[i_] + s[i_] * alpha;
+            if (with_p) p[i_] = p[i_] + s[i_] * alpha;
             double rv = r[i_] + z[i_] * nalpha;
             r[i_] = rv;
             unsigned bits = absf_bits(rv);
@@ -623,6 +642,11 @@ __device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity) {
 /* keeps a value in a register: the compiler would otherwise re-derive shared-memory addresses from the thread id on
  * every use, which costs issue slots on a one-warp-per-scheduler critical path */
 __device__ __forceinline__ unsigned pin_u32(unsigned v) { asm volatile("mov.u32 %0, %0;" : "+r"(v)); return v; }
+__device__ __forceinline__ unsigned mapa_u32(unsigned local_addr, unsigned cta_rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
 
 /* ---- per-macro-step edge feed from this strip's shared-memory ring ------------------------------------------------
  * Every lane reads the same slot pair (a broadcast), so the flag-in-data test is warp uniform: no vote, no divergence.
@@ -659,11 +683,24 @@ __device__ __forceinline__ void ring_wait(unsigned slot_addr, double (&v)[SKB], 
  * the adjacent lane's PREVIOUS macro-step.  Each result is shuffled to the adjacent lane as soon as it exists (dn_next),
  * so the shuffle latency overlaps the rest of the lane's own dependency chain; `edge_next` is what the edge lane
  * injects into that rotation (the neighbouring strip's values for the NEXT macro-step), nullptr = no early shuffle. */
-template <int DIR, bool WITH_DOT, bool CHECKED, bool MASKED>
+/* one 16-byte store into a (possibly remote) shared-memory ring slot (generic address of mapped shared memory) */
+__device__ __forceinline__ void st_ring_pair(double* slot, double a, double b) {
+    static_assert(SKB == 2, "one 16-byte store per macro-step");
+#ifdef IFL_SW_ST128                         /* measured slower than two 8-byte stores */
+    asm volatile("st.v2.f64 [%0], {%1, %2};" ::"l"(slot), "d"(a), "d"(b) : "memory");
+#else
+    slot[0] = a; slot[1] = b;
+#endif
+}
+/* OUTRING: po is a 16-byte aligned slot (the next strip's ring slot for the edge lane, a scratch slot for the others)
+ * and takes one vector store.  `edge_ready()` is called after the first cell's arithmetic has been issued and before the
+ * incoming edge values are first used: a wait placed there hides behind the latency of that cell's last operation, and
+ * the code between two such points (second cell of this macro-step, first cell of the next) is one basic block. */
+template <int DIR, bool WITH_DOT, bool CHECKED, bool MASKED, bool OUTRING, class Ready>
 __device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB], const double* edge_next, const int m,
                                            const int lane, const int srclane, const bool is_out, const int w, const bool yok,
                                            double* pd, double* po, double* dummy, double (&dprev)[SKB], double& cxprev,
-                                           double& acc) {
+                                           double& acc, Ready&& edge_ready) {
     double dl = DIR > 0 ? dprev[SKB - 1] : dprev[0];
     bool fl[SKB];
     double dnn[SKB];
@@ -683,6 +720,9 @@ __device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB],
         double d = v * pr;
         fl[j] = MASKED ? (pr == pr) : true;              /* NaN precon tags a non-fluid cell (k_precon_coeffs) */
         if (MASKED) d = fl[j] ? d : 0.0;                 /* skipped cell: dst stays, neighbours see +0.0 */
+#ifdef IFL_SW_MIDCHECK                      /* measured slower: the compiler's schedule of the two half-steps is worse */
+        if (jj == 0) edge_ready();
+#endif
         if (edge_next != nullptr) {                      /* hand the result to the adjacent lane right away */
             const double give = is_out ? edge_next[j] : d;
             dnn[j] = __shfl_sync(0xffffffffu, give, srclane);
@@ -699,8 +739,9 @@ __device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB],
             const int x = xb + j;
             const bool inx = x >= 0 && x < w;
             st_if(yok && inx && fl[j], pd + j, dprev[j]);
-            st_if(inx && is_out, po + j, dprev[j]);           /* the edge value is published for every column */
+            if (!OUTRING) st_if(inx && is_out, po + j, dprev[j]);           /* the edge value is published for every column */
         }
+        if (OUTRING) st_ring_pair(po, dprev[0], dprev[SKB - 1]);
     } else {
         /* interior block: only rows y >= h are inactive; they hold +0.0, and storing +0.0 into
          * their (zero) padding cells keeps the padding zero -- no predicate needed.  Lanes that have nothing to
@@ -712,8 +753,11 @@ __device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB],
         } else {
             store_cells(pd, dprev);
         }
+        if (OUTRING) st_ring_pair(po, dprev[0], dprev[SKB - 1]);
+        else {
 #pragma unroll
-        for (int j = 0; j < SKB; j++) po[j] = dprev[j];       /* po: the edge lane's slot, the dummy slot for the others */
+            for (int j = 0; j < SKB; j++) po[j] = dprev[j];   /* po: the edge lane's slot, the dummy slot for the others */
+        }
     }
     if (edge_next != nullptr) {
 #pragma unroll
@@ -750,6 +794,7 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     __shared__ __align__(16) double s_inbox[SW_WARPS][SW_RB * SKB];   /* edge-row rings of this block's strips */
     __shared__ volatile int s_credit[SW_WARPS];          /* steps of MINE the strip after me has consumed */
     __shared__ __align__(16) double s_dummy[SW_WARPS][32][SKB];       /* where lanes with nothing to publish store */
+    __shared__ __align__(16) double s_scratch[SW_WARPS][SW_FG * SKB]; /* ... when the edge row goes to a ring (one block of slots) */
     __shared__ int s_ticket;
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
@@ -848,6 +893,8 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
         else out_base = (to_peer ? bnd_peer : bnd) + (long long)k * w;
         if (in_ring) credit_of_prev = cluster.map_shared_rank((int*)&s_credit[(cslot - 1) % SW_WARPS], (cslot - 1) / SW_WARPS);
         const bool pub_credit = lane0 && credit_of_prev != nullptr;
+        /* shared::cluster addresses of the next strip's ring and of my scratch slots */
+        double* const oscratch = &s_scratch[warp][0];
         /* per macro-step the edge lane's store moves by +1 slot group in a ring, by DIR column blocks in a global row */
 
         double* pdst = dst + (long long)k * g.ss + ((long long)tfirst * 32 + lane) * SKB;
@@ -907,10 +954,11 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
          * storing +0.0 into padding keeps it zero.  (The first 31 macro-steps of every strip are on the critical path of
          * the whole sweep.)  CHECKED blocks (per-cell predicates) remain only where the edge row goes to a global
          * boundary row, which has no padding: the last strip of a cluster / slab. */
-        auto run_block = [&](auto checked_tag, auto ringfeed_tag, const int t0, const int sc0, const double (&ecur)[SW_GV],
-                             double* po_lane, const int ostep_l) {
+        auto run_block = [&](auto checked_tag, auto ringfeed_tag, auto outring_tag, const int t0, const int sc0,
+                             const double (&ecur)[SW_GV], double* po_lane, const int ostep_l) {
             constexpr bool CHECKED = decltype(checked_tag)::value;
             constexpr bool RINGFEED = decltype(ringfeed_tag)::value;
+            constexpr bool OUTRING = decltype(outring_tag)::value;
             const unsigned in_rest = inbox0 + (unsigned)(((sc0 + 32) & (SW_RB - 1)) * SKB * (int)sizeof(double));
             const unsigned in_next = inbox0 + (unsigned)(((sc0 + UB + 32) & (SW_RB - 1)) * SKB * (int)sizeof(double));
             const int cin0 = t0 - E_IN;                                    /* column block the edge lane needs at step 0 */
@@ -925,19 +973,26 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
 #pragma unroll
             for (int s = 0; s < UB; s++) {
                 const int r = (s + 1) % U;
-                if (RINGFEED) {
-                    /* values of macro-step s+1: requested one macro-step ago into epk[(s+1)&1]; request those of s+2 */
-                    const unsigned a = in_rest + (unsigned)(s * SKB * (int)sizeof(double));
-                    double (&e)[SKB] = epk[(s + 1) & 1];
-                    ring_wait(a, e, true, true IFL_TW_PASS);
-                    ring_rearm(a, sent_hi);
-                    if (CHECKED) {                                          /* the producer's padding cells hold +0.0 anyway */
-                        const int c = cin0 + DIR * (s + 1);
+                /* values of macro-step s+1: requested one macro-step ago into epk[(s+1)&1]; tested in the middle of this
+                 * macro-step (see sweep_step), then those of s+2 are requested */
+                auto edge_ready = [&]() {
+                    if (RINGFEED) {
+                        const unsigned a = in_rest + (unsigned)(s * SKB * (int)sizeof(double));
+                        double (&e)[SKB] = epk[(s + 1) & 1];
+                        ring_wait(a, e, true, true IFL_TW_PASS);
+                        ring_rearm(a, sent_hi);
+                        if (CHECKED) {                                      /* the producer's padding cells hold +0.0 anyway */
+                            const int c = cin0 + DIR * (s + 1);
 #pragma unroll
-                        for (int j = 0; j < SKB; j++) if (c < 0 || c * SKB + j >= w) e[j] = 0.0;
+                            for (int j = 0; j < SKB; j++) if (c < 0 || c * SKB + j >= w) e[j] = 0.0;
+                        }
+                        ring_peek(s + 1 < UB ? a + (unsigned)(SKB * sizeof(double)) : in_next, epk[s & 1]);
                     }
-                    ring_peek(s + 1 < UB ? a + (unsigned)(SKB * sizeof(double)) : in_next, epk[s & 1]);
-                } else if (s + 1 < UB) {
+                };
+#ifndef IFL_SW_MIDCHECK
+                edge_ready();
+#endif
+                if (!RINGFEED && s + 1 < UB) {
 #pragma unroll
                     for (int j = 0; j < SKB; j++) ecar[j] = ecur[(s + 1) * SKB + j];
                 }
@@ -952,9 +1007,10 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
                 }
                 load_step<DIR, WITH_DOT>(ops[(s + 1) & 1], tile, r);
                 const double* en = RINGFEED ? &epk[(s + 1) & 1][0] : (s + 1 < UB ? &ecar[0] : nullptr);
-                sweep_step<DIR, WITH_DOT, CHECKED, MASKED>(ops[s & 1], dn, en, t0 + DIR * s, lane, srclane, is_out, w, yok,
-                                                           pdst + DIR * s * (32 * SKB), po_lane + ostep_l * s, dummy,
-                                                           dprev, cxprev, acc);
+                sweep_step<DIR, WITH_DOT, CHECKED, MASKED, OUTRING>(ops[s & 1], dn, en, t0 + DIR * s, lane, srclane, is_out, w, yok,
+                                                           pdst + DIR * s * (32 * SKB),
+                                                           po_lane + (OUTRING ? SKB : ostep_l) * s, dummy,
+                                                           dprev, cxprev, acc, edge_ready);
                 /* every row of the finished tile is in registers (the loads are warp-wide instructions issued, in
                  * order, before this arrive): hand the stage back to the loader warp */
                 if (r == 0) mbar_arrive_if(lane0, done_bar);
@@ -1004,11 +1060,9 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
                 if (trace && b == 4) tw_t4 = (long long)globaltimer_ns();
 #endif
                 if ((b & 1) == 0) credit_wait(sc0 + 2 * UB - 1);
-                const bool pub = is_out && b >= 3;
-                double* po_lane = pub ? out_base + (sc0 & (SW_RB - 1)) * SKB : dummy;
-                const int ostep_l = pub ? SKB : 0;
-                if (ring_feed && b <= last_ring_block) run_block(F, T, t0, sc0, eb0, po_lane, ostep_l);
-                else                                   run_block(F, F, t0, sc0, eb0, po_lane, ostep_l);
+                double* po_lane = (is_out && b >= 3) ? out_base + (sc0 & (SW_RB - 1)) * SKB : oscratch;
+                if (ring_feed && b <= last_ring_block) run_block(F, T, T, t0, sc0, eb0, po_lane, 0);
+                else                                   run_block(F, F, T, t0, sc0, eb0, po_lane, 0);
                 pdst += DIR * UB * (32 * SKB);
                 /* I have consumed my producer's steps up to (my step count + 31) */
                 st_int_if(pub_credit, credit_of_prev, (b + 1) * UB + 31);
@@ -1034,19 +1088,18 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
                 const bool rf = ring_feed && b <= last_ring_block;
                 if (out_ring) {
                     /* ring out, global row in: plain arithmetic and stores in every block (see above) */
-                    const bool pub = is_out && b >= 3;
-                    double* po_lane = pub ? out_base + (sc0 & (SW_RB - 1)) * SKB : dummy;
-                    run_block(F, F, t0, sc0, ecur, po_lane, pub ? SKB : 0);
+                    double* po_lane = (is_out && b >= 3) ? out_base + (sc0 & (SW_RB - 1)) * SKB : oscratch;
+                    run_block(F, F, T, t0, sc0, ecur, po_lane, 0);
                 } else {
                     /* global row out: per-cell predicates in the first and last blocks */
                     double* po_lane = is_out ? out_base + (t0 - E_OUT) * SKB : dummy;
                     const int ostep_l = is_out ? DIR * SKB : 0;
                     if (rf) {
-                        if (interior) run_block(F, T, t0, sc0, ecur, po_lane, ostep_l);
-                        else          run_block(T, T, t0, sc0, ecur, po_lane, ostep_l);
+                        if (interior) run_block(F, T, F, t0, sc0, ecur, po_lane, ostep_l);
+                        else          run_block(T, T, F, t0, sc0, ecur, po_lane, ostep_l);
                     } else {
-                        if (interior) run_block(F, F, t0, sc0, ecur, po_lane, ostep_l);
-                        else          run_block(T, F, t0, sc0, ecur, po_lane, ostep_l);
+                        if (interior) run_block(F, F, F, t0, sc0, ecur, po_lane, ostep_l);
+                        else          run_block(T, F, F, t0, sc0, ecur, po_lane, ostep_l);
                     }
                 }
                 pdst += DIR * UB * (32 * SKB);
@@ -1484,13 +1537,26 @@ void pcg_enqueue_iterations(SolveCtx& c, int n) {
         }
         dist_dot(c, DOT_ZS, 1);
         prof_mark(c, ps, 1);
+        const bool split_p = c.side != nullptr;
         k_update_pr<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.p, c.s, c.r, c.z, c.bnd_f, c.bnd_b, c.sc, c.tolerance, mfl,
-                                                     c.rank_max, rank, single_gpu(c));
+                                                     c.rank_max, rank, single_gpu(c), split_p ? 0 : 1);
         count(c);
+        if (split_p) {
+            /* scaledAdd(p, p, s, alpha) F3:607 next to the sweeps: it only has to finish before s is overwritten */
+            cudaEventRecord(c.ev_r, c.stream);
+            cudaStreamWaitEvent(c.side, c.ev_r, 0);
+            /* measured at 16384^2: the shorter the burst the better (a throttled grid disturbs the sweeps for longer) */
+            static const int side_blocks = getenv("IFL_SIDE_BLOCKS") ? atoi(getenv("IFL_SIDE_BLOCKS")) : (1 << 30);
+            const int nvb = (int)(eg.x * eg.y);
+            k_update_p<<<nvb < side_blocks ? nvb : side_blocks, EW_THREADS, 0, c.side>>>(c.g, c.p, c.s, c.sc, mfl, (int)eg.x, (int)eg.y);
+            cudaEventRecord(c.ev_p, c.side);
+            count(c);
+        }
         dist_max(c, 0);
         prof_mark(c, ps, 2);
         enqueue_precon(c, c.r, c.z, DOT_SIGMA_NEW, 1, ps);
         dist_dot(c, DOT_SIGMA_NEW, 1);
+        if (split_p) cudaStreamWaitEvent(c.stream, c.ev_p, 0);
         k_update_s<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.sc, mfl);
         count(c);
         dist_halo_rows(c, c.s);
