@@ -28,6 +28,8 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"       # NCCL prints its version banner on stdout: keep stdout to the one JSON line
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -43,6 +45,9 @@ WORKLOADS = {
 METRIC = "cell-updates/sec per full timestep"
 UNIT = "cell-updates/s"
 A_SWEEP_BYTES_PER_CELL = 40       # R a,aPlusX,aPlusY,precon -> W dst
+A_BWD_BYTES_PER_CELL = 48         # backward sweep (a14, 40 B) fused with dotProduct(z, r) (a16: the 8 B of r; z is in registers)
+# algorithmic bytes per cell and launch of the five kernels of a PCG iteration
+A_KERNEL_BYTES = {"matvec_dot": 40, "update_pr": 24, "precon_fwd": 40, "precon_bwd": 48, "update_s": 24}
 CPU_SAMPLE_GRID = 1024
 CPU_SAMPLE_LIMITS = (40, 120)
 
@@ -240,7 +245,7 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = g.launch_count() - launches0 + args.steps      # + one flush kernel per step (torch)
     value = W * H * args.steps / (ms * 1e-3)                  # strong scaling: the ranks share ONE grid
-    sweep_ms, nsamp = g.kernel_timing("precon_fwd")
+    sweep_ms, nsamp = g.kernel_timing("precon_bwd")
     kt = {k: g.kernel_timing(k)[0] for k in ("matvec_dot", "update_pr", "precon_fwd", "precon_bwd", "update_s")}
     phase = g.last_timing()
     g.set_profiling(False)
@@ -305,12 +310,12 @@ def main():
         s1.close()
 
     peak, peak_src = measured_hbm_peak()
-    achieved = A_SWEEP_BYTES_PER_CELL * W * H / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+    achieved = A_BWD_BYTES_PER_CELL * W * H / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(f"precon_fwd_dram_bytes_per_launch_{grid}")
+            traffic = json.load(open(tpath)).get(f"precon_bwd_dram_bytes_per_launch_{grid}")
         except Exception:
             traffic = None
 
@@ -329,14 +334,18 @@ def main():
                        "are computed redundantly on every rank"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_precon_sweep<+1> (applyPreconditioner forward sweep, F3:496-507)",
+            "roofline": {"bound": "hbm", "kernel": "k_precon_sweep<-1,dot> (applyPreconditioner backward sweep F3:509-520 fused "
+                                                   "with dotProduct(z,r) F3:625; the longest kernel of an iteration)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": A_SWEEP_BYTES_PER_CELL * W * H // world,
+                         "algorithmic_bytes_per_launch": A_BWD_BYTES_PER_CELL * W * H // world,
                          "avg_launch_ms": sweep_ms, "samples": nsamp,
                          "note": "a lexicographic recurrence: at most one anti-diagonal is in flight and the critical path is "
                                  "w + h dependent steps, so the kernel is latency bound below ~16k^2 (DESIGN.md 5)"},
             "kernel_ms": kt,
+            "kernel_gbs": {k: (A_KERNEL_BYTES[k] * W * H / world / (v * 1e-3) / 1e9 if v > 0 else None) for k, v in kt.items()},
+            "kernel_note": "precon_fwd runs next to k_update_p (p += alpha*s, 24 B/cell, side stream): its window moves 64 B/cell; "
+                           "update_pr is the r half (r -= alpha*z + infinityNorm, 24 B/cell)",
             "phase_ms_last_step": phase,
         }
         if world > 1:
