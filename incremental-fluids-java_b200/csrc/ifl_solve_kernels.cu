@@ -491,7 +491,10 @@ k_precon_coeffs(SkewGeom g, const double* __restrict__ ax, const double* __restr
  *     block; the producer only checks that word (local) before a block, so it can never lap the ring.
  * Only the first strip of a cluster takes its input from a global boundary row (previous cluster / previous GPU)
  * and only the last one writes one. */
-static constexpr int SW_CL_MAX = 8;                /* blocks per cluster (portable maximum) */
+#ifndef IFL_SW_CL
+#define IFL_SW_CL 8
+#endif
+static constexpr int SW_CL_MAX = IFL_SW_CL;        /* blocks per cluster (8 = portable maximum) */
 static constexpr int SW_RB = 128;                  /* ring slots per strip inbox */
 
 /* sentinel test on the high word only (0xFFF8B200: a NaN payload no arithmetic produces) */
@@ -668,7 +671,7 @@ __device__ __forceinline__ void ring_rearm(unsigned slot_addr, unsigned sent_hi)
 #define IFL_TW_PASS
 #endif
 __device__ __forceinline__ void ring_wait(unsigned slot_addr, double (&v)[SKB], bool need0, bool need1 IFL_TW_ARGS) {
-    if ((need0 && is_sentinel_hi(v[0])) || (need1 && is_sentinel_hi(v[SKB - 1]))) {
+    if (__builtin_expect((need0 && is_sentinel_hi(v[0])) || (need1 && is_sentinel_hi(v[SKB - 1])), 0)) {
         unsigned spins = 0;
         do { ring_peek(slot_addr, v); }
         while (((need0 && is_sentinel_hi(v[0])) || (need1 && is_sentinel_hi(v[SKB - 1]))) && ++spins < (1u << 22));
@@ -1500,6 +1503,8 @@ static void launch_sweep(SolveCtx& c, const double* src, double* dst, const doub
     if (!attr_done) {
         cudaFuncSetAttribute(k_precon_sweep<DIR, WITH_DOT, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sweep_smem(WITH_DOT));
+        if (SW_CL_MAX > 8)
+            cudaFuncSetAttribute(k_precon_sweep<DIR, WITH_DOT, MASKED>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         attr_done = true;
     }
     const int nown = c.g.s1 - c.g.s0;
