@@ -719,7 +719,7 @@ __device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB],
                                            const int lane, const int srclane, const bool is_out, const int w, const bool yok,
                                            double* pd, double* po, double* dummy, double (&dprev)[SKB], double& cxprev,
                                            double& acc, Ready&& edge_ready, double* xw, const unsigned xr,
-                                           const bool is_in_feed) {
+                                           const bool is_in_feed, double& acc_b) {
     double dl = DIR > 0 ? dprev[SKB - 1] : dprev[0];
     bool fl[SKB];
     double dnn[SKB];
@@ -758,7 +758,11 @@ __device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB],
         }
 #endif
         /* inactive lanes hold +0.0 and rr is zero in the padding: adding them is exact */
+#ifdef IFL_SW_ACC2
+        if (WITH_DOT) { if (j == 0) acc += d * op.rr[j]; else acc_b += d * op.rr[j]; }   /* one partial sum per sub-column */
+#else
         if (WITH_DOT) acc += d * op.rr[j];
+#endif
         dprev[j] = d;
         dl = d;
     }
@@ -883,7 +887,7 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     const int cw = (w + SKB - 1) / SKB;                               /* column blocks per row */
     const int nblk = (cw + 31 + UB - 1) / UB;
     const int ntile = nblk * (UB / U);
-    double acc = 0.0;
+    double acc = 0.0, acc_b = 0.0;
     if (live && loader) {
         if (lane == 0) {
             /* running pointers / shared addresses: this loop has to issue a tile faster than the strip warp consumes one */
@@ -1085,7 +1089,7 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
                                                            pdst + DIR * s * (32 * SKB),
                                                            po_lane + (OUTRING ? SKB : ostep_l) * s, dummy,
                                                            dprev, cxprev, acc, edge_ready, xw_b + s * SKB,
-                                                           xr_b + (unsigned)(s * SKB * (int)sizeof(double)), is_in_feed);
+                                                           xr_b + (unsigned)(s * SKB * (int)sizeof(double)), is_in_feed, acc_b);
 #ifndef IFL_SW_SHFL
                 if (RINGFEED) ring_rearm(in_rest + (unsigned)(s * SKB * (int)sizeof(double)), sent_hi);   /* after it was read */
 #endif
@@ -1226,7 +1230,7 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
         }
     }
     if (WITH_DOT && live && !loader) {
-        double ws = warp_sum(acc);
+        double ws = warp_sum(acc + acc_b);
         if (lane == 0) {
             strip_part[k] = ws;
             __threadfence();
