@@ -47,7 +47,8 @@ UNIT = "cell-updates/s"
 A_SWEEP_BYTES_PER_CELL = 40       # R a,aPlusX,aPlusY,precon -> W dst
 A_BWD_BYTES_PER_CELL = 48         # backward sweep (a14, 40 B) fused with dotProduct(z, r) (a16: the 8 B of r; z is in registers)
 # algorithmic bytes per cell and launch of the five kernels of a PCG iteration
-A_KERNEL_BYTES = {"matvec_dot": 40, "update_pr": 24, "precon_fwd": 40, "precon_bwd": 48, "update_s": 24}
+# matvec_dot: F3's matrix is re-derived from the grid position (R s -> W z); update_s carries the deferred p += alpha*s
+A_KERNEL_BYTES = {"matvec_dot": 16, "update_pr": 24, "precon_fwd": 40, "precon_bwd": 48, "update_s": 40}
 CPU_SAMPLE_GRID = 1024
 CPU_SAMPLE_LIMITS = (40, 120)
 
@@ -344,8 +345,9 @@ def main():
                                  "w + h dependent steps, so the kernel is latency bound below ~16k^2 (DESIGN.md 5)"},
             "kernel_ms": kt,
             "kernel_gbs": {k: (A_KERNEL_BYTES[k] * W * H / world / (v * 1e-3) / 1e9 if v > 0 else None) for k, v in kt.items()},
-            "kernel_note": "precon_fwd runs next to k_update_p (p += alpha*s, 24 B/cell, side stream): its window moves 64 B/cell; "
-                           "update_pr is the r half (r -= alpha*z + infinityNorm, 24 B/cell)",
+            "kernel_note": "algorithmic bytes per cell: matvec_dot 16 (F3 matrix re-derived per cell: R s, W z), update_pr 24 "
+                           "(r -= alpha*z + infinityNorm), sweeps 40 / 48, update_s 40 (k_update_sp: p += alpha*s and "
+                           "s = z + beta*s in one pass)",
             "phase_ms_last_step": phase,
         }
         if world > 1:

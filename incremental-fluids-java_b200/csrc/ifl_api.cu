@@ -179,9 +179,6 @@ void ifl_destroy(ifl_solver* s) {
     }
     for (auto& e : s->ev_chunk) if (e) cudaEventDestroy(e);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
-    if (s->sx.ev_r) cudaEventDestroy(s->sx.ev_r);
-    if (s->sx.ev_p) cudaEventDestroy(s->sx.ev_p);
-    if (s->sx.side) cudaStreamDestroy(s->sx.side);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -290,12 +287,7 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
         s->sx.fl += guard;
     }
     s->sx.stream = s->stream;
-    s->sx.side = nullptr; s->sx.ev_r = nullptr; s->sx.ev_p = nullptr;
-    if (uses_pcg(s) && !getenv("IFL_NO_SIDE_STREAM")) {
-        CU(cudaStreamCreateWithFlags(&s->sx.side, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&s->sx.ev_r, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&s->sx.ev_p, cudaEventDisableTiming));
-    }
+    s->sx.const_matrix = 0; s->sx.const_scale = 0.0;
     s->sx.launches = &s->launches;
     s->sx.prof = &s->prof;
     s->sx.trace = nullptr;
@@ -434,6 +426,8 @@ static int stage_build_rhs(ifl_solver* s) {
 static int stage_build_matrix(ifl_solver* s, double timestep) {
     double scale = timestep / (s->cfg.density * s->hx * s->hx);             /* F3:436 */
     launch_build_matrix_f3(s->stream, s->sx.g, s->sx.adiag, s->sx.aplusx, s->sx.aplusy, scale);
+    s->sx.const_matrix = getenv("IFL_NO_CONST_MATRIX") ? 0 : 1;   /* the arrays are still filled: MIC(0) build and read_field use them */
+    s->sx.const_scale = scale;
     s->launches++;
     return IFL_OK;
 }
@@ -886,6 +880,7 @@ int ifl_write_field(ifl_solver* s, int32_t field, const double* host, size_t cou
         snprintf(g_err, sizeof g_err, "field %d (cell/body) is derived by fillSolidFields and is read-only", field);
         return IFL_ERR_UNSUPPORTED;
     }
+    if (field == IFL_FIELD_ADIAG || field == IFL_FIELD_APLUSX || field == IFL_FIELD_APLUSY) s->sx.const_matrix = 0;
     if (kind == KIND_SKEW) {
         CU(cudaMemcpyAsync(s->scratch, host, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
         launch_rows_to_skew(s->stream, s->sx.g, s->scratch, (double*)p);

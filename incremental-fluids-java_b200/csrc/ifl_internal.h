@@ -53,7 +53,7 @@ struct SolveScalars {
     unsigned int ctr_b;
     unsigned int ticket_f;  /* strip tickets of the forward / backward wavefront */
     unsigned int ticket_b;
-    int p_go;            /* 1: the p += alpha*s of this iteration has to be applied (k_update_p, side stream) */
+    int p_pending;       /* 1: r has been updated by this iteration but its p += alpha*s has not been applied yet */
 };
 
 /* slab decomposition (ifl_comm.cu): rank r owns the strips [s0, s1) of the pressure solve */
@@ -102,8 +102,8 @@ struct SolveCtx {
     unsigned char* fl;    /* skewed fluid flags of _d._cell (F4+), nullptr for F1-F3 */
     int mask_vector_ops;  /* F6+: dotProduct/scaledAdd/infinityNorm only over fluid cells (F6:999-1064) */
     cudaStream_t stream;
-    cudaStream_t side;    /* p += alpha*s runs here, next to the triangular sweeps (which leave half the bandwidth idle) */
-    cudaEvent_t ev_r, ev_p;
+    int const_matrix;     /* F3: the matrix is a function of the grid position alone (k_matvec_dot<true> re-derives it) */
+    double const_scale;   /* ... with this `scale` (F3:436) */
     unsigned long long* launches;
     Profiler* prof;
     /* slab decomposition */

@@ -135,25 +135,45 @@ __global__ void k_apply_max(const unsigned long long* __restrict__ rank_max, int
     if (err != err) { sc->done = 1; sc->nan = 1; }
 }
 
-/* z = A s fused with the partial sums of z.s   (matrixVectorProduct F3:544, dotProduct F3:532) */
+/* z = A s fused with the partial sums of z.s   (matrixVectorProduct F3:544, dotProduct F3:532).
+ * CONSTM (F3, whose matrix buildPressureMatrix F3:435 fills from the grid position alone): the coefficients are
+ * re-derived per cell instead of read -- aDiag is `scale` added once per in-grid neighbour (the same additions, in the
+ * same order, as k_build_matrix_f3), aPlusX / aPlusY are -scale wherever the guarded term exists -- so the kernel moves
+ * 16 instead of 40 bytes per cell and produces the same bits. */
+template <bool CONSTM>
 __global__ void __launch_bounds__(EW_THREADS)
 k_matvec_dot(SkewGeom g, const double* __restrict__ adiag, const double* __restrict__ ax,
              const double* __restrict__ ay, const double* __restrict__ b, double* __restrict__ dst,
              double* partials, double* strip_part, SolveScalars* sc, int dot_mode, int check_done,
-             const unsigned char* __restrict__ fl, int single_gpu) {
+             const unsigned char* __restrict__ fl, int single_gpu, double cscale) {
     if (check_done && sc->done) return;
     __shared__ double smem8[8];
     __shared__ bool s_last;
     double acc = 0.0;
+    const double ms = -cscale;
     IFL_EW_LOOP_BEGIN(g)
         IFL_EW_NEIGHBOURS(g)
         if (ok_) {
             double bc = b[i_];
-            double tv = adiag[i_] * bc;
-            if (x_ > 0) tv += ax[nl_] * b[nl_];
-            if (y_ > 0) tv += ay[nu_] * b[nu_];
-            if (x_ < g.w - 1) tv += ax[i_] * b[nr_];
-            if (y_ < g.h - 1) tv += ay[i_] * b[nd_];
+            double tv;
+            if (CONSTM) {
+                double dg = 0.0;
+                if (y_ > 0) dg += cscale;
+                if (x_ > 0) dg += cscale;
+                if (x_ < g.w - 1) dg += cscale;
+                if (y_ < g.h - 1) dg += cscale;
+                tv = dg * bc;
+                if (x_ > 0) tv += ms * b[nl_];
+                if (y_ > 0) tv += ms * b[nu_];
+                if (x_ < g.w - 1) tv += ms * b[nr_];
+                if (y_ < g.h - 1) tv += ms * b[nd_];
+            } else {
+                tv = adiag[i_] * bc;
+                if (x_ > 0) tv += ax[nl_] * b[nl_];
+                if (y_ > 0) tv += ay[nu_] * b[nu_];
+                if (x_ < g.w - 1) tv += ax[i_] * b[nr_];
+                if (y_ < g.h - 1) tv += ay[i_] * b[nd_];
+            }
             dst[i_] = tv;                                   /* matrixVectorProduct is never masked (F6:1011) */
             if (fl == nullptr || fl[i_]) acc += tv * bc;    /* dotProduct: fluid cells only from F6 on (F6:999) */
         }
@@ -163,40 +183,35 @@ k_matvec_dot(SkewGeom g, const double* __restrict__ adiag, const double* __restr
     finish_partials(bs, partials, g, strip_part, sc, dot_mode, single_gpu, &s_last);
 }
 
-/* scaledAdd(_p, _p, _s, alpha) F3:607 (masked F6:1041) on its own: see k_update_pr(with_p = 0) */
+/* scaledAdd(_p, _p, _s, alpha) F3:607 (masked F6:1041) of the LAST iteration of a solve.  Inside the loop the update
+ * of p rides on k_update_sp (p is not read by anything else in the loop, so it only has to happen before s is
+ * overwritten); the iteration that converges never reaches k_update_sp, and its update is applied here. */
 __global__ void __launch_bounds__(EW_THREADS)
 k_update_p(SkewGeom g, double* __restrict__ p, const double* __restrict__ s, const SolveScalars* sc,
-           const unsigned char* __restrict__ fl, int nvx, int nvy) {
-    if (!sc->p_go) return;
+           const unsigned char* __restrict__ fl) {
+    if (!sc->p_pending) return;
     const double alpha = sc->alpha;
-    /* the grid walks the (nvx, nvy) blocks of the usual element-wise decomposition (one each by default) */
-    for (int vb = blockIdx.x; vb < nvx * nvy; vb += gridDim.x) {
-        IFL_EW_LOOP_BEGIN_AT(g, vb % nvx, vb / nvx)
-            if (ok_ && (fl == nullptr || fl[i_])) p[i_] = p[i_] + s[i_] * alpha;
-        IFL_EW_LOOP_END
-    }
+    IFL_EW_LOOP_BEGIN(g)
+        if (ok_ && (fl == nullptr || fl[i_])) p[i_] = p[i_] + s[i_] * alpha;
+    IFL_EW_LOOP_END
 }
 
-/* p += alpha s ; r -= alpha z ; maxError = infinityNorm(r)   (F3:606-608, scaledAdd F3:570,
- * infinityNorm F3:579).  Also re-arms the boundary rows and tickets of the two sweeps
+/* r -= alpha z ; maxError = infinityNorm(r)   (F3:608, scaledAdd F3:570, infinityNorm F3:579); the p += alpha s of
+ * F3:607 is flagged as pending (k_update_sp / k_update_p).  Also re-arms the boundary rows and tickets of the two sweeps
  * that follow.  The last block decides convergence (F3:609-619). */
 __global__ void __launch_bounds__(EW_THREADS)
-k_update_pr(SkewGeom g, double* __restrict__ p, const double* __restrict__ s, double* __restrict__ r,
+k_update_pr(SkewGeom g, double* __restrict__ r,
             const double* __restrict__ z, double* __restrict__ bnd_f, double* __restrict__ bnd_b,
             SolveScalars* sc, double tol, const unsigned char* __restrict__ fl,
-            unsigned long long* rank_max, int rank, int single_gpu, int with_p) {
-    /* with_p == 0: p is updated by k_update_p on the side stream; it has to know whether THIS iteration runs (`done`
-     * may be set by this very kernel's last block, after every block has passed this point) */
-    const bool first = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
-    if (sc->done) { if (!with_p && first) sc->p_go = 0; return; }
-    if (!with_p && first) sc->p_go = 1;
+            unsigned long long* rank_max, int rank, int single_gpu) {
+    if (sc->done) return;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) sc->p_pending = 1;
     __shared__ unsigned s_max[8];
     __shared__ bool s_last;
-    const double alpha = sc->alpha, nalpha = sc->neg_alpha;
+    const double nalpha = sc->neg_alpha;
     unsigned m = 0;
     IFL_EW_LOOP_BEGIN(g)
         if (ok_ && (fl == nullptr || fl[i_])) {
-            if (with_p) p[i_] = p[i_] + s[i_] * alpha;
             double rv = r[i_] + z[i_] * nalpha;
             r[i_] = rv;
             unsigned bits = absf_bits(rv);
@@ -245,14 +260,19 @@ k_update_pr(SkewGeom g, double* __restrict__ p, const double* __restrict__ s, do
     }
 }
 
-/* s = z + s * beta   (F3:626) */
+/* p = p + s * alpha (F3:607, deferred: see k_update_p) ; s = z + s * beta   (F3:626) */
 __global__ void __launch_bounds__(EW_THREADS)
-k_update_s(SkewGeom g, double* __restrict__ s, const double* __restrict__ z, SolveScalars* sc,
-           const unsigned char* __restrict__ fl) {
-    if (sc->done) return;
-    const double beta = sc->beta;
+k_update_sp(SkewGeom g, double* __restrict__ s, const double* __restrict__ z, double* __restrict__ p, SolveScalars* sc,
+            const unsigned char* __restrict__ fl) {
+    if (sc->done) return;          /* `done` is only ever set by this iteration's k_update_pr: not done => p is pending */
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) sc->p_pending = 0;
+    const double beta = sc->beta, alpha = sc->alpha;
     IFL_EW_LOOP_BEGIN(g)
-        if (ok_ && (fl == nullptr || fl[i_])) s[i_] = z[i_] + s[i_] * beta;
+        if (ok_ && (fl == nullptr || fl[i_])) {
+            const double sv = s[i_];
+            p[i_] = p[i_] + sv * alpha;
+            s[i_] = z[i_] + sv * beta;
+        }
     IFL_EW_LOOP_END
 }
 
@@ -312,7 +332,7 @@ __global__ void k_solve_reset(SkewGeom g, double* bnd_f, double* bnd_b, SolveSca
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc->sigma = 0.0; sc->alpha = 0.0; sc->neg_alpha = 0.0; sc->beta = 0.0; sc->zs = 0.0;
         sc->max_error = 0.0; sc->max_bits = 0ull;
-        sc->iterations = 0; sc->done = 0; sc->nan = 0; sc->exceeded = 0;
+        sc->iterations = 0; sc->done = 0; sc->nan = 0; sc->exceeded = 0; sc->p_pending = 0;
         sc->ctr_a = 0; sc->ctr_b = 0; sc->ticket_f = 0; sc->ticket_b = 0;
     }
 }
@@ -328,6 +348,7 @@ __global__ void k_sweep_rearm(SkewGeom g, double* bnd_f, double* bnd_b, SolveSca
 }
 
 __global__ void k_solve_finish(SolveScalars* sc, int limit) {
+    sc->p_pending = 0;
     if (!sc->done && sc->iterations >= limit) sc->exceeded = 1;
 }
 
@@ -1557,13 +1578,23 @@ static void enqueue_precon(SolveCtx& c, const double* src, double* dst, int dot_
 void launch_apply_precon(SolveCtx& c, const double* src, double* dst, int /*with_dot_mode*/) {
     k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
     count(c);
+    /* slab decomposition: no neighbour may store into an inbox row before its owner has re-armed it */
+    if (!single_gpu(c)) comm_all_gather(*c.comm, c.rank_max + c.comm->rank, c.rank_max, sizeof(unsigned long long));
     enqueue_precon(c, src, dst, DOT_NONE, 0);
 }
 
-void launch_matvec(SolveCtx& c, const double* b, double* dst) {
-    k_matvec_dot<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, b, dst,
-                                                           c.partials, c.strip_part, c.sc, DOT_NONE, 0, nullptr, 1);
+static void enqueue_matvec(SolveCtx& c, const SkewGeom& g, const double* b, double* dst, int dot_mode, int check_done,
+                           const unsigned char* fl, int single) {
+    if (c.const_matrix)
+        k_matvec_dot<true><<<ew_grid(g), EW_THREADS, 0, c.stream>>>(g, c.adiag, c.aplusx, c.aplusy, b, dst, c.partials, c.strip_part,
+                                                                    c.sc, dot_mode, check_done, fl, single, c.const_scale);
+    else
+        k_matvec_dot<false><<<ew_grid(g), EW_THREADS, 0, c.stream>>>(g, c.adiag, c.aplusx, c.aplusy, b, dst, c.partials, c.strip_part,
+                                                                     c.sc, dot_mode, check_done, fl, single, 0.0);
     count(c);
+}
+void launch_matvec(SolveCtx& c, const double* b, double* dst) {
+    enqueue_matvec(c, c.g, b, dst, DOT_NONE, 0, nullptr, 1);
 }
 
 /* ---- distributed pieces (no-ops on a single GPU) ---- */
@@ -1631,36 +1662,21 @@ void pcg_enqueue_iterations(SolveCtx& c, int n) {
     const int rank = c.comm ? c.comm->rank : 0;
     for (int it = 0; it < n; it++) {
         const int ps = (it == 0 && !c.sequential) ? prof_begin(c, 0) : -1;
-        k_matvec_dot<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.s, c.z, c.partials, c.strip_part,
-                                                      c.sc, c.sequential ? DOT_NONE : DOT_ZS, 1, mfl, single_gpu(c));
-        count(c);
+        enqueue_matvec(c, c.g, c.s, c.z, c.sequential ? DOT_NONE : DOT_ZS, 1, mfl, single_gpu(c));
         if (c.sequential) {
             k_dot_sequential<<<1, 32, 0, c.stream>>>(c.g, c.z, c.s, c.sc, DOT_ZS, 1, mfl);
             count(c);
         }
         dist_dot(c, DOT_ZS, 1);
         prof_mark(c, ps, 1);
-        const bool split_p = c.side != nullptr;
-        k_update_pr<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.p, c.s, c.r, c.z, c.bnd_f, c.bnd_b, c.sc, c.tolerance, mfl,
-                                                     c.rank_max, rank, single_gpu(c), split_p ? 0 : 1);
+        k_update_pr<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.r, c.z, c.bnd_f, c.bnd_b, c.sc, c.tolerance, mfl,
+                                                     c.rank_max, rank, single_gpu(c));
         count(c);
-        if (split_p) {
-            /* scaledAdd(p, p, s, alpha) F3:607 next to the sweeps: it only has to finish before s is overwritten */
-            cudaEventRecord(c.ev_r, c.stream);
-            cudaStreamWaitEvent(c.side, c.ev_r, 0);
-            /* measured at 16384^2: the shorter the burst the better (a throttled grid disturbs the sweeps for longer) */
-            static const int side_blocks = getenv("IFL_SIDE_BLOCKS") ? atoi(getenv("IFL_SIDE_BLOCKS")) : (1 << 30);
-            const int nvb = (int)(eg.x * eg.y);
-            k_update_p<<<nvb < side_blocks ? nvb : side_blocks, EW_THREADS, 0, c.side>>>(c.g, c.p, c.s, c.sc, mfl, (int)eg.x, (int)eg.y);
-            cudaEventRecord(c.ev_p, c.side);
-            count(c);
-        }
         dist_max(c, 0);
         prof_mark(c, ps, 2);
         enqueue_precon(c, c.r, c.z, DOT_SIGMA_NEW, 1, ps);
         dist_dot(c, DOT_SIGMA_NEW, 1);
-        if (split_p) cudaStreamWaitEvent(c.stream, c.ev_p, 0);
-        k_update_s<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.sc, mfl);
+        k_update_sp<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.p, c.sc, mfl);
         count(c);
         dist_halo_rows(c, c.s);
         prof_mark(c, ps, 5);
@@ -1668,8 +1684,10 @@ void pcg_enqueue_iterations(SolveCtx& c, int n) {
 }
 
 void pcg_enqueue_finish(SolveCtx& c, int limit) {
+    /* the converging iteration's p += alpha*s (no-op when the loop ended on its iteration limit) */
+    k_update_p<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.p, c.s, c.sc, c.mask_vector_ops ? c.fl : nullptr);
     k_solve_finish<<<1, 1, 0, c.stream>>>(c.sc, limit);
-    count(c);
+    count(c, 2);
     if (!single_gpu(c)) {
         /* every rank needs the whole pressure field for applyPressure: in-place all-gather of the slabs */
         const size_t chunk = (size_t)(c.strips_alloc / c.comm->world) * (size_t)c.g.ss;

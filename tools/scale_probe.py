@@ -16,7 +16,7 @@ st = g.update(0.005)
 dt = time.perf_counter() - t0
 cells = n * n
 print(f"grid {n}^2 its {st['iterations_pressure']} step {dt*1e3:.1f} ms  phases {g.last_timing()}")
-for k, bytes_per_cell in (("matvec_dot", 40), ("update_pr", 24), ("precon_fwd", 40), ("precon_bwd", 48), ("update_s", 24)):
+for k, bytes_per_cell in (("matvec_dot", 16), ("update_pr", 24), ("precon_fwd", 40), ("precon_bwd", 48), ("update_s", 40)):
     ms, ns = g.kernel_timing(k)
     if ns:
         print(f"  {k:12s} {ms:9.3f} ms  {bytes_per_cell*cells/ms/1e6:8.1f} GB/s  ({ns} samples)")
