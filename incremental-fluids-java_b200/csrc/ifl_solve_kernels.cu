@@ -1271,6 +1271,8 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     cluster.sync();
 }
 
+#include "ifl_sweep2.cuh"
+
 /* buildPreconditioner F3:464 / masked F4:744 (=F5:858, F6:918, F7:951) -- MIC(0) with tau/sigma,
  * lexicographic recurrence on precon.  fl = skewed fluid flags (F4+: non-fluid cells are skipped and
  * never used as neighbours) or nullptr. */
@@ -1551,20 +1553,57 @@ static void launch_sweep(SolveCtx& c, const double* src, double* dst, const doub
                        dot_mode, check_done, trace);
 }
 
+/* the two-rows-per-lane sweep (ifl_sweep2.cuh): same launch shape, unmasked variants only */
+template <int DIR, bool WITH_DOT>
+static void launch_sweep2(SolveCtx& c, const double* src, double* dst, const double* pack, const double* rr, double* bnd,
+                          int dot_mode, int check_done, long long* trace) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_precon_sweep2<DIR, WITH_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem(WITH_DOT));
+        if (SW_CL_MAX > 8) cudaFuncSetAttribute(k_precon_sweep2<DIR, WITH_DOT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        attr_done = true;
+    }
+    const int nown = c.g.s1 - c.g.s0;
+    double* peer = nullptr;
+    if (c.comm) peer = DIR > 0 ? c.peer_bnd_f_next : c.peer_bnd_b_prev;
+    const int nblocks = (nown + SW_WARPS - 1) / SW_WARPS;
+    int cl = SW_CL_MAX;
+    while (cl > 1 && cl > nblocks) cl >>= 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(((nblocks + cl - 1) / cl) * cl);
+    cfg.blockDim = dim3(2 * SW_WARPS * 32);
+    cfg.dynamicSmemBytes = sweep_smem(WITH_DOT);
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = cl; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_precon_sweep2<DIR, WITH_DOT>, c.g, src, dst, pack, rr, bnd, peer, c.strip_part, c.sc,
+                       dot_mode, check_done, trace);
+}
+
 /* dst = M^-1 src: forward then backward sweep.  Boundary rows must be armed. */
 static inline void prof_mark(SolveCtx& c, int slot, int e);
 static void enqueue_precon(SolveCtx& c, const double* src, double* dst, int dot_mode, int check_done, int ps = -1) {
     const bool masked = c.fl != nullptr;
+    /* IFL_SWEEP2=1 selects the two-rows-per-lane kernel (ifl_sweep2.cuh; unmasked variants).  It halves the skew of a
+     * strip but its macro-step costs 1.3-1.5x, and with 80-100 KB of staged operands per strip too few strips are
+     * resident: measured slower at 16384^2 on 1 and 2 GPUs, equal at 4096^2, 10 % faster at 1024^2. */
+    static const bool want2 = getenv("IFL_SWEEP2") != nullptr;
+    const bool two_rows = !masked && want2;
     if (masked) launch_sweep<1, false, true>(c, src, dst, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
+    else if (two_rows) launch_sweep2<1, false>(c, src, dst, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
     else        launch_sweep<1, false, false>(c, src, dst, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
     prof_mark(c, ps, 3);
     int fused_mode = c.sequential ? DOT_NONE : dot_mode;
     long long* tr2 = c.trace ? c.trace + 8 * c.g.nstrips : nullptr;
     if (dot_mode != DOT_NONE) {
         if (masked) launch_sweep<-1, true, true>(c, dst, dst, c.pack_b, src, c.bnd_b, fused_mode, check_done, tr2);
+        else if (two_rows) launch_sweep2<-1, true>(c, dst, dst, c.pack_b, src, c.bnd_b, fused_mode, check_done, tr2);
         else        launch_sweep<-1, true, false>(c, dst, dst, c.pack_b, src, c.bnd_b, fused_mode, check_done, tr2);
     } else {
         if (masked) launch_sweep<-1, false, true>(c, dst, dst, c.pack_b, nullptr, c.bnd_b, DOT_NONE, check_done, tr2);
+        else if (two_rows) launch_sweep2<-1, false>(c, dst, dst, c.pack_b, nullptr, c.bnd_b, DOT_NONE, check_done, tr2);
         else        launch_sweep<-1, false, false>(c, dst, dst, c.pack_b, nullptr, c.bnd_b, DOT_NONE, check_done, tr2);
     }
     prof_mark(c, ps, 4);
