@@ -243,6 +243,20 @@ int ifl_write_particles(ifl_solver* s, const double* pos_x, const double* pos_y,
                         const double* prop_d, const double* prop_t,
                         const double* prop_u, const double* prop_v, size_t count);
 
+/* FluidSolver.toImage: the reference's only observable output (a plain-text PPM frame per call from main()).
+ *   F1:341 (=F2:356, F3:397): shade = clamp((int)((1 - d) * 255), 0, 255);  F4:664: solid cells black;
+ *   F5:1133: (1 - d) * volume * 255;  toImage(destination, renderHeat) F6:1250 (=F7:1282): the density panel
+ *   (int)(clamp((1 - d) * volume, 0, 1) * 255) and, with renderHeat, a heat panel to its LEFT (t = (T - Tamb) / 700);
+ *   F8:1417: EMPTY cells red, t = |(float) T - Tamb| / 70.
+ * ifl_image_size: pixels of a frame = (render_heat ? 2w : w) * h (render_heat needs variant >= F6).
+ * ifl_to_image:   the three integers per pixel the reference writes, rgb[3 * pixels], computed on the device.
+ * ifl_write_ppm:  the reference's text file, byte for byte: "P3\n<W> <h>\n255\n", then "r g b " per pixel with a
+ *                 newline after every pixel whose index is a multiple of the SOLVER width (the `i % _w == 0` of F1:354,
+ *                 kept as is -- also for the double-width frames of renderHeat). */
+int ifl_image_size(const ifl_solver* s, int32_t render_heat, size_t* pixels);
+int ifl_to_image(ifl_solver* s, int32_t render_heat, int32_t* rgb, size_t pixels);
+int ifl_write_ppm(ifl_solver* s, const char* path, int32_t render_heat);
+
 /* Block until every launched kernel of this handle has finished. */
 int ifl_synchronize(ifl_solver* s);
 

@@ -101,6 +101,9 @@ PROTOTYPES = {
     "ifl_particle_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "ifl_read_particles": (C.c_int, [C.c_void_p] + [_dp] * 6 + [C.c_size_t]),
     "ifl_write_particles": (C.c_int, [C.c_void_p] + [_dp] * 6 + [C.c_size_t]),
+    "ifl_image_size": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_size_t)]),
+    "ifl_to_image": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_size_t]),
+    "ifl_write_ppm": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
     "ifl_synchronize": (C.c_int, [C.c_void_p]),
     "ifl_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "ifl_last_timing": (C.c_int, [C.c_void_p, _dp]),

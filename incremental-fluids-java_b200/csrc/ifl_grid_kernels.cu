@@ -277,6 +277,51 @@ __global__ void k_max_velocity(FieldView u, FieldView v, int w, int h, unsigned 
     }
     if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0) atomicMax(out_bits, bits);
 }
+/* FluidSolver.toImage: the integers of one frame (see include/incfluid_b200.h).  One thread per cell; with render_heat
+ * the frame is 2w wide, heat panel at x, density panel at x + w (idxl / idxr of F6:1263-1264). */
+__global__ void k_to_image(int variant, int w, int h, const double* __restrict__ d, const double* __restrict__ t,
+                           const double* __restrict__ volume, const unsigned char* __restrict__ cell,
+                           double t_ambient, int render_heat, int* __restrict__ rgb) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const size_t i = (size_t)x + (size_t)y * w;
+    if (variant < IFL_F6_HEAT) {
+        double v = 1.0 - d[i];
+        if (variant == IFL_F5_CURVED_BOUNDARIES) v = v * volume[i];          /* F5:1142 */
+        int shade = jint(v * 255.0);                                         /* F1:351 */
+        shade = max(min(shade, 255), 0);                                     /* F1:352 */
+        if (variant == IFL_F4_SOLID_BOUNDARIES && cell[i] == IFL_CELL_SOLID) shade = 0;   /* F4:678 */
+        rgb[3 * i + 0] = shade; rgb[3 * i + 1] = shade; rgb[3 * i + 2] = shade;
+        return;
+    }
+    const size_t fw = render_heat ? 2 * (size_t)w : (size_t)w;
+    const size_t ir = 3 * ((size_t)x + (size_t)y * fw + (render_heat ? (size_t)w : 0));
+    const double vol = volume[i];
+    double shade = (1.0 - d[i]) * vol;                                       /* F6:1271 */
+    shade = jmin(jmax(shade, 0.0), 1.0);
+    int c = jint(shade * 255.0);
+    int r = c, g = c, b = c;
+    if (variant == IFL_F8_FLIP && cell[i] == IFL_CELL_EMPTY) { r = 0xFF; g = 0; b = 0; }   /* F8:1444 */
+    rgb[ir + 0] = r; rgb[ir + 1] = g; rgb[ir + 2] = b;
+    if (render_heat) {
+        double tt;
+        if (variant == IFL_F8_FLIP) tt = fabs(jfloat(t[i]) - t_ambient) / 70.0;      /* F8:1450: (float) binds to the sample only */
+        else tt = (t[i] - t_ambient) / 700.0;                                        /* F6:1279 */
+        tt = jmin(jmax(tt, 0.0), 1.0);
+        const double hr = 1.0 + vol * (jmin(tt * 4.0, 1.0) - 1.0);
+        const double hg = 1.0 + vol * (jmin(tt * 2.0, 1.0) - 1.0);
+        const double hb = 1.0 + vol * (jmax(jmin(tt * 4.0 - 3.0, 1.0), 0.0) - 1.0);
+        const size_t il = 3 * ((size_t)x + (size_t)y * fw);
+        rgb[il + 0] = jint(hr * 255.0); rgb[il + 1] = jint(hg * 255.0); rgb[il + 2] = jint(hb * 255.0);
+    }
+}
+void launch_to_image(cudaStream_t st, int variant, int w, int h, const double* d, const double* t, const double* volume,
+                     const unsigned char* cell, double t_ambient, int render_heat, int* rgb) {
+    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+    k_to_image<<<grid, block, 0, st>>>(variant, w, h, d, t, volume, cell, t_ambient, render_heat, rgb);
+}
+
 void launch_max_velocity(cudaStream_t st, int w, int h, const double* u, const double* v, unsigned long long* out_bits) {
     QGeom qu{w + 1, h, 0.0, 0.5}, qv{w, h + 1, 0.5, 0.0};
     dim3 block(32, 8);

@@ -128,6 +128,8 @@ void launch_apply_pressure(cudaStream_t st, const SkewGeom& g, const double* p, 
 void launch_skew_to_rows(cudaStream_t st, const SkewGeom& g, const double* skew, double* rows);
 void launch_rows_to_skew(cudaStream_t st, const SkewGeom& g, const double* rows, double* skew);
 void launch_max_velocity(cudaStream_t st, int w, int h, const double* u, const double* v, unsigned long long* out_bits);
+void launch_to_image(cudaStream_t st, int variant, int w, int h, const double* d, const double* t, const double* volume,
+                     const unsigned char* cell, double t_ambient, int render_heat, int* rgb);
 
 /* ---- F4-F7 grid kernels: ifl_solid_kernels.cu ---- */
 void launch_fill_solid_fields(cudaStream_t st, const SolidQ& q, const ifl_body* bodies, int nbodies, double hx, int variant);

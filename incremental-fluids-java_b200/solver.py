@@ -7,6 +7,7 @@ FluidQuantity, physics.solidBodies.SolidBox / SolidSphere): `FluidSolver(w, h, d
 entry points a Java FluidSolver binds with Panama FFM.  No arithmetic happens here.
 """
 import ctypes as C
+import os
 import math
 
 import numpy as np
@@ -169,6 +170,19 @@ class FluidSolver:
         check(self._fn["ifl_max_timestep"](self._h_, C.byref(out)))
         return out.value
 
+    def toImage(self, destination, renderHeat=False):
+        """FluidSolver.toImage(destination) F1:341 ... F5:1133 / toImage(destination, renderHeat) F6:1250, F8:1417:
+        the reference's plain-text PPM frame, byte for byte (pixels computed on the device)."""
+        check(self._fn["ifl_write_ppm"](self._h_, os.fsencode(destination), 1 if renderHeat else 0))
+
+    def image(self, renderHeat=False):
+        """The integers of one frame as an array [h][(2w if renderHeat else w)][3] (ifl_to_image)."""
+        n = C.c_size_t()
+        check(self._fn["ifl_image_size"](self._h_, 1 if renderHeat else 0, C.byref(n)))
+        out = np.empty(3 * n.value, dtype=np.int32)
+        check(self._fn["ifl_to_image"](self._h_, 1 if renderHeat else 0, out.ctypes.data_as(C.POINTER(C.c_int32)), n.value))
+        return out.reshape(self._h, -1, 3)
+
     def ambientT(self):
         """FluidSolver.ambientT() F6:1240"""
         return self.cfg.t_ambient
@@ -210,6 +224,7 @@ class FluidSolver:
     read = read_field
     write = write_field
     add_inflow = addInflow
+    to_image = toImage
     max_timestep = maxTimestep
 
     # -- F8 particles (ParticleQuantities F8:1479) ------------------------------------------

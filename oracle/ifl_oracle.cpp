@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 #include <algorithm>
 
@@ -1259,6 +1260,63 @@ struct Solver {
         return jmin(maxTimestep, 1.0);
     }
 
+    /* toImage: the integers of one frame, rgb[3 * pixels], pixels = (renderHeat ? 2w : w) * h.
+     * F1:341 (=F2:356, F3:397), F4:664, F5:1133; toImage(destination, renderHeat) F6:1250 (=F7:1282), F8:1417. */
+    void toImage(bool renderHeat, int32_t* rgb) const {
+        if (variant < IFL_F6_HEAT) {
+            for (int i = 0; i < w * h; i++) {
+                double val = 1.0 - d.src[i];
+                if (variant == IFL_F5_CURVED_BOUNDARIES) val = val * d.vol(i % w, i / w);        /* F5:1142 */
+                int shade = jint(val * 255.0);                                                  /* F1:351 */
+                shade = jmaxi(jmini(shade, 255), 0);                                            /* F1:352 */
+                if (variant == IFL_F4_SOLID_BOUNDARIES && d.cell[i] == CELL_SOLID) shade = 0;   /* F4:678 */
+                rgb[3 * i] = shade; rgb[3 * i + 1] = shade; rgb[3 * i + 2] = shade;
+            }
+            return;
+        }
+        const size_t fw = renderHeat ? 2 * (size_t)w : (size_t)w;
+        for (int y = 0; y < h; y++) {
+            for (int x = 0; x < w; x++) {
+                const size_t idxl = 3 * ((size_t)x + (size_t)y * fw);                            /* F6:1263 */
+                const size_t idxr = renderHeat ? 3 * ((size_t)x + (size_t)y * fw + w) : idxl;    /* F6:1264,1266 */
+                double volume = d.vol(x, y);
+                double shade = (1.0 - d.getSrc(x, y)) * volume;                                  /* F6:1271 */
+                shade = jmin(jmax(shade, 0.0), 1.0);
+                rgb[idxr + 0] = jint(shade * 255.0);
+                rgb[idxr + 1] = jint(shade * 255.0);
+                rgb[idxr + 2] = jint(shade * 255.0);
+                if (variant == IFL_F8_FLIP && d.cell[(size_t)x + (size_t)y * w] == CELL_EMPTY) { /* F8:1444 */
+                    rgb[idxr] = 0xFF;
+                    rgb[idxr + 1] = rgb[idxr + 2] = 0;
+                }
+                if (renderHeat) {
+                    double tt;
+                    if (variant == IFL_F8_FLIP) tt = std::fabs(jfloat(t.getSrc(x, y)) - cfg.t_ambient) / 70.0;   /* F8:1450 */
+                    else tt = (t.getSrc(x, y) - cfg.t_ambient) / 700.0;                          /* F6:1279 */
+                    tt = jmin(jmax(tt, 0.0), 1.0);
+                    double r = 1.0 + volume * (jmin(tt * 4.0, 1.0) - 1.0);
+                    double g = 1.0 + volume * (jmin(tt * 2.0, 1.0) - 1.0);
+                    double b = 1.0 + volume * (jmax(jmin(tt * 4.0 - 3.0, 1.0), 0.0) - 1.0);
+                    rgb[idxl + 0] = jint(r * 255.0);
+                    rgb[idxl + 1] = jint(g * 255.0);
+                    rgb[idxl + 2] = jint(b * 255.0);
+                }
+            }
+        }
+    }
+    /* the text the reference writes (F1:344-357 / F6:1255-1299): note `i % _w` with the SOLVER width */
+    std::string ppmText(bool renderHeat) const {
+        const size_t pixels = (size_t)(renderHeat ? 2 * w : w) * h;
+        std::vector<int32_t> rgb(3 * pixels);
+        toImage(renderHeat, rgb.data());
+        std::string out = "P3\n" + std::to_string(renderHeat ? w * 2 : w) + " " + std::to_string(h) + "\n" + std::to_string(255) + "\n";
+        for (size_t i = 0; i < pixels; i++) {
+            out += std::to_string(rgb[3 * i]) + " " + std::to_string(rgb[3 * i + 1]) + " " + std::to_string(rgb[3 * i + 2]) + " ";
+            if (i % (size_t)w == 0) out += "\n";
+        }
+        return out;
+    }
+
     Quantity* quantity(int q) { return q == 0 ? &d : q == 1 ? &t : q == 2 ? &u : &v; }
 
     std::vector<double>* field(int f) {
@@ -1422,6 +1480,28 @@ int ifo_run_stage(void* h, int stage, double dt, ifl_step_status* st) {
     return IFL_OK;
 }
 int ifo_max_timestep(void* h, double* out) { *out = ((Solver*)h)->maxTimestep(); return IFL_OK; }
+int ifo_image_size(void* h, int render_heat, size_t* pixels) {
+    Solver* s = (Solver*)h;
+    if (render_heat && s->variant < IFL_F6_HEAT) return IFL_ERR_INVALID;
+    *pixels = (size_t)(render_heat ? 2 * s->w : s->w) * s->h;
+    return IFL_OK;
+}
+int ifo_to_image(void* h, int render_heat, int32_t* rgb, size_t pixels) {
+    size_t want = 0;
+    if (ifo_image_size(h, render_heat, &want) != IFL_OK || want != pixels) return IFL_ERR_INVALID;
+    ((Solver*)h)->toImage(render_heat != 0, rgb);
+    return IFL_OK;
+}
+int ifo_write_ppm(void* h, const char* path, int render_heat) {
+    size_t want = 0;
+    if (ifo_image_size(h, render_heat, &want) != IFL_OK) return IFL_ERR_INVALID;
+    std::string text = ((Solver*)h)->ppmText(render_heat != 0);
+    FILE* f = fopen(path, "wb");
+    if (!f) return IFL_ERR_INVALID;
+    bool ok = fwrite(text.data(), 1, text.size(), f) == text.size();
+    fclose(f);
+    return ok ? IFL_OK : IFL_ERR_INVALID;
+}
 
 int ifo_field_size(void* h, int f, size_t* count) {
     Solver* s = (Solver*)h;

@@ -36,6 +36,9 @@ def _load(abi):
         "ifo_run_steps": (C.c_int, [C.c_void_p, C.c_int32, C.c_double] + [C.c_double] * 8 + [C.POINTER(abi.StepStatus)]),
         "ifo_run_stage": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.POINTER(abi.StepStatus)]),
         "ifo_max_timestep": (C.c_int, [C.c_void_p, dp]),
+        "ifo_image_size": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_size_t)]),
+        "ifo_to_image": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_size_t]),
+        "ifo_write_ppm": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
         "ifo_field_size": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_size_t)]),
         "ifo_read_field": (C.c_int, [C.c_void_p, C.c_int32, dp, C.c_size_t]),
         "ifo_write_field": (C.c_int, [C.c_void_p, C.c_int32, dp, C.c_size_t]),
@@ -109,6 +112,18 @@ class OracleSolver:
         out = C.c_double()
         assert self.lib.ifo_max_timestep(self.h, C.byref(out)) == 0
         return out.value
+
+    def to_image(self, destination, render_heat=False):
+        rc = self.lib.ifo_write_ppm(self.h, os.fsencode(destination), 1 if render_heat else 0)
+        assert rc == 0, rc
+
+    def image(self, render_heat=False):
+        n = C.c_size_t()
+        assert self.lib.ifo_image_size(self.h, 1 if render_heat else 0, C.byref(n)) == 0
+        out = np.empty(3 * n.value, dtype=np.int32)
+        rc = self.lib.ifo_to_image(self.h, 1 if render_heat else 0, out.ctypes.data_as(C.POINTER(C.c_int32)), n.value)
+        assert rc == 0, rc
+        return out.reshape(self.cfg.h, -1, 3)
 
     def field_size(self, name):
         n = C.c_size_t()

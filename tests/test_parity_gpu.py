@@ -178,3 +178,37 @@ def test_projection_property_large_grid(ifl):
     r2 = g.read("r")
     if not st2["exceeded_budget"]:
         assert np.max(np.abs(r2)) < 1e-3
+
+
+@pytest.mark.parametrize("w,h", [(100, 70), (33, 65)])
+def test_matvec_general_and_position_derived_matrix_agree(ifl, oracle_cls, w, h):
+    """F3's mat-vec re-derives aDiag / aPlusX / aPlusY from the grid position (matrixVectorProduct F3:544 on the matrix
+    of F3:435); writing a matrix array switches the solver back to the kernel that reads them.  Both must give the
+    oracle's bits."""
+    g, o = pair(ifl, oracle_cls, ifl.abi.F3_CONJUGATE_GRADIENTS, w, h)
+    svec = np.random.default_rng(7 * w + h).normal(size=w * h)
+    for s in (g, o):
+        s.run_stage("build_matrix", scenes.DT)
+        s.write("s", svec)
+        s.run_stage("matvec")
+    derived = g.read("z")
+    assert np.array_equal(derived, o.read("z"))
+    g.write("adiag", g.read("adiag"))               # same values: only the kernel choice changes
+    g.run_stage("matvec")
+    assert np.array_equal(g.read("z"), derived)
+
+
+@pytest.mark.parametrize("limit", [1, 7])
+def test_pcg_iteration_limit_keeps_the_last_p_update(ifl, oracle_cls, limit):
+    """project() leaves the loop on its iteration limit (F3:603, 629): the p += alpha*s of the last iteration (F3:607) is
+    applied by the s-update kernel, the one of a converging iteration by the trailing k_update_p -- both bit-exact."""
+    flags = ifl.abi.FLAG_SEQUENTIAL_REDUCTIONS
+    g, o = pair(ifl, oracle_cls, ifl.abi.F3_CONJUGATE_GRADIENTS, 100, 70, flags=flags, solver_limit=limit)
+    for step in range(2):
+        for s in (g, o):
+            s.add_inflow(*scenes.F3_INFLOW)
+        sg, so = g.update(scenes.DT), o.update(scenes.DT)
+        assert sg["iterations_pressure"] == so["iterations_pressure"]
+        assert sg["exceeded_budget"] == 1
+        assert sg["exceeded_budget"] == so["exceeded_budget"]
+        assert_fields_equal(g, o, ["p", "r", "d", "u", "v"])
