@@ -48,6 +48,29 @@ def test_oracle_ppm_known_answer_heat(ifl, oracle_cls, tmp_path):
     assert o5.lib.ifo_image_size(o5.h, 1, __import__("ctypes").byref(__import__("ctypes").c_size_t())) != 0   # renderHeat needs F6+
 
 
+def test_oracle_image_solid_and_volume_variants(ifl, oracle_cls):
+    """F4:678 paints SOLID cells black; F5:1142 weights the shade with the fluid volume of the cell."""
+    abi = ifl.abi
+    w, h = 48, 32
+    for variant, spec in ((abi.F4_SOLID_BOUNDARIES, scenes.F4_BODIES), (abi.F5_CURVED_BOUNDARIES, scenes.F5_BODIES)):
+        o = oracle_cls(abi, abi.default_config(variant, w, h))
+        o.set_bodies(scenes.make_bodies(ifl, spec))
+        o.run_stage("fill_solid_fields")
+        dens = np.linspace(0.0, 0.9, w * h)
+        o.write("d", dens)
+        shade = o.image()[:, :, 0].ravel()
+        if variant == abi.F4_SOLID_BOUNDARIES:
+            solid = o.read("cell_d") == 1.0
+            assert solid.any() and not solid.all()
+            assert np.all(shade[solid] == 0)
+            assert np.array_equal(shade[~solid], ((1.0 - dens[~solid]) * 255.0).astype(np.int64))
+        else:
+            vol = o.read("volume_d")
+            assert (vol < 1.0).any() and (vol > 0.0).any()
+            assert np.array_equal(shade, np.clip(((1.0 - dens) * vol * 255.0).astype(np.int64), 0, 255))
+        o.close()
+
+
 def _frames_equal(g, o, tmp_path, render_heat, tag):
     assert np.array_equal(g.image(render_heat), o.image(render_heat)), tag
     pg, po = tmp_path / f"{tag}_gpu.ppm", tmp_path / f"{tag}_ref.ppm"
