@@ -1,0 +1,117 @@
+/* Panama FFM binding of include/incfluid_b200.h for the reference's physics.* classes (INTEGRATION.md, section 2).
+ * NOT compiled in this repository's image (no JDK here): build with JDK 22+,
+ *   javac -d out java/physics/b200/IncFluidB200.java ; java --enable-native-access=ALL-UNNAMED ...
+ * tests/test_abi.py keeps this file and the listing in INTEGRATION.md identical. */
+package physics.b200;
+
+import java.lang.foreign.*;
+import java.lang.invoke.MethodHandle;
+import static java.lang.foreign.ValueLayout.*;
+
+/** Thin binding of include/incfluid_b200.h.  One instance = one ifl_solver handle (not thread safe,
+ *  like the reference).  Field layouts mirror `struct ifl_config` / `ifl_step_status` byte for byte. */
+public final class IncFluidB200 implements AutoCloseable {
+    private static final Linker LINKER = Linker.nativeLinker();
+    private static final SymbolLookup LIB = SymbolLookup.libraryLookup("libincfluid_b200.so", Arena.global());
+
+    private static MethodHandle fn(String name, FunctionDescriptor d) {
+        return LINKER.downcallHandle(LIB.find(name).orElseThrow(), d);
+    }
+    // int ifl_default_config(ifl_config*, int32 variant, int32 w, int32 h)
+    private static final MethodHandle DEFAULT_CONFIG = fn("ifl_default_config", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT));
+    // int ifl_create(const ifl_config*, ifl_solver**)          -- new FluidSolver(...)  F1:262 F3:339 F4:594 F6:763
+    private static final MethodHandle CREATE = fn("ifl_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle DESTROY = fn("ifl_destroy", FunctionDescriptor.ofVoid(ADDRESS));
+    // int ifl_add_inflow(s, x, y, w, h, d, t, u, v)            -- FluidSolver.addInflow  F1:298 F6:1233
+    private static final MethodHandle ADD_INFLOW = fn("ifl_add_inflow", FunctionDescriptor.of(JAVA_INT, ADDRESS,
+            JAVA_DOUBLE, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_DOUBLE));
+    // int ifl_update(s, timestep, ifl_step_status*)            -- FluidSolver.update     F1:276 ... F8:1306
+    private static final MethodHandle UPDATE = fn("ifl_update", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_DOUBLE, ADDRESS));
+    // int ifl_max_timestep(s, double*)                         -- FluidSolver.maxTimestep F1:309
+    private static final MethodHandle MAX_TIMESTEP = fn("ifl_max_timestep", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    // int ifl_set_bodies(s, const ifl_body*, int32 count)      -- the shared `bodies` list F4:594
+    private static final MethodHandle SET_BODIES = fn("ifl_set_bodies", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+    // int ifl_read_field / ifl_write_field(s, int32 field, double*, size_t count)   -- solver._d._src[i]  F1:351
+    private static final MethodHandle READ_FIELD = fn("ifl_read_field", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG));
+    private static final MethodHandle WRITE_FIELD = fn("ifl_write_field", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG));
+    // int ifl_write_ppm(s, const char* path, int32 render_heat) -- FluidSolver.toImage F1:341 ... F6:1250, F8:1417
+    private static final MethodHandle WRITE_PPM = fn("ifl_write_ppm", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+    private static final MethodHandle LAST_ERROR = fn("ifl_last_error", FunctionDescriptor.of(ADDRESS));
+
+    /** struct ifl_config (include/incfluid_b200.h) */
+    static final StructLayout CONFIG = MemoryLayout.structLayout(
+        JAVA_INT.withName("abi_version"), JAVA_INT.withName("variant"), JAVA_INT.withName("w"), JAVA_INT.withName("h"),
+        JAVA_DOUBLE.withName("density"), JAVA_DOUBLE.withName("density_soot"), JAVA_DOUBLE.withName("diffusion"),
+        JAVA_DOUBLE.withName("t_ambient"), JAVA_DOUBLE.withName("gravity"), JAVA_DOUBLE.withName("flip_alpha"),
+        JAVA_DOUBLE.withName("tolerance"), JAVA_INT.withName("solver_limit"), MemoryLayout.paddingLayout(4),
+        JAVA_DOUBLE.withName("mic_tau"), JAVA_DOUBLE.withName("mic_sigma"),
+        JAVA_INT.withName("particles_avg_per_cell"), JAVA_INT.withName("particles_max_per_cell"),
+        JAVA_INT.withName("particles_min_per_cell"), MemoryLayout.paddingLayout(4),
+        JAVA_LONG.withName("rng_seed"), JAVA_INT.withName("device"), JAVA_INT.withName("rank"),
+        JAVA_INT.withName("world_size"), JAVA_INT.withName("flags"),
+        MemoryLayout.sequenceLayout(128, JAVA_BYTE).withName("comm_id"));
+    /** struct ifl_step_status */
+    static final StructLayout STATUS = MemoryLayout.structLayout(
+        JAVA_INT.withName("iterations_pressure"), JAVA_INT.withName("iterations_heat"),
+        JAVA_DOUBLE.withName("residual_pressure"), JAVA_DOUBLE.withName("residual_heat"),
+        JAVA_INT.withName("exceeded_budget"), JAVA_INT.withName("nan_residual"),
+        JAVA_INT.withName("particle_count"), JAVA_INT.withName("reserved"));
+
+    private final Arena arena = Arena.ofConfined();
+    private final MemorySegment handle;
+    private final MemorySegment status = arena.allocate(STATUS);
+
+    public IncFluidB200(int variant, int w, int h, double density) {
+        try {
+            MemorySegment cfg = arena.allocate(CONFIG);
+            check((int) DEFAULT_CONFIG.invokeExact(cfg, variant, w, h));
+            cfg.set(JAVA_DOUBLE, CONFIG.byteOffset(MemoryLayout.PathElement.groupElement("density")), density);
+            MemorySegment out = arena.allocate(ADDRESS);
+            check((int) CREATE.invokeExact(cfg, out));
+            handle = out.get(ADDRESS, 0);
+        } catch (Throwable t) { throw wrap(t); }
+    }
+    public void addInflow(double x, double y, double w, double h, double d, double t, double u, double v) {
+        try { check((int) ADD_INFLOW.invokeExact(handle, x, y, w, h, d, t, u, v)); } catch (Throwable e) { throw wrap(e); }
+    }
+    /** returns the iteration count the reference only logs (F3:613,628) */
+    public int update(double timestep) {
+        try {
+            int rc = (int) UPDATE.invokeExact(handle, timestep, status);
+            if (rc == 4 /* IFL_ERR_NAN: the reference calls System.exit(-1) here, F3:616-619 */) System.exit(-1);
+            check(rc);
+            return status.get(JAVA_INT, 0);
+        } catch (Throwable e) { throw wrap(e); }
+    }
+    public double maxTimestep() {
+        try {
+            MemorySegment out = arena.allocate(JAVA_DOUBLE);
+            check((int) MAX_TIMESTEP.invokeExact(handle, out));
+            return out.get(JAVA_DOUBLE, 0);
+        } catch (Throwable e) { throw wrap(e); }
+    }
+    /** the reference's PPM frame, byte for byte, rendered from the device fields (toImage F1:341 / F6:1250 / F8:1417) */
+    public void toImage(java.io.File destination, boolean renderHeat) {
+        try (Arena a = Arena.ofConfined()) {
+            check((int) WRITE_PPM.invokeExact(handle, a.allocateFrom(destination.getPath()), renderHeat ? 1 : 0));
+        } catch (Throwable e) { throw wrap(e); }
+    }
+    /** copy a device field into a Java array (field ids: enum ifl_field; 0 = _d._src, 2 = _u._src, 3 = _v._src) */
+    public void readField(int field, double[] dst) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment buf = a.allocate(JAVA_DOUBLE, dst.length);
+            check((int) READ_FIELD.invokeExact(handle, field, buf, (long) dst.length));
+            MemorySegment.copy(buf, JAVA_DOUBLE, 0, dst, 0, dst.length);
+        } catch (Throwable e) { throw wrap(e); }
+    }
+    @Override public void close() {
+        try { DESTROY.invokeExact(handle); } catch (Throwable e) { throw wrap(e); } finally { arena.close(); }
+    }
+    private static void check(int rc) throws Throwable {
+        if (rc != 0) {
+            MemorySegment msg = ((MemorySegment) LAST_ERROR.invokeExact()).reinterpret(512);
+            throw new IllegalStateException("ifl status " + rc + ": " + msg.getString(0));
+        }
+    }
+    private static RuntimeException wrap(Throwable t) { return t instanceof RuntimeException r ? r : new RuntimeException(t); }
+}
