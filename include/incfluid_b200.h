@@ -274,10 +274,10 @@ int ifl_last_timing(ifl_solver* s, double out_ms[3]);
  * since the last ifl_set_profiling(s, 1). */
 typedef enum ifl_kernel {
     IFL_KERNEL_MATVEC_DOT = 0,    /* matrixVectorProduct + dotProduct        F3:544 F3:532 */
-    IFL_KERNEL_UPDATE_PR = 1,     /* 2x scaledAdd + infinityNorm             F3:570 F3:579 */
+    IFL_KERNEL_UPDATE_PR = 1,     /* scaledAdd(r) + infinityNorm             F3:608 F3:579 */
     IFL_KERNEL_PRECON_FWD = 2,    /* applyPreconditioner, forward sweep      F3:496-507   */
     IFL_KERNEL_PRECON_BWD = 3,    /* applyPreconditioner, backward sweep + dotProduct F3:509-521 */
-    IFL_KERNEL_UPDATE_S = 4,      /* scaledAdd(s, z, s, beta)                F3:626 */
+    IFL_KERNEL_UPDATE_S = 4,      /* scaledAdd(p) F3:607 (deferred) + scaledAdd(s, z, s, beta) F3:626 */
     IFL_KERNEL_GS_SWEEP = 5,      /* one Gauss-Seidel sweep                  F1:383-417 */
     IFL_KERNEL_COUNT = 6
 } ifl_kernel;
