@@ -43,6 +43,10 @@ def run_case(abi, variant, spec, rect, kw, solver_factory):
             out["particle_" + k] = v
     for n in ["d", "u", "v", "p"] + (["t"] if variant >= abi.F6_HEAT else []):
         out[n] = s.read(n)
+    # the frame toImage would write after the last step (F1:341 ... F8:1417), with the heat panel where it exists
+    out["image"] = s.image(False)
+    if variant >= abi.F6_HEAT:
+        out["image_heat"] = s.image(True)
     return out
 
 
