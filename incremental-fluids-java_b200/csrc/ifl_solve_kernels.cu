@@ -704,28 +704,14 @@ __device__ __forceinline__ void ring_wait(unsigned slot_addr, double (&v)[SKB], 
 
 /* One macro-step of one lane: the SKB cells x = (m - lane)*SKB + j of its row, in the sweep's direction.  The left/right
  * neighbour is the previous cell of the same lane (a register); the upper/lower neighbours `dn` are the SKB results of
- * the adjacent lane's PREVIOUS macro-step.  Each result is shuffled to the adjacent lane as soon as it exists (dn_next),
- * so the shuffle latency overlaps the rest of the lane's own dependency chain; `edge_next` is what the edge lane
- * injects into that rotation (the neighbouring strip's values for the NEXT macro-step), nullptr = no early shuffle. */
-/* one 16-byte store into a (possibly remote) shared-memory ring slot (generic address of mapped shared memory) */
-__device__ __forceinline__ void st_ring_pair(double* slot, double a, double b) {
-    static_assert(SKB == 2, "one 16-byte store per macro-step");
-#ifdef IFL_SW_ST128                         /* measured slower than two 8-byte stores */
-    asm volatile("st.v2.f64 [%0], {%1, %2};" ::"l"(slot), "d"(a), "d"(b) : "memory");
-#else
-    slot[0] = a; slot[1] = b;
-#endif
-}
-/* OUTRING: po is a 16-byte aligned slot (the next strip's ring slot for the edge lane, a scratch slot for the others)
- * and takes one vector store.  `edge_ready()` is called after the first cell's arithmetic has been issued and before the
- * incoming edge values are first used: a wait placed there hides behind the latency of that cell's last operation, and
- * the code between two such points (second cell of this macro-step, first cell of the next) is one basic block. */
-#ifndef IFL_SW_SHFL
-/* Lane-to-lane hand-over through shared memory instead of shuffles: every lane stores its result into its own exchange
- * slot (the edge lane: straight into the next strip's ring slot) and loads the adjacent lane's (the lane at the incoming
- * edge: this strip's ring slot, or a zero slot).  One 8-byte store and one 8-byte load per cell replace two selects, two
- * shuffles and the register moves that pair their halves up again, and the loaded values land in an aligned register
- * pair.  xw / xr: this macro-step's store slot (generic address) and load slot (shared address). */
+ * the adjacent lane's PREVIOUS macro-step.
+ * Lane-to-lane hand-over goes through shared memory: every lane stores each result, as soon as it exists, into its own
+ * exchange slot (the lane at the outgoing edge of a ring-out strip: straight into the next strip's ring slot) and loads
+ * the adjacent lane's slot (the lane at the incoming edge: this strip's ring slot, or a zero slot) -- one 8-byte store and
+ * one 8-byte load per cell, and the loaded values land in an aligned register pair.  xw / xr: this macro-step's store
+ * slot (generic address: it may be a mapped, remote ring slot) and load slot (shared address).  `edge_next`: incoming
+ * edge values held in registers (global boundary row), injected by the lane at the incoming edge; nullptr = none.
+ * OUTRING: the outgoing edge went to a ring through xw; otherwise it is also stored at po (global boundary row). */
 __device__ __forceinline__ void xchg_store(double* slot, double v) {
     asm volatile("st.f64 [%0], %1;" ::"l"(slot), "d"(v) : "memory");
 }
@@ -734,13 +720,11 @@ __device__ __forceinline__ double xchg_load(unsigned addr) {
     asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
     return v;
 }
-#endif
-template <int DIR, bool WITH_DOT, bool CHECKED, bool MASKED, bool OUTRING, class Ready>
+template <int DIR, bool WITH_DOT, bool CHECKED, bool MASKED, bool OUTRING>
 __device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB], const double* edge_next, const int m,
-                                           const int lane, const int srclane, const bool is_out, const int w, const bool yok,
+                                           const int lane, const bool is_out, const int w, const bool yok,
                                            double* pd, double* po, double* dummy, double (&dprev)[SKB], double& cxprev,
-                                           double& acc, Ready&& edge_ready, double* xw, const unsigned xr,
-                                           const bool is_in_feed, double& acc_b) {
+                                           double& acc, double* xw, const unsigned xr, const bool is_in_feed) {
     double dl = DIR > 0 ? dprev[SKB - 1] : dprev[0];
     bool fl[SKB];
     double dnn[SKB];
@@ -760,30 +744,13 @@ __device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB],
         double d = v * pr;
         fl[j] = MASKED ? (pr == pr) : true;              /* NaN precon tags a non-fluid cell (k_precon_coeffs) */
         if (MASKED) d = fl[j] ? d : 0.0;                 /* skipped cell: dst stays, neighbours see +0.0 */
-#ifdef IFL_SW_MIDCHECK                      /* measured slower: the compiler's schedule of the two half-steps is worse */
-        if (jj == 0) edge_ready();
-#endif
-#ifndef IFL_SW_SHFL
         /* store, then load, in program order: the warp is converged here and its shared-memory accesses are performed in
          * order, so the load of lane l sees the store of lane l-1 of the same macro-step */
         xchg_store(xw + j, d);                           /* hand the result to the adjacent lane right away */
-#ifdef IFL_SW_XCHG_SYNC
-        __syncwarp();
-#endif
         dnn[j] = xchg_load(xr + (unsigned)(j * sizeof(double)));
         if (edge_next != nullptr) dnn[j] = is_in_feed ? edge_next[j] : dnn[j];      /* edge values held in registers */
-#else
-        if (edge_next != nullptr) {                      /* hand the result to the adjacent lane right away */
-            const double give = is_out ? edge_next[j] : d;
-            dnn[j] = __shfl_sync(0xffffffffu, give, srclane);
-        }
-#endif
         /* inactive lanes hold +0.0 and rr is zero in the padding: adding them is exact */
-#ifdef IFL_SW_ACC2
-        if (WITH_DOT) { if (j == 0) acc += d * op.rr[j]; else acc_b += d * op.rr[j]; }   /* one partial sum per sub-column */
-#else
         if (WITH_DOT) acc += d * op.rr[j];
-#endif
         dprev[j] = d;
         dl = d;
     }
@@ -796,9 +763,6 @@ __device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB],
             st_if(yok && inx && fl[j], pd + j, dprev[j]);
             if (!OUTRING) st_if(inx && is_out, po + j, dprev[j]);           /* the edge value is published for every column */
         }
-#ifdef IFL_SW_SHFL
-        if (OUTRING) st_ring_pair(po, dprev[0], dprev[SKB - 1]);
-#endif
     } else {
         /* interior block: only rows y >= h are inactive; they hold +0.0, and storing +0.0 into
          * their (zero) padding cells keeps the padding zero -- no predicate needed.  Lanes that have nothing to
@@ -810,25 +774,14 @@ __device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB],
         } else {
             store_cells(pd, dprev);
         }
-#ifdef IFL_SW_SHFL
-        if (OUTRING) st_ring_pair(po, dprev[0], dprev[SKB - 1]);
-#else
         if (OUTRING) {}
-#endif
         else {
 #pragma unroll
             for (int j = 0; j < SKB; j++) po[j] = dprev[j];   /* po: the edge lane's slot, the dummy slot for the others */
         }
     }
-#ifndef IFL_SW_SHFL
 #pragma unroll
     for (int j = 0; j < SKB; j++) dn[j] = dnn[j];
-#else
-    if (edge_next != nullptr) {
-#pragma unroll
-        for (int j = 0; j < SKB; j++) dn[j] = dnn[j];
-    }
-#endif
 }
 
 /* applyPreconditioner F3:495: DIR=+1 forward substitution (first loop nest), DIR=-1
@@ -861,11 +814,9 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     __shared__ volatile int s_credit[SW_WARPS];          /* steps of MINE the strip after me has consumed */
     __shared__ __align__(16) double s_dummy[SW_WARPS][32][SKB];       /* where lanes with nothing to publish store */
     __shared__ __align__(16) double s_scratch[SW_WARPS][SW_FG * SKB]; /* ... when the edge row goes to a ring (one block of slots) */
-#ifndef IFL_SW_SHFL
     constexpr int XS = SW_FG * SKB + 1;                               /* doubles per lane: one slot per macro-step of a block, */
     __shared__ __align__(16) double s_xchg[SW_WARPS][32 * XS];        /* odd stride (conflict-free 8-byte accesses)            */
     __shared__ __align__(16) double s_zero[SW_FG * SKB];              /* what the lane at an edge without a neighbour reads     */
-#endif
     __shared__ int s_ticket;
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
@@ -881,10 +832,8 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
         wf_smem + (size_t)SW_WARPS * S * STAGE * sizeof(double)) + warp * 2 * S;
     unsigned long long* bar_empty = bar_full + S;
     if (!loader) {
-#ifndef IFL_SW_SHFL
         for (int i = lane; i < 32 * XS; i += 32) s_xchg[warp][i] = 0.0;
         if (warp == 0 && lane < SW_FG * SKB) s_zero[lane] = 0.0;
-#endif
         for (int i = lane; i < SW_RB * SKB; i += 32) s_inbox[warp][i] = sentinel();
         if (lane == 0) {
             s_credit[warp] = 0;
@@ -908,7 +857,7 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     const int cw = (w + SKB - 1) / SKB;                               /* column blocks per row */
     const int nblk = (cw + 31 + UB - 1) / UB;
     const int ntile = nblk * (UB / U);
-    double acc = 0.0, acc_b = 0.0;
+    double acc = 0.0;
     if (live && loader) {
         if (lane == 0) {
             /* running pointers / shared addresses: this loop has to issue a tile faster than the strip warp consumes one */
@@ -944,7 +893,6 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
         const bool yok = y < g.h;
         const int tfirst = DIR > 0 ? 0 : nblk * UB - 1;
         const bool has_prev = DIR > 0 ? (k > 0) : (k < g.nstrips - 1);
-        const int srclane = (lane - DIR) & 31;                            /* rotation: E_IN reads from E_OUT */
         const bool is_out = lane == E_OUT;
         const bool lane0 = lane == 0;
 
@@ -955,11 +903,7 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
         feed.src = in_ring ? &s_inbox[warp][0] : (has_prev ? bnd + (long long)(k - DIR) * w : nullptr);
         feed.ring = in_ring ? &s_inbox[warp][0] : nullptr;
         feed.w = w;
-#ifndef IFL_SW_SHFL
         feed.feeder = lane == E_IN && feed.mode != 0;                     /* the lane that consumes the edge values */
-#else
-        feed.feeder = is_out && feed.mode != 0;                           /* the lane that injects them into the rotation */
-#endif
         const bool use_feed = feed.mode != 0;                             /* warp uniform */
         const bool ring_feed = feed.mode == 2;
         /* outgoing edge: the next strip's ring (mapped shared memory of its block) unless I am the last strip of
@@ -974,12 +918,10 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
         const bool pub_credit = lane0 && credit_of_prev != nullptr;
         /* shared::cluster addresses of the next strip's ring and of my scratch slots */
         double* const oscratch = &s_scratch[warp][0];
-#ifndef IFL_SW_SHFL
         const bool is_in = lane == E_IN;
         double* const xw_own = &s_xchg[warp][lane * XS];
         const unsigned xr_nb = pin_u32(smem_u32(&s_xchg[warp][((lane - DIR) & 31) * XS]));
         const unsigned xr_zero = pin_u32(smem_u32(&s_zero[0]));
-#endif
         /* per macro-step the edge lane's store moves by +1 slot group in a ring, by DIR column blocks in a global row */
 
         double* pdst = dst + (long long)k * g.ss + ((long long)tfirst * 32 + lane) * SKB;
@@ -1048,7 +990,6 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
             const unsigned in_next = inbox0 + (unsigned)(((sc0 + UB + 32) & (SW_RB - 1)) * SKB * (int)sizeof(double));
             const int cin0 = t0 - E_IN;                                    /* column block the edge lane needs at step 0 */
             double ecar[SKB];
-#ifndef IFL_SW_SHFL
             /* the lane at the incoming edge reads the ring slots of the block's steps 1..8 (or zeros); values from a global
              * boundary row are in registers (ecur) and replace what it read */
             const bool is_in_feed = is_in && use_feed && !RINGFEED;
@@ -1057,16 +998,6 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
 #pragma unroll
                 for (int j = 0; j < SKB; j++) dn[j] = is_in_feed ? ecur[j] : dn[j];
             }
-#else
-            const bool is_in_feed = false; const unsigned xr_b = 0;
-            if (!RINGFEED) {
-#pragma unroll
-                for (int j = 0; j < SKB; j++) {
-                    const double give = is_out ? ecur[j] : dprev[j];
-                    dn[j] = __shfl_sync(0xffffffffu, give, srclane);
-                }
-            }
-#endif
 #pragma unroll
             for (int s = 0; s < UB; s++) {
                 const int r = (s + 1) % U;
@@ -1077,9 +1008,6 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
                         const unsigned a = in_rest + (unsigned)(s * SKB * (int)sizeof(double));
                         double (&e)[SKB] = epk[(s + 1) & 1];
                         ring_wait(a, e, true, true IFL_TW_PASS);
-#ifdef IFL_SW_SHFL
-                        ring_rearm(a, sent_hi);
-#endif
                         if (CHECKED) {                                      /* the producer's padding cells hold +0.0 anyway */
                             const int c = cin0 + DIR * (s + 1);
 #pragma unroll
@@ -1088,9 +1016,7 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
                         ring_peek(s + 1 < UB ? a + (unsigned)(SKB * sizeof(double)) : in_next, epk[s & 1]);
                     }
                 };
-#ifndef IFL_SW_MIDCHECK
                 edge_ready();
-#endif
                 if (!RINGFEED && s + 1 < UB) {
 #pragma unroll
                     for (int j = 0; j < SKB; j++) ecar[j] = ecur[(s + 1) * SKB + j];
@@ -1106,14 +1032,12 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
                 }
                 load_step<DIR, WITH_DOT>(ops[(s + 1) & 1], tile, r);
                 const double* en = RINGFEED ? &epk[(s + 1) & 1][0] : (s + 1 < UB ? &ecar[0] : nullptr);
-                sweep_step<DIR, WITH_DOT, CHECKED, MASKED, OUTRING>(ops[s & 1], dn, en, t0 + DIR * s, lane, srclane, is_out, w, yok,
+                sweep_step<DIR, WITH_DOT, CHECKED, MASKED, OUTRING>(ops[s & 1], dn, en, t0 + DIR * s, lane, is_out, w, yok,
                                                            pdst + DIR * s * (32 * SKB),
                                                            po_lane + (OUTRING ? SKB : ostep_l) * s, dummy,
-                                                           dprev, cxprev, acc, edge_ready, xw_b + s * SKB,
-                                                           xr_b + (unsigned)(s * SKB * (int)sizeof(double)), is_in_feed, acc_b);
-#ifndef IFL_SW_SHFL
+                                                           dprev, cxprev, acc, xw_b + s * SKB,
+                                                           xr_b + (unsigned)(s * SKB * (int)sizeof(double)), is_in_feed);
                 if (RINGFEED) ring_rearm(in_rest + (unsigned)(s * SKB * (int)sizeof(double)), sent_hi);   /* after it was read */
-#endif
                 /* every row of the finished tile is in registers (the loads are warp-wide instructions issued, in
                  * order, before this arrive): hand the stage back to the loader warp */
                 if (r == 0) mbar_arrive_if(lane0, done_bar);
@@ -1148,12 +1072,7 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
             }
 #pragma unroll
             for (int j = 0; j < SKB; j++) {
-#ifndef IFL_SW_SHFL
                 dn[j] = is_in ? e0[j] : 0.0;
-#else
-                const double give = is_out ? e0[j] : 0.0;
-                dn[j] = __shfl_sync(0xffffffffu, give, srclane);
-#endif
             }
             ring_peek(inbox0 + (unsigned)(32 * SKB * (int)sizeof(double)), epk[1]);            /* macro-step 1 */
         }
@@ -1168,11 +1087,7 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
 #endif
                 if ((b & 1) == 0) credit_wait(sc0 + 2 * UB - 1);
                 double* po_lane = (is_out && b >= 3) ? out_base + (sc0 & (SW_RB - 1)) * SKB : oscratch;
-#ifndef IFL_SW_SHFL
                 double* xw_b = (is_out && b >= 3) ? po_lane : xw_own;   /* the edge lane's results go straight into the next ring */
-#else
-                double* xw_b = nullptr;
-#endif
                 if (ring_feed && b <= last_ring_block) run_block(F, T, T, t0, sc0, eb0, po_lane, 0, xw_b);
                 else                                   run_block(F, F, T, t0, sc0, eb0, po_lane, 0, xw_b);
                 pdst += DIR * UB * (32 * SKB);
@@ -1201,21 +1116,13 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
                 if (out_ring) {
                     /* ring out, global row in: plain arithmetic and stores in every block (see above) */
                     double* po_lane = (is_out && b >= 3) ? out_base + (sc0 & (SW_RB - 1)) * SKB : oscratch;
-#ifndef IFL_SW_SHFL
                     double* xw_b = (is_out && b >= 3) ? po_lane : xw_own;
-#else
-                    double* xw_b = nullptr;
-#endif
                     run_block(F, F, T, t0, sc0, ecur, po_lane, 0, xw_b);
                 } else {
                     /* global row out: per-cell predicates in the first and last blocks */
                     double* po_lane = is_out ? out_base + (t0 - E_OUT) * SKB : dummy;
                     const int ostep_l = is_out ? DIR * SKB : 0;
-#ifndef IFL_SW_SHFL
                     double* xw_b = xw_own;
-#else
-                    double* xw_b = nullptr;
-#endif
                     if (rf) {
                         if (interior) run_block(F, T, F, t0, sc0, ecur, po_lane, ostep_l, xw_b);
                         else          run_block(T, T, F, t0, sc0, ecur, po_lane, ostep_l, xw_b);
@@ -1251,7 +1158,7 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
         }
     }
     if (WITH_DOT && live && !loader) {
-        double ws = warp_sum(acc + acc_b);
+        double ws = warp_sum(acc);
         if (lane == 0) {
             strip_part[k] = ws;
             __threadfence();
