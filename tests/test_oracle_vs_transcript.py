@@ -1,0 +1,62 @@
+"""The C++ oracle against an independent, literal Python transcription of ExplicitFluid1matrixless.java
+(tests/java_f1_transcript.py): whole timesteps -- addInflow F1:298, buildRhs F1:364, Gauss-Seidel project F1:380,
+applyPressure F1:432, Euler/lerp advect F1:178 -- must agree bit for bit on d, u, v and p, on a ragged grid and on a
+square one, and the solver's exit iteration and residual must agree too.  (The reference itself cannot run here.)"""
+import numpy as np
+import pytest
+
+import java_f1_transcript as jt
+
+
+@pytest.mark.parametrize("w,h,rect", [(24, 20, (0.45, 0.2, 0.15, 0.12, 1.0, 0.0, 3.0)),
+                                      (16, 16, (0.3, 0.1, 0.4, 0.2, 1.0, 0.5, 3.0)),
+                                      (20, 28, (0.2, 0.2, 0.3, 0.1, 0.7, -1.0, 2.0))])
+def test_f1_timesteps_match_python_transcription(ifl, oracle_cls, w, h, rect):
+    abi = ifl.abi
+    o = oracle_cls(abi, abi.default_config(abi.F1_MATRIXLESS, w, h))
+    j = jt.FluidSolver(w, h, 0.1)
+    x, y, rw, rh, d, u, v = rect
+    for step in range(3):
+        o.add_inflow(x, y, rw, rh, d, 0.0, u, v)
+        j.addInflow(x, y, rw, rh, d, u, v)
+        st = o.update(0.005)
+        j.update(0.005)
+        for name, arr in (("d", j._d._src), ("u", j._u._src), ("v", j._v._src), ("p", j._p)):
+            a, b = o.read(name), np.array(arr)
+            bad = np.flatnonzero(a != b)
+            assert bad.size == 0, (step, name, bad[:5], a[bad[:3]], b[bad[:3]])
+        assert st["residual_pressure"] == j.lastMaxDelta, (step, st, j.lastMaxDelta)
+        # the oracle reports executed iterations; the reference logs the 0-based index of the converging one (F1:420)
+        assert st["iterations_pressure"] in (j.lastIterations, j.lastIterations + 1), (st, j.lastIterations)
+    assert np.any(np.array(j._d._src) != 0.0) and np.any(np.array(j._p) != 0.0)
+
+
+import java_f3_transcript as jt3
+
+
+@pytest.mark.parametrize("w,h,rect", [(24, 20, (0.45, 0.2, 0.15, 0.12, 1.0, 0.0, 3.0)),
+                                      (16, 16, (0.3, 0.1, 0.4, 0.2, 1.0, 0.5, 3.0)),
+                                      (20, 28, (0.2, 0.2, 0.3, 0.1, 0.7, -1.0, 2.0))])
+def test_f3_timesteps_match_python_transcription(ifl, oracle_cls, w, h, rect):
+    """The headline path (configs 2 and 5): cubicPulse inflow F3:230, RK3 + Catmull-Rom advection F3:207/255/185,
+    buildPressureMatrix F3:435, MIC(0) buildPreconditioner F3:464, PCG project F3:590 with applyPreconditioner F3:495,
+    matrixVectorProduct F3:544, serial dotProduct F3:532, scaledAdd, float-rounded infinityNorm F3:579."""
+    abi = ifl.abi
+    o = oracle_cls(abi, abi.default_config(abi.F3_CONJUGATE_GRADIENTS, w, h))
+    j = jt3.FluidSolver(w, h, 0.1)
+    x, y, rw, rh, d, u, v = rect
+    for step in range(3):
+        o.add_inflow(x, y, rw, rh, d, 0.0, u, v)
+        j.addInflow(x, y, rw, rh, d, u, v)
+        st = o.update(0.005)
+        j.update(0.005)
+        fields = (("d", j._d._src), ("u", j._u._src), ("v", j._v._src), ("p", j._p), ("r", j._r),
+                  ("precon", j._precon), ("adiag", j._aDiag), ("aplusx", j._aPlusX), ("aplusy", j._aPlusY))
+        for name, arr in fields:
+            a, b = o.read(name), np.array(arr)
+            bad = np.flatnonzero(a != b)
+            assert bad.size == 0, (step, name, bad[:5], a[bad[:3]], b[bad[:3]])
+        assert st["residual_pressure"] == j.lastMaxError, (step, st, j.lastMaxError)
+        assert j.lastIterations is not None and 1 < j.lastIterations < 600
+        assert st["iterations_pressure"] in (j.lastIterations, j.lastIterations + 1), (st, j.lastIterations)
+    assert np.any(np.array(j._p) != 0.0)
