@@ -60,3 +60,52 @@ def test_f3_timesteps_match_python_transcription(ifl, oracle_cls, w, h, rect):
         assert j.lastIterations is not None and 1 < j.lastIterations < 600
         assert st["iterations_pressure"] in (j.lastIterations, j.lastIterations + 1), (st, j.lastIterations)
     assert np.any(np.array(j._p) != 0.0)
+
+
+class F2Solver(jt.FluidSolver):
+    """ExplicitFluid2betterAdvection.java: its FluidQuantity is F3's and its FluidSolver is F1's minus maxTimestep
+    (checked mechanically against the reference: the comment-stripped class bodies are identical), so the transcription
+    is the composition of the two."""
+    def __init__(self, w, h, density):
+        super().__init__(w, h, density)
+        self._d = jt3.FluidQuantity(w, h, 0.5, 0.5, self._hx)
+        self._u = jt3.FluidQuantity(w + 1, h, 0.0, 0.5, self._hx)
+        self._v = jt3.FluidQuantity(w, h + 1, 0.5, 0.0, self._hx)
+
+
+@pytest.mark.parametrize("w,h,rect", [(24, 20, (0.45, 0.2, 0.15, 0.12, 1.0, 0.0, 3.0)), (16, 22, (0.3, 0.1, 0.4, 0.2, 1.0, 0.5, 3.0))])
+def test_f2_timesteps_match_python_transcription(ifl, oracle_cls, w, h, rect):
+    abi = ifl.abi
+    o = oracle_cls(abi, abi.default_config(abi.F2_BETTER_ADVECTION, w, h))
+    j = F2Solver(w, h, 0.1)
+    x, y, rw, rh, d, u, v = rect
+    for step in range(3):
+        o.add_inflow(x, y, rw, rh, d, 0.0, u, v)
+        j.addInflow(x, y, rw, rh, d, u, v)
+        st = o.update(0.005)
+        j.update(0.005)
+        for name, arr in (("d", j._d._src), ("u", j._u._src), ("v", j._v._src), ("p", j._p)):
+            a, b = o.read(name), np.array(arr)
+            bad = np.flatnonzero(a != b)
+            assert bad.size == 0, (step, name, bad[:5], a[bad[:3]], b[bad[:3]])
+        assert st["residual_pressure"] == j.lastMaxDelta
+
+
+def test_max_timestep_matches_python_transcription(ifl, oracle_cls):
+    """maxTimestep F1:309 (lerpGrid at cell centres, sqrt, 2 hx / max, capped at 1)."""
+    import math
+    abi = ifl.abi
+    w, h = 20, 14
+    o = oracle_cls(abi, abi.default_config(abi.F1_MATRIXLESS, w, h))
+    j = jt.FluidSolver(w, h, 0.1)
+    for s in range(2):
+        o.add_inflow(0.3, 0.1, 0.4, 0.3, 1.0, 0.0, 0.7, 3.0)
+        j.addInflow(0.3, 0.1, 0.4, 0.3, 1.0, 0.7, 3.0)
+        o.update(0.005); j.update(0.005)
+    maxVelocity = 0.0
+    for y in range(h):
+        for x in range(w):
+            uu = j._u.lerpGrid(x + 0.5, y + 0.5)
+            vv = j._v.lerpGrid(x + 0.5, y + 0.5)
+            maxVelocity = jt.jmax(maxVelocity, math.sqrt(uu * uu + vv * vv))
+    assert o.max_timestep() == jt.jmin(2.0 * j._hx / maxVelocity, 1.0)
