@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import java_f1_transcript as jt
+import scenes
 
 
 @pytest.mark.parametrize("w,h,rect", [(24, 20, (0.45, 0.2, 0.15, 0.12, 1.0, 0.0, 3.0)),
@@ -109,3 +110,33 @@ def test_max_timestep_matches_python_transcription(ifl, oracle_cls):
             vv = j._v.lerpGrid(x + 0.5, y + 0.5)
             maxVelocity = jt.jmax(maxVelocity, math.sqrt(uu * uu + vv * vv))
     assert o.max_timestep() == jt.jmin(2.0 * j._hx / maxVelocity, 1.0)
+
+
+def test_solid_bodies_and_fill_solid_fields_match_python_transcription(ifl, oracle_cls):
+    """SolidBox / SolidSphere distance and distanceNormal (BOX:81,117; SPH:62,84) through fillSolidFields F4:329 on the
+    three staggered quantities, two bodies (a rotated, moving box and a sphere)."""
+    import java_solid_transcript as js
+    abi = ifl.abi
+    w, h = 40, 28
+    spec = scenes.MIXED_BODIES
+    recs = scenes.make_bodies(ifl, spec)
+    bodies = []
+    for (kind, args), rec in zip(spec, recs):
+        if kind == "box":
+            px, py, sx, sy, th, vx, vy, vt = args
+            bodies.append(js.SolidBox(px, py, sx, sy, th, vx, vy, vt, rec.cos_theta, rec.sin_theta))
+        else:
+            px, py, s, th, vx, vy, vt = args
+            bodies.append(js.SolidSphere(px, py, s, s, th, vx, vy, vt, rec.cos_theta, rec.sin_theta))
+    o = oracle_cls(abi, abi.default_config(abi.F4_SOLID_BOUNDARIES, w, h))
+    o.set_bodies(recs)
+    o.run_stage("fill_solid_fields")
+    hx = 1.0 / min(w, h)
+    for q, (qw, qh, ox, oy) in {"d": (w, h, 0.5, 0.5), "u": (w + 1, h, 0.0, 0.5), "v": (w, h + 1, 0.5, 0.0)}.items():
+        nx, ny = [0.0] * (qw * qh), [0.0] * (qw * qh)
+        cell, body = js.fillSolidFields(qw, qh, ox, oy, hx, bodies, nx, ny)
+        assert np.array_equal(o.read(f"cell_{q}"), np.array(cell, dtype=np.float64)), q
+        assert np.array_equal(o.read(f"body_{q}"), np.array(body, dtype=np.float64)), q
+        assert np.array_equal(o.read(f"normalx_{q}"), np.array(nx)), q
+        assert np.array_equal(o.read(f"normaly_{q}"), np.array(ny)), q
+        assert 0 < sum(cell) < qw * qh and 0 < sum(body) < qw * qh
