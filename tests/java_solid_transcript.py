@@ -106,3 +106,74 @@ def fillSolidFields(w, h, ox, oy, hx, bodies, normalX, normalY):      # F4:329
             normalX[idx], normalY[idx] = bodies[body[idx]].distanceNormal(normalX[idx], normalY[idx], x, y)
             idx += 1
     return cell, body
+
+
+# ---- ExplicitFluid5curvedBoundaries.java: marching-squares cell volumes ------------------------------------------
+def triangleOccupancy(out1, in_, out2):             # F5:135
+    return 0.5 * in_ * in_ / ((out1 - in_) * (out2 - in_))
+
+
+def trapezoidOccupancy(out1, out2, in1, in2):       # F5:146
+    return 0.5 * (-in1 / (out1 - in1) - in2 / (out2 - in2))
+
+
+def occupancy(d11, d12, d21, d22):                  # F5:165
+    ds = [d11, d12, d22, d21]
+    b = 0
+    for i in range(3, -1, -1):
+        b = (b << 1) | (1 if ds[i] < 0.0 else 0)
+    if b == 0x0: return 0.0
+    if b == 0x1: return triangleOccupancy(d21, d11, d12)
+    if b == 0x2: return triangleOccupancy(d11, d12, d22)
+    if b == 0x4: return triangleOccupancy(d12, d22, d21)
+    if b == 0x8: return triangleOccupancy(d22, d21, d11)
+    if b == 0xE: return 1.0 - triangleOccupancy(-d21, -d11, -d12)
+    if b == 0xD: return 1.0 - triangleOccupancy(-d11, -d12, -d22)
+    if b == 0xB: return 1.0 - triangleOccupancy(-d12, -d22, -d21)
+    if b == 0x7: return 1.0 - triangleOccupancy(-d22, -d21, -d11)
+    if b == 0x3: return trapezoidOccupancy(d21, d22, d11, d12)
+    if b == 0x6: return trapezoidOccupancy(d11, d21, d12, d22)
+    if b == 0x9: return trapezoidOccupancy(d12, d22, d11, d21)
+    if b == 0xC: return trapezoidOccupancy(d11, d12, d21, d22)
+    if b == 0x5: return triangleOccupancy(d11, d12, d22) + triangleOccupancy(d22, d21, d11)
+    if b == 0xA: return triangleOccupancy(d21, d11, d12) + triangleOccupancy(d12, d22, d21)
+    if b == 0xF: return 1.0
+    return 0.0
+
+
+def fillSolidFields5(w, h, ox, oy, hx, bodies, normalX, normalY):     # F5:463
+    """returns (_phi, _volume, _cell, _body)"""
+    from java_f1_transcript import jmin
+    phi = [0.0] * ((w + 1) * (h + 1))
+    volume, cell, body = [1.0] * (w * h), [CELL_FLUID] * (w * h), [0] * (w * h)
+    if not bodies:
+        return phi, volume, cell, body
+    idx = 0
+    for iy in range(h + 1):
+        for ix in range(w + 1):
+            x = (ix + ox - 0.5) * hx
+            y = (iy + oy - 0.5) * hx
+            phi[idx] = bodies[0].distance(x, y)
+            for i in range(1, len(bodies)):
+                phi[idx] = jmin(phi[idx], bodies[i].distance(x, y))
+            idx += 1
+    idx = 0
+    for iy in range(h):
+        for ix in range(w):
+            x = (ix + ox) * hx
+            y = (iy + oy) * hx
+            body[idx] = 0
+            d = bodies[0].distance(x, y)
+            for i in range(1, len(bodies)):
+                di = bodies[i].distance(x, y)
+                if di < d:
+                    body[idx] = i
+                    d = di
+            idxp = ix + iy * (w + 1)
+            volume[idx] = 1.0 - occupancy(phi[idxp], phi[idxp + 1], phi[idxp + w + 1], phi[idxp + w + 2])
+            if volume[idx] < 0.01:
+                volume[idx] = 0.0
+            normalX[idx], normalY[idx] = bodies[body[idx]].distanceNormal(normalX[idx], normalY[idx], x, y)
+            cell[idx] = CELL_SOLID if volume[idx] == 0.0 else CELL_FLUID
+            idx += 1
+    return phi, volume, cell, body

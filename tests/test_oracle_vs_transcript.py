@@ -140,3 +140,41 @@ def test_solid_bodies_and_fill_solid_fields_match_python_transcription(ifl, orac
         assert np.array_equal(o.read(f"normalx_{q}"), np.array(nx)), q
         assert np.array_equal(o.read(f"normaly_{q}"), np.array(ny)), q
         assert 0 < sum(cell) < qw * qh and 0 < sum(body) < qw * qh
+
+
+def test_curved_boundary_volumes_match_python_transcription(ifl, oracle_cls):
+    """occupancy / triangleOccupancy / trapezoidOccupancy (F5:135-232) through fillSolidFields F5:463: level set at the
+    cell corners, marching-squares volumes (all 16 cases occur with two bodies), the 0.01 cut-off, cell types."""
+    import java_solid_transcript as js
+    abi = ifl.abi
+    w, h = 48, 36
+    spec = scenes.MIXED_BODIES
+    recs = scenes.make_bodies(ifl, spec)
+    bodies = []
+    for (kind, args), rec in zip(spec, recs):
+        if kind == "box":
+            px, py, sx, sy, th, vx, vy, vt = args
+            bodies.append(js.SolidBox(px, py, sx, sy, th, vx, vy, vt, rec.cos_theta, rec.sin_theta))
+        else:
+            px, py, s, th, vx, vy, vt = args
+            bodies.append(js.SolidSphere(px, py, s, s, th, vx, vy, vt, rec.cos_theta, rec.sin_theta))
+    o = oracle_cls(abi, abi.default_config(abi.F5_CURVED_BOUNDARIES, w, h))
+    o.set_bodies(recs)
+    o.run_stage("fill_solid_fields")
+    hx = 1.0 / min(w, h)
+    seen = set()
+    for q, (qw, qh, ox, oy) in {"d": (w, h, 0.5, 0.5), "u": (w + 1, h, 0.0, 0.5), "v": (w, h + 1, 0.5, 0.0)}.items():
+        nx, ny = [0.0] * (qw * qh), [0.0] * (qw * qh)
+        phi, volume, cell, body = js.fillSolidFields5(qw, qh, ox, oy, hx, bodies, nx, ny)
+        assert np.array_equal(o.read(f"phi_{q}"), np.array(phi)), q
+        assert np.array_equal(o.read(f"volume_{q}"), np.array(volume)), q
+        assert np.array_equal(o.read(f"cell_{q}"), np.array(cell, dtype=np.float64)), q
+        assert np.array_equal(o.read(f"body_{q}"), np.array(body, dtype=np.float64)), q
+        assert np.array_equal(o.read(f"normalx_{q}"), np.array(nx)), q
+        assert np.array_equal(o.read(f"normaly_{q}"), np.array(ny)), q
+        for iy in range(qh):
+            for ix in range(qw):
+                p = ix + iy * (qw + 1)
+                ds = [phi[p], phi[p + 1], phi[p + qw + 2], phi[p + qw + 1]]
+                seen.add(sum((1 if ds[i] < 0.0 else 0) << i for i in range(4)))
+    assert len(seen) >= 12, sorted(seen)          # the marching-squares cases this scene exercises
