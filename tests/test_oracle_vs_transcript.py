@@ -178,3 +178,45 @@ def test_curved_boundary_volumes_match_python_transcription(ifl, oracle_cls):
                 ds = [phi[p], phi[p + 1], phi[p + qw + 2], phi[p + qw + 1]]
                 seen.add(sum((1 if ds[i] < 0.0 else 0) << i for i in range(4)))
     assert len(seen) >= 12, sorted(seen)          # the marching-squares cases this scene exercises
+
+
+def _transcript_bodies(ifl, spec):
+    import java_solid_transcript as js
+    recs = scenes.make_bodies(ifl, spec)
+    bodies = []
+    for (kind, args), rec in zip(spec, recs):
+        if kind == "box":
+            px, py, sx, sy, th, vx, vy, vt = args
+            bodies.append(js.SolidBox(px, py, sx, sy, th, vx, vy, vt, rec.cos_theta, rec.sin_theta))
+        else:
+            px, py, s, th, vx, vy, vt = args
+            bodies.append(js.SolidSphere(px, py, s, s, th, vx, vy, vt, rec.cos_theta, rec.sin_theta))
+    return recs, bodies
+
+
+@pytest.mark.parametrize("w,h,spec", [(32, 32, scenes.F4_BODIES), (36, 28, scenes.MIXED_BODIES)])
+def test_f4_timesteps_match_python_transcription(ifl, oracle_cls, w, h, spec):
+    """Whole ExplicitFluid4 timesteps (F4:617): fillSolidFields, setBoundaryCondition (velocityX quirk), masked
+    buildRhs / matrix / MIC(0) / PCG, applyPressure, stack-driven extrapolate F4:452, back-projected advect F4:268 --
+    with the reference scene's static box and with a moving box + sphere."""
+    import java_f4_transcript as j4
+    abi = ifl.abi
+    recs, bodies = _transcript_bodies(ifl, spec)
+    o = oracle_cls(abi, abi.default_config(abi.F4_SOLID_BOUNDARIES, w, h))
+    o.set_bodies(recs)
+    j = j4.FluidSolver(w, h, 0.1, bodies)
+    x, y, rw, rh, d, t, u, v = scenes.F4_INFLOW
+    rh = 0.12                                        # tall enough to hit a v face at this resolution
+    for step in range(3):
+        o.add_inflow(x, y, rw, rh, d, t, u, v)
+        j.addInflow(x, y, rw, rh, d, u, v)
+        st = o.update(0.005)
+        j.update(0.005)
+        for name, arr in (("d", j._d._src), ("u", j._u._src), ("v", j._v._src), ("p", j._p), ("r", j._r),
+                          ("precon", j._precon), ("adiag", j._aDiag), ("aplusx", j._aPlusX), ("aplusy", j._aPlusY)):
+            a, b = o.read(name), np.array(arr)
+            bad = np.flatnonzero(a != b)
+            assert bad.size == 0, (step, name, bad[:5], a[bad[:3]], b[bad[:3]])
+        assert st["residual_pressure"] == j.lastMaxError, (step, st, j.lastMaxError)
+        assert st["iterations_pressure"] in (j.lastIterations, j.lastIterations + 1), (st, j.lastIterations)
+    assert np.any(np.array(j._p) != 0.0) and j._d._cell.count(j4.CELL_SOLID) > 0
