@@ -220,3 +220,31 @@ def test_f4_timesteps_match_python_transcription(ifl, oracle_cls, w, h, spec):
         assert st["residual_pressure"] == j.lastMaxError, (step, st, j.lastMaxError)
         assert st["iterations_pressure"] in (j.lastIterations, j.lastIterations + 1), (st, j.lastIterations)
     assert np.any(np.array(j._p) != 0.0) and j._d._cell.count(j4.CELL_SOLID) > 0
+
+
+@pytest.mark.parametrize("w,h,spec", [(32, 32, scenes.F5_BODIES), (36, 28, scenes.MIXED_BODIES)])
+def test_f5_timesteps_match_python_transcription(ifl, oracle_cls, w, h, spec):
+    """Whole ExplicitFluid5 timesteps (F5:1089): marching-squares volumes, the volume-weighted right-hand side with the
+    body velocities F5:785, the volume-weighted matrix F5:825, everything else as in F4."""
+    import java_f5_transcript as j5
+    abi = ifl.abi
+    recs, bodies = _transcript_bodies(ifl, spec)
+    o = oracle_cls(abi, abi.default_config(abi.F5_CURVED_BOUNDARIES, w, h))
+    o.set_bodies(recs)
+    j = j5.FluidSolver(w, h, 0.1, bodies)
+    x, y, rw, rh, d, t, u, v = scenes.F4_INFLOW
+    rh = 0.12
+    for step in range(3):
+        o.add_inflow(x, y, rw, rh, d, t, u, v)
+        j.addInflow(x, y, rw, rh, d, u, v)
+        st = o.update(0.005)
+        j.update(0.005)
+        for name, arr in (("d", j._d._src), ("u", j._u._src), ("v", j._v._src), ("p", j._p), ("r", j._r),
+                          ("precon", j._precon), ("adiag", j._aDiag), ("aplusx", j._aPlusX), ("aplusy", j._aPlusY),
+                          ("volume_u", j._u._volume), ("volume_v", j._v._volume)):
+            a, b = o.read(name), np.array(arr)
+            bad = np.flatnonzero(a != b)
+            assert bad.size == 0, (step, name, bad[:5], a[bad[:3]], b[bad[:3]])
+        assert st["residual_pressure"] == j.lastMaxError, (step, st, j.lastMaxError)
+        assert st["iterations_pressure"] in (j.lastIterations, j.lastIterations + 1), (st, j.lastIterations)
+    assert np.any(np.array(j._p) != 0.0) and any(0.0 < vv < 1.0 for vv in j._d._volume)
