@@ -248,3 +248,30 @@ def test_f5_timesteps_match_python_transcription(ifl, oracle_cls, w, h, spec):
         assert st["residual_pressure"] == j.lastMaxError, (step, st, j.lastMaxError)
         assert st["iterations_pressure"] in (j.lastIterations, j.lastIterations + 1), (st, j.lastIterations)
     assert np.any(np.array(j._p) != 0.0) and any(0.0 < vv < 1.0 for vv in j._d._volume)
+
+
+@pytest.mark.parametrize("w,h,spec,soot", [(32, 32, scenes.F6_BODIES, 0.1), (36, 28, scenes.MIXED_BODIES, 0.3)])
+def test_f6_timesteps_match_python_transcription(ifl, oracle_cls, w, h, spec, soot):
+    """Whole ExplicitFluid6heat timesteps (F6:1181): implicit heat diffusion solve, buoyancy, fluid-only vector
+    operations, then the F5 projection and four advected quantities."""
+    import java_f6_transcript as j6
+    abi = ifl.abi
+    recs, bodies = _transcript_bodies(ifl, spec)
+    o = oracle_cls(abi, abi.default_config(abi.F6_HEAT, w, h, density_soot=soot))
+    o.set_bodies(recs)
+    j = j6.FluidSolver(w, h, 0.1, soot, 0.01, bodies)
+    assert o.cfg.t_ambient == j._tAmb and o.cfg.diffusion == 0.01 and o.cfg.gravity == j._g
+    x, y, rw, rh, d, t, u, v = scenes.F6_INFLOW
+    y, rh = 0.8, 0.12
+    for step in range(3):
+        o.add_inflow(x, y, rw, rh, d, t, u, v)
+        j.addInflow(x, y, rw, rh, d, t, u, v)
+        st = o.update(0.005)
+        j.update(0.005)
+        for name, arr in (("d", j._d._src), ("t", j._t._src), ("u", j._u._src), ("v", j._v._src), ("p", j._p), ("r", j._r)):
+            a, b = o.read(name), np.array(arr)
+            bad = np.flatnonzero(a != b)
+            assert bad.size == 0, (step, name, bad[:5], a[bad[:3]], b[bad[:3]])
+        assert st["residual_pressure"] == j.lastMaxError and st["residual_heat"] == j.heatMaxError, (step, st)
+        assert st["iterations_heat"] in (j.heatIterations, j.heatIterations + 1), (st, j.heatIterations)
+    assert np.any(np.array(j._t._src) != j._tAmb) and np.any(np.array(j._p) != 0.0)
