@@ -275,3 +275,29 @@ def test_f6_timesteps_match_python_transcription(ifl, oracle_cls, w, h, spec, so
         assert st["residual_pressure"] == j.lastMaxError and st["residual_heat"] == j.heatMaxError, (step, st)
         assert st["iterations_heat"] in (j.heatIterations, j.heatIterations + 1), (st, j.heatIterations)
     assert np.any(np.array(j._t._src) != j._tAmb) and np.any(np.array(j._p) != 0.0)
+
+
+@pytest.mark.parametrize("w,h,spec", [(32, 32, scenes.F7_BODIES), (36, 28, scenes.MIXED_BODIES)])
+def test_f7_timesteps_match_python_transcription(ifl, oracle_cls, w, h, spec):
+    """Whole ExplicitFluid7variableDensity timesteps (F7:1212): face densities from temperature and soot, the
+    density-weighted matrix (index quirk included) and pressure application -- BASELINE config 3's variant."""
+    import java_f7_transcript as j7
+    abi = ifl.abi
+    recs, bodies = _transcript_bodies(ifl, spec)
+    o = oracle_cls(abi, abi.default_config(abi.F7_VARIABLE_DENSITY, w, h, density_soot=1.0))
+    o.set_bodies(recs)
+    j = j7.FluidSolver(w, h, 0.1, 1.0, 0.01, bodies)
+    x, y, rw, rh, d, t, u, v = scenes.F7_INFLOW
+    rh = 0.12
+    for step in range(3):
+        o.add_inflow(x, y, rw, rh, d, t + 40.0 * step, u, v)
+        j.addInflow(x, y, rw, rh, d, t + 40.0 * step, u, v)
+        st = o.update(0.005)
+        j.update(0.005)
+        for name, arr in (("d", j._d._src), ("t", j._t._src), ("u", j._u._src), ("v", j._v._src), ("p", j._p), ("r", j._r),
+                          ("udensity", j._uDensity), ("vdensity", j._vDensity)):
+            a, b = o.read(name), np.array(arr)
+            bad = np.flatnonzero(a != b)
+            assert bad.size == 0, (step, name, bad[:5], a[bad[:3]], b[bad[:3]])
+        assert st["residual_pressure"] == j.lastMaxError and st["residual_heat"] == j.heatMaxError, (step, st)
+    assert np.any(np.array(j._p) != 0.0) and np.any(np.array(j._uDensity) != j._uDensity[0])
