@@ -1,0 +1,58 @@
+"""Literal Python transcription of the particle-side pieces of ExplicitFluid8flip.java that can be isolated through the
+C ABI's stages: gridToParticles F8:1748 (the PIC/FLIP blend `p = (1 - alpha) p + lerpGrid`), the particle Runge-Kutta
+F8:1708 (forward in time: `+`), backProject F8:1673 and advect F8:1778.  The particle-to-grid transfer (fromParticles
+F8:722 with the EMPTY-cell extrapolation that follows it) is not transcribed; it stays pinned by the oracle alone.
+See java_f1_transcript.py."""
+import java_f4_transcript as f4
+from java_f1_transcript import jmax, jmin
+
+
+def gridToParticles(quantities, properties, posX, posY, count, alpha):      # F8:1748
+    for t in range(len(quantities)):
+        for i in range(count):
+            properties[t][i] *= 1.0 - alpha
+            properties[t][i] += quantities[t].lerpGrid(posX[i], posY[i])
+
+
+def rungeKutta3(x, y, timestep, u, v, _hx):         # F8:1708
+    firstU = u.lerpGrid(x, y) / _hx
+    firstV = v.lerpGrid(x, y) / _hx
+    midX = x + 0.5 * timestep * firstU
+    midY = y + 0.5 * timestep * firstV
+    midU = u.lerpGrid(midX, midY) / _hx
+    midV = v.lerpGrid(midX, midY) / _hx
+    lastX = x + 0.75 * timestep * midU
+    lastY = y + 0.75 * timestep * midV
+    lastU = u.lerpGrid(lastX, lastY)                 # sic: no division by _hx
+    lastV = v.lerpGrid(lastX, lastY)
+    x += timestep * ((2.0 / 9.0) * firstU + (3.0 / 9.0) * midU + (4.0 / 9.0) * lastU)
+    y += timestep * ((2.0 / 9.0) * firstV + (3.0 / 9.0) * midV + (4.0 / 9.0) * lastV)
+    return x, y
+
+
+def backProject(x, y, bodies, _hx):                 # F8:1673
+    d = 1e30
+    closestBody = -1
+    for i in range(len(bodies)):
+        di = bodies[i].distance(x * _hx, y * _hx)
+        if di < d:
+            d = di
+            closestBody = i
+    if d < -1.0:
+        x *= _hx
+        y *= _hx
+        x, y = f4.closestSurfacePoint(bodies[closestBody], x, y)
+        nx, ny = bodies[closestBody].distanceNormal(0.0, 0.0, x, y)
+        x -= nx * _hx
+        y -= ny * _hx
+        x /= _hx
+        y /= _hx
+    return x, y
+
+
+def advect(posX, posY, count, timestep, u, v, bodies, _w, _h, _hx):         # F8:1778
+    for i in range(count):
+        posX[i], posY[i] = rungeKutta3(posX[i], posY[i], timestep, u, v, _hx)
+        posX[i], posY[i] = backProject(posX[i], posY[i], bodies, _hx)
+        posX[i] = jmax(jmin(posX[i], _w - 0.001), 0.0)
+        posY[i] = jmax(jmin(posY[i], _h - 0.001), 0.0)

@@ -301,3 +301,43 @@ def test_f7_timesteps_match_python_transcription(ifl, oracle_cls, w, h, spec):
             assert bad.size == 0, (step, name, bad[:5], a[bad[:3]], b[bad[:3]])
         assert st["residual_pressure"] == j.lastMaxError and st["residual_heat"] == j.heatMaxError, (step, st)
     assert np.any(np.array(j._p) != 0.0) and np.any(np.array(j._uDensity) != j._uDensity[0])
+
+
+def test_f8_particle_stages_match_python_transcription(ifl, oracle_cls):
+    """gridToParticles F8:1748 and the particle advect F8:1778 (rungeKutta3 F8:1708, backProject F8:1673, clamping) in
+    isolation, on particles and grid fields written through the ABI (no random stream involved)."""
+    import java_f8_transcript as j8
+    import java_f3_transcript as j3
+    abi = ifl.abi
+    w, h = 28, 24
+    hx = 1.0 / min(w, h)
+    recs, bodies = _transcript_bodies(ifl, scenes.F7_BODIES)
+    o = oracle_cls(abi, abi.default_config(abi.F8_FLIP, w, h))
+    o.set_bodies(recs)
+    rng = np.random.default_rng(5)
+    n = 400
+    parts = {"x": rng.uniform(-0.5, w + 0.5, n), "y": rng.uniform(-0.5, h + 0.5, n)}
+    for k in ("d", "t", "u", "v"):
+        parts[k] = rng.normal(size=n)
+    grids = {"d": (w, h, 0.5, 0.5), "t": (w, h, 0.5, 0.5), "u": (w + 1, h, 0.0, 0.5), "v": (w, h + 1, 0.5, 0.0)}
+    qs = {}
+    for k, (qw, qh, ox, oy) in grids.items():
+        q = j3.FluidQuantity(qw, qh, ox, oy, hx)
+        q._src = list(rng.normal(size=qw * qh) * (0.05 if k in "uv" else 1.0))
+        o.write(k, np.array(q._src))
+        qs[k] = q
+    o.write_particles(parts)
+    # grid -> particles (the stage also applies diff / undiff with _old = 0, which leaves the grids unchanged)
+    o.run_stage("grid_to_particles")
+    props = [list(parts[k]) for k in ("d", "t", "u", "v")]
+    px, py = list(parts["x"]), list(parts["y"])
+    j8.gridToParticles([qs[k] for k in ("d", "t", "u", "v")], props, px, py, n, o.cfg.flip_alpha)
+    got = o.read_particles()
+    for k, p in zip(("d", "t", "u", "v"), props):
+        assert np.array_equal(got[k], np.array(p)), k
+    # particle advection
+    o.run_stage("advect_particles", 0.0025)
+    j8.advect(px, py, n, 0.0025, qs["u"], qs["v"], bodies, w, h, hx)
+    got = o.read_particles()
+    assert np.array_equal(got["x"], np.array(px)) and np.array_equal(got["y"], np.array(py))
+    assert np.any(np.array(px) != parts["x"])
