@@ -1,7 +1,8 @@
 """Literal Python transcription of the particle-side pieces of ExplicitFluid8flip.java that can be isolated through the
 C ABI's stages: gridToParticles F8:1748 (the PIC/FLIP blend `p = (1 - alpha) p + lerpGrid`), the particle Runge-Kutta
-F8:1708 (forward in time: `+`), backProject F8:1673 and advect F8:1778.  The particle-to-grid transfer (fromParticles
-F8:722 with the EMPTY-cell extrapolation that follows it) is not transcribed; it stays pinned by the oracle alone.
+F8:1708 (forward in time: `+`), backProject F8:1673 and advect F8:1778, and the particle-to-grid transfer fromParticles
+F8:722 / addSample F8:312.  Not transcribed (pinned by the oracle alone): the EMPTY-cell extrapolation F8:651 and the
+particle bookkeeping on the random stream (init / count / prune / seed F8:1571-1660).
 See java_f1_transcript.py."""
 import java_f4_transcript as f4
 from java_f1_transcript import jmax, jmin
@@ -56,3 +57,37 @@ def advect(posX, posY, count, timestep, u, v, bodies, _w, _h, _hx):         # F8
         posX[i], posY[i] = backProject(posX[i], posY[i], bodies, _hx)
         posX[i] = jmax(jmin(posX[i], _w - 0.001), 0.0)
         posY[i] = jmax(jmin(posY[i], _h - 0.001), 0.0)
+
+
+# ---- particle -> grid: FluidQuantity.addSample F8:312 and fromParticles F8:722 (without the extrapolation that follows)
+CELL_FLUID, CELL_SOLID, CELL_EMPTY = 0, 1, 2
+
+
+def addSample(q_src, weight, _w, _h, value, x, y, ix, iy):                  # F8:312
+    if ix < 0 or iy < 0 or ix >= _w or iy >= _h:
+        return
+    k = (1.0 - abs(ix - x)) * (1.0 - abs(iy - y))
+    weight[ix + iy * _w] += k
+    q_src[ix + iy * _w] += k * value
+
+
+def fromParticles(_w, _h, _ox, _oy, cell, count, posX, posY, prop):         # F8:722
+    _src = [0.0] * (_w * _h)
+    weight = [0.0] * (_w * _h)
+    for i in range(count):
+        x = posX[i] - _ox
+        y = posY[i] - _oy
+        x = jmax(0.5, jmin(_w - 1.5, x))
+        y = jmax(0.5, jmin(_h - 1.5, y))
+        ix = int(x)
+        iy = int(y)
+        addSample(_src, weight, _w, _h, prop[i], x, y, ix + 0, iy + 0)
+        addSample(_src, weight, _w, _h, prop[i], x, y, ix + 1, iy + 0)
+        addSample(_src, weight, _w, _h, prop[i], x, y, ix + 0, iy + 1)
+        addSample(_src, weight, _w, _h, prop[i], x, y, ix + 1, iy + 1)
+    for i in range(_w * _h):
+        if weight[i] != 0.0:
+            _src[i] /= weight[i]
+        elif cell[i] == CELL_FLUID:
+            cell[i] = CELL_EMPTY
+    return _src

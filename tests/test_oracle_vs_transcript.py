@@ -341,3 +341,26 @@ def test_f8_particle_stages_match_python_transcription(ifl, oracle_cls):
     got = o.read_particles()
     assert np.array_equal(got["x"], np.array(px)) and np.array_equal(got["y"], np.array(py))
     assert np.any(np.array(px) != parts["x"])
+
+
+def test_f8_particles_to_grid_matches_python_transcription(ifl, oracle_cls):
+    """fromParticles F8:722 / addSample F8:312: the bilinear splat in particle-index order and the division by the
+    accumulated weights.  Particles cover every node and there are no bodies, so the extrapolation that follows the
+    transfer inside particlesToGrid F8:1761 has nothing to fill and the stage's grids are the transfer's output."""
+    import java_f8_transcript as j8
+    abi = ifl.abi
+    w, h = 20, 16
+    o = oracle_cls(abi, abi.default_config(abi.F8_FLIP, w, h))
+    rng = np.random.default_rng(11)
+    n = w * h * 6
+    parts = {"x": rng.uniform(0.0, w, n), "y": rng.uniform(0.0, h, n)}
+    for k in ("d", "t", "u", "v"):
+        parts[k] = rng.normal(size=n)
+    o.write_particles(parts)
+    o.run_stage("particles_to_grid")
+    grids = {"d": (w, h, 0.5, 0.5), "t": (w, h, 0.5, 0.5), "u": (w + 1, h, 0.0, 0.5), "v": (w, h + 1, 0.5, 0.0)}
+    for k, (qw, qh, ox, oy) in grids.items():
+        cell = [j8.CELL_FLUID] * (qw * qh)
+        want = j8.fromParticles(qw, qh, ox, oy, cell, n, list(parts["x"]), list(parts["y"]), list(parts[k]))
+        assert cell.count(j8.CELL_EMPTY) == 0, k            # the premise of this test
+        assert np.array_equal(o.read(k), np.array(want)), k
