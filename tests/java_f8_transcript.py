@@ -1,7 +1,7 @@
 """Literal Python transcription of the particle-side pieces of ExplicitFluid8flip.java that can be isolated through the
 C ABI's stages: gridToParticles F8:1748 (the PIC/FLIP blend `p = (1 - alpha) p + lerpGrid`), the particle Runge-Kutta
 F8:1708 (forward in time: `+`), backProject F8:1673 and advect F8:1778, and the particle-to-grid transfer fromParticles
-F8:722 / addSample F8:312.  Not transcribed (pinned by the oracle alone): the EMPTY-cell extrapolation F8:651 and the
+F8:722 / addSample F8:312 with the EMPTY-cell extrapolation F8:651.  Not transcribed (pinned by the oracle alone): the
 particle bookkeeping on the random stream (init / count / prune / seed F8:1571-1660).
 See java_f1_transcript.py."""
 import java_f4_transcript as f4
@@ -91,3 +91,113 @@ def fromParticles(_w, _h, _ox, _oy, cell, count, posX, posY, prop):         # F8
         elif cell[i] == CELL_FLUID:
             cell[i] = CELL_EMPTY
     return _src
+
+
+# ---- FluidQuantity.extrapolate of ExplicitFluid8flip.java (F8:651): SOLID cells along the normal as in F4, EMPTY cells
+# (no particle weight) by the average of their FLUID neighbours, EMPTY cells on the domain border from their inner
+# neighbour; every EMPTY cell ends up FLUID.
+def isignum(v):
+    return int(v and (1 if v > 0 else -1))
+
+
+def extrapolate8(_src, cell, normalX, normalY, _w, _h):
+    from java_f1_transcript import f32
+    mask = [0] * (_w * _h)
+    # fillSolidMask F8:~520
+    for x in range(_w):
+        mask[x] = mask[x + (_h - 1) * _w] = 0xFF
+    for y in range(_h):
+        mask[y * _w] = mask[y * _w + _w - 1] = 0xFF
+    for y in range(1, _h - 1):
+        for x in range(1, _w - 1):
+            idx = x + y * _w
+            mask[idx] = 0
+            if cell[idx] == CELL_SOLID:
+                nx, ny = normalX[idx], normalY[idx]
+                if nx != 0.0 and cell[idx + isignum(nx)] != CELL_FLUID:
+                    mask[idx] |= 1
+                if ny != 0.0 and cell[idx + isignum(ny) * _w] != CELL_FLUID:
+                    mask[idx] |= 2
+            elif cell[idx] == CELL_EMPTY:
+                mask[idx] = 1 if (cell[idx - 1] != CELL_FLUID and cell[idx + 1] != CELL_FLUID
+                                  and cell[idx - _w] != CELL_FLUID and cell[idx + _w] != CELL_FLUID) else 0
+
+    def extrapolateNormal(idx):                     # as F4:426
+        nx, ny = normalX[idx], normalY[idx]
+        srcX = _src[idx + isignum(nx)]
+        srcY = _src[idx + isignum(ny) * _w]
+        return (abs(f32(nx)) * srcX + abs(f32(ny)) * srcY) / (abs(f32(nx)) + abs(f32(ny)))
+
+    def extrapolateAverage(idx):                    # F8:~545
+        value, count = 0.0, 0
+        if cell[idx - 1] == CELL_FLUID:
+            value += _src[idx - 1]; count += 1
+        if cell[idx + 1] == CELL_FLUID:
+            value += _src[idx + 1]; count += 1
+        if cell[idx - _w] == CELL_FLUID:
+            value += _src[idx - _w]; count += 1
+        if cell[idx + _w] == CELL_FLUID:
+            value += _src[idx + _w]; count += 1
+        return value / count
+
+    def freeSolidNeighbour(idx, border, m):         # F8:567
+        if cell[idx] == CELL_SOLID:
+            mask[idx] &= ~m
+            if mask[idx] == 0:
+                border.append(idx)
+
+    def freeEmptyNeighbour(idx, border):            # F8:~585
+        if cell[idx] == CELL_EMPTY and mask[idx] == 1:
+            mask[idx] = 0
+            border.append(idx)
+
+    border = []
+    for y in range(1, _h - 1):
+        for x in range(1, _w - 1):
+            idx = x + y * _w
+            if cell[idx] != CELL_FLUID and mask[idx] == 0:
+                border.append(idx)
+    while border:
+        idx = border.pop()
+        if cell[idx] == CELL_EMPTY:
+            _src[idx] = extrapolateAverage(idx)
+            cell[idx] = CELL_FLUID
+        else:
+            _src[idx] = extrapolateNormal(idx)
+        if normalX[idx - 1] > 0.0:
+            freeSolidNeighbour(idx - 1, border, 1)
+        if normalX[idx + 1] < 0.0:
+            freeSolidNeighbour(idx + 1, border, 1)
+        if normalY[idx - _w] > 0.0:
+            freeSolidNeighbour(idx - _w, border, 2)
+        if normalY[idx + _w] < 0.0:
+            freeSolidNeighbour(idx + _w, border, 2)
+        freeEmptyNeighbour(idx - 1, border)
+        freeEmptyNeighbour(idx + 1, border)
+        freeEmptyNeighbour(idx - _w, border)
+        freeEmptyNeighbour(idx + _w, border)
+    # extrapolateEmptyBorders F8:~600
+    for x in range(1, _w - 1):
+        idxT, idxB = x, x + (_h - 1) * _w
+        if cell[idxT] == CELL_EMPTY:
+            _src[idxT] = _src[idxT + _w]
+        if cell[idxB] == CELL_EMPTY:
+            _src[idxB] = _src[idxB - _w]
+    for y in range(1, _h - 1):
+        idxL, idxR = y * _w, y * _w + _w - 1
+        if cell[idxL] == CELL_EMPTY:
+            _src[idxL] = _src[idxL + 1]
+        if cell[idxR] == CELL_EMPTY:
+            _src[idxR] = _src[idxR - 1]
+    idxTL, idxTR, idxBL, idxBR = 0, _w - 1, (_h - 1) * _w, _h * _w - 1
+    if cell[idxTL] == CELL_EMPTY:
+        _src[idxTL] = 0.5 * (_src[idxTL + 1] + _src[idxTL + _w])
+    if cell[idxTR] == CELL_EMPTY:
+        _src[idxTR] = 0.5 * (_src[idxTR - 1] + _src[idxTR + _w])
+    if cell[idxBL] == CELL_EMPTY:
+        _src[idxBL] = 0.5 * (_src[idxBL + 1] + _src[idxBL - _w])
+    if cell[idxBR] == CELL_EMPTY:
+        _src[idxBR] = 0.5 * (_src[idxBR - 1] + _src[idxBR - _w])
+    for i in range(_w * _h):
+        if cell[i] == CELL_EMPTY:
+            cell[i] = CELL_FLUID

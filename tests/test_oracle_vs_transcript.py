@@ -364,3 +364,30 @@ def test_f8_particles_to_grid_matches_python_transcription(ifl, oracle_cls):
         want = j8.fromParticles(qw, qh, ox, oy, cell, n, list(parts["x"]), list(parts["y"]), list(parts[k]))
         assert cell.count(j8.CELL_EMPTY) == 0, k            # the premise of this test
         assert np.array_equal(o.read(k), np.array(want)), k
+
+
+def test_f8_empty_cell_extrapolation_matches_python_transcription(ifl, oracle_cls):
+    """Sparse particles leave EMPTY cells (fromParticles F8:745): the transfer followed by FluidQuantity.extrapolate
+    F8:651 -- averages of FLUID neighbours in stack order, chains of EMPTY cells, domain borders and corners."""
+    import java_f8_transcript as j8
+    abi = ifl.abi
+    w, h = 24, 20
+    o = oracle_cls(abi, abi.default_config(abi.F8_FLIP, w, h))
+    rng = np.random.default_rng(3)
+    # a blob that covers the middle of the domain only, with holes
+    n = 500
+    parts = {"x": rng.uniform(3.0, w - 2.0, n), "y": rng.uniform(0.0, h - 5.0, n)}
+    for k in ("d", "t", "u", "v"):
+        parts[k] = rng.normal(size=n)
+    o.write_particles(parts)
+    o.run_stage("particles_to_grid")
+    grids = {"d": (w, h, 0.5, 0.5), "t": (w, h, 0.5, 0.5), "u": (w + 1, h, 0.0, 0.5), "v": (w, h + 1, 0.5, 0.0)}
+    for k, (qw, qh, ox, oy) in grids.items():
+        cell = [j8.CELL_FLUID] * (qw * qh)
+        src = j8.fromParticles(qw, qh, ox, oy, cell, n, list(parts["x"]), list(parts["y"]), list(parts[k]))
+        empties = cell.count(j8.CELL_EMPTY)
+        assert 20 < empties < qw * qh - 20, (k, empties)
+        j8.extrapolate8(src, cell, [0.0] * (qw * qh), [0.0] * (qw * qh), qw, qh)
+        a, b = o.read(k), np.array(src)
+        bad = np.flatnonzero(~((a == b) | (np.isnan(a) & np.isnan(b))))
+        assert bad.size == 0, (k, bad[:8], a[bad[:4]], b[bad[:4]])
