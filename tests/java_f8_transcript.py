@@ -201,3 +201,73 @@ def extrapolate8(_src, cell, normalX, normalY, _w, _h):
     for i in range(_w * _h):
         if cell[i] == CELL_EMPTY:
             cell[i] = CELL_FLUID
+
+
+# ---- ParticleQuantities bookkeeping after the transfer (particlesToGrid F8:1761): countParticles F8:1595,
+# pruneParticles F8:1610, seedParticles F8:1637.  `Math.random()` is the injected stream of include/incfluid_b200.h
+# (splitmix64 finaliser of seed + golden-ratio * (k + 1), top 24 bits as a float in [0, 1)); `x + (float) random()` is
+# a FLOAT addition (int promoted to float), widened on assignment.
+class InjectedRandom:
+    def __init__(self, seed):
+        self.seed, self.k = seed, 0
+
+    def next_float(self):
+        M = (1 << 64) - 1
+        z = (self.seed + 0x9E3779B97F4A7C15 * (self.k + 1)) & M
+        self.k += 1
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        z = z ^ (z >> 31)
+        return (z >> 40) / 16777216.0               # exact: a 24-bit integer times 2^-24
+
+
+def countParticles(_w, _h, count, posX, posY):      # F8:1595
+    counts = [0] * (_w * _h)
+    for i in range(count):
+        ix = int(posX[i])
+        iy = int(posY[i])
+        if ix >= 0 and iy >= 0 and ix < _w and iy < _h:
+            counts[ix + iy * _w] += 1
+    return counts
+
+
+def pruneParticles(_w, _h, count, posX, posY, properties, counts, _MaxPerCell):      # F8:1610
+    i = 0
+    while i < count:
+        ix = int(posX[i])
+        iy = int(posY[i])
+        idx = ix + iy * _w
+        if ix < 0 and iy < 0 and ix >= _w and iy >= _h:      # sic: && -- never true
+            i += 1
+            continue
+        if counts[idx] > _MaxPerCell:
+            count -= 1
+            j = count
+            posX[i] = posX[j]
+            posY[i] = posY[j]
+            for t in range(len(properties)):
+                properties[t][i] = properties[t][j]
+            counts[idx] -= 1
+            i -= 1
+        i += 1
+    return count
+
+
+def seedParticles(_w, _h, count, maxParticles, posX, posY, properties, quantities, counts, _MinPerCell, rnd, pointInBody):   # F8:1637
+    from java_f1_transcript import f32
+    idx = 0
+    for y in range(_h):
+        for x in range(_w):
+            for i in range(_MinPerCell - counts[idx]):
+                if count == maxParticles:
+                    return count
+                j = count
+                posX[j] = f32(x + rnd.next_float())
+                posY[j] = f32(y + rnd.next_float())
+                if pointInBody(posX[idx], posY[idx]):        # sic: [idx], the cell index
+                    continue
+                for t in range(len(quantities)):
+                    properties[t][j] = quantities[t].lerpGrid(posX[j], posY[j])
+                count += 1
+            idx += 1
+    return count

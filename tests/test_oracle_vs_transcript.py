@@ -391,3 +391,54 @@ def test_f8_empty_cell_extrapolation_matches_python_transcription(ifl, oracle_cl
         a, b = o.read(k), np.array(src)
         bad = np.flatnonzero(~((a == b) | (np.isnan(a) & np.isnan(b))))
         assert bad.size == 0, (k, bad[:8], a[bad[:4]], b[bad[:4]])
+
+
+def test_f8_particle_bookkeeping_matches_python_transcription(ifl, oracle_cls):
+    """countParticles / pruneParticles / seedParticles (F8:1595-1660) after the transfer, on the injected random stream:
+    over-full cells lose particles (swap with the last), under-full cells are re-seeded from the grids."""
+    import java_f8_transcript as j8
+    import java_f3_transcript as j3
+    abi = ifl.abi
+    w, h = 14, 12
+    cfg = abi.default_config(abi.F8_FLIP, w, h)
+    o = oracle_cls(abi, cfg)
+    rng = np.random.default_rng(9)
+    # 40 particles in each of a few cells (pruned to 12), 0-2 in most others (seeded up to 3)
+    xs, ys = [], []
+    for cx, cy in ((3, 4), (7, 7), (10, 2)):
+        xs += list(cx + rng.uniform(0.0, 1.0, 40)); ys += list(cy + rng.uniform(0.0, 1.0, 40))
+    xs += list(rng.uniform(0.0, w, 150)); ys += list(rng.uniform(0.0, h, 150))
+    n = len(xs)
+    parts = {"x": np.array(xs), "y": np.array(ys)}
+    for k in ("d", "t", "u", "v"):
+        parts[k] = rng.normal(size=n)
+    o.write_particles(parts)
+    o.run_stage("particles_to_grid")
+    # transcription: transfer + extrapolation per quantity, then the bookkeeping
+    hx = 1.0 / min(w, h)
+    grids = {"d": (w, h, 0.5, 0.5), "t": (w, h, 0.5, 0.5), "u": (w + 1, h, 0.0, 0.5), "v": (w, h + 1, 0.5, 0.0)}
+    maxp = w * h * cfg.particles_max_per_cell
+    px, py = xs + [0.0] * (maxp - n), ys + [0.0] * (maxp - n)
+    props, quantities = [], []
+    for k, (qw, qh, ox, oy) in grids.items():
+        cell = [j8.CELL_FLUID] * (qw * qh)
+        src = j8.fromParticles(qw, qh, ox, oy, cell, n, px, py, list(parts[k]))
+        j8.extrapolate8(src, cell, [0.0] * (qw * qh), [0.0] * (qw * qh), qw, qh)
+        q = j3.FluidQuantity(qw, qh, ox, oy, hx)
+        q._src = src
+        quantities.append(q)
+        props.append(list(parts[k]) + [0.0] * (maxp - n))
+        assert np.array_equal(o.read(k), np.array(src)), k
+    counts = j8.countParticles(w, h, n, px, py)
+    assert max(counts) > cfg.particles_max_per_cell and min(counts) < cfg.particles_min_per_cell
+    count = j8.pruneParticles(w, h, n, px, py, props, counts, cfg.particles_max_per_cell)
+    assert count < n
+    rnd = j8.InjectedRandom(cfg.rng_seed)
+    count2 = j8.seedParticles(w, h, count, maxp, px, py, props, quantities, counts, cfg.particles_min_per_cell, rnd,
+                              lambda x, y: False)
+    assert count2 > count
+    got = o.read_particles()
+    assert got["x"].size == count2
+    assert np.array_equal(got["x"], np.array(px[:count2])) and np.array_equal(got["y"], np.array(py[:count2]))
+    for k, p in zip(("d", "t", "u", "v"), props):
+        assert np.array_equal(got[k], np.array(p[:count2])), k
