@@ -19,7 +19,7 @@
  *   (iii) solver iteration counts measured independently during the survey
  *         which this restatement must reproduce,
  *   (iv) a second restatement made independently from the Java text -- literal Python
- *        transcriptions of ExplicitFluid1 ... ExplicitFluid7 and physics/solidBodies
+ *        transcriptions of ExplicitFluid1 ... ExplicitFluid8 and physics/solidBodies
  *        (tests/java_f*_transcript.py, tests/java_solid_transcript.py) -- that this library
  *        must reproduce bit for bit on whole timesteps (tests/test_oracle_vs_transcript.py),
  *   (v)  committed golden dumps (tests/golden/) that it must keep reproducing.

@@ -1,9 +1,9 @@
-"""Literal Python transcription of the particle-side pieces of ExplicitFluid8flip.java that can be isolated through the
-C ABI's stages: gridToParticles F8:1748 (the PIC/FLIP blend `p = (1 - alpha) p + lerpGrid`), the particle Runge-Kutta
-F8:1708 (forward in time: `+`), backProject F8:1673 and advect F8:1778, and the particle-to-grid transfer fromParticles
-F8:722 / addSample F8:312 with the EMPTY-cell extrapolation F8:651.  Not transcribed (pinned by the oracle alone): the
-particle bookkeeping on the random stream (init / count / prune / seed F8:1571-1660).
-See java_f1_transcript.py."""
+"""Literal Python transcription of ExplicitFluid8flip.java, made from the Java text -- see java_f1_transcript.py.  First the
+pieces that the C ABI's stages let a test isolate (gridToParticles F8:1748, the particle Runge-Kutta F8:1708 -- forward
+in time: `+` --, backProject F8:1673, advect F8:1778, fromParticles F8:722 / addSample F8:312, the EMPTY-cell
+extrapolation F8:651, count / prune / seed F8:1595-1660 on the injected random stream), then the whole program assembled
+from them and from the ExplicitFluid7 transcription (its projection, heat solve, buoyancy, densities and boundary
+conditions are textually F8's, checked mechanically)."""
 import java_f4_transcript as f4
 from java_f1_transcript import jmax, jmin
 
@@ -271,3 +271,144 @@ def seedParticles(_w, _h, count, maxParticles, posX, posY, properties, quantitie
                 count += 1
             idx += 1
     return count
+
+
+# ---- the whole program: FluidQuantity / ParticleQuantities / FluidSolver of ExplicitFluid8flip.java, assembled from
+# the pieces above and from ExplicitFluid7 (whose projection, heat solve, buoyancy, densities and boundary conditions
+# are textually F8's, checked mechanically).
+import java_f5_transcript as _f5
+import java_f7_transcript as _f7
+
+
+class FluidQuantity(_f5.FluidQuantity):             # F8:196
+    def __init__(self, w, h, ox, oy, hx):
+        super().__init__(w, h, ox, oy, hx)
+        self._old = [0.0] * (w * h)
+        del self._dst
+
+    def copy(self):                                 # F8:340
+        self._old[:] = self._src
+
+    def diff(self, alpha):                          # F8:346
+        for i in range(self._w * self._h):
+            self._src[i] -= (1.0 - alpha) * self._old[i]
+
+    def undiff(self, alpha):                        # F8:355
+        for i in range(self._w * self._h):
+            self._src[i] += (1.0 - alpha) * self._old[i]
+
+    def extrapolate(self):                          # F8:651
+        extrapolate8(self._src, self._cell, self._normalX, self._normalY, self._w, self._h)
+
+    def fromParticles(self, count, posX, posY, prop):   # F8:722
+        self._src = fromParticles(self._w, self._h, self._ox, self._oy, self._cell, count, posX, posY, prop)
+
+
+class ParticleQuantities:                           # F8:1479
+    def __init__(self, w, h, hx, bodies, rnd, avg=4, maxpc=12, minpc=3):
+        self._w, self._h, self._hx, self._bodies, self._rnd = w, h, hx, bodies, rnd
+        self._AvgPerCell, self._MaxPerCell, self._MinPerCell = avg, maxpc, minpc
+        self._maxParticles = w * h * maxpc
+        self._posX = [0.0] * self._maxParticles
+        self._posY = [0.0] * self._maxParticles
+        self._properties, self._quantities = [], []
+        self._counts = [0] * (w * h)
+        self.initParticles()
+
+    def pointInBody(self, x, y):                    # F8:1566
+        return any(b.distance(x * self._hx, y * self._hx) < 0.0 for b in self._bodies)
+
+    def initParticles(self):                        # F8:1571
+        from java_f1_transcript import f32
+        idx = 0
+        for y in range(self._h):
+            for x in range(self._w):
+                i = 0
+                while i < self._AvgPerCell:
+                    self._posX[idx] = f32(x + self._rnd.next_float())
+                    self._posY[idx] = f32(y + self._rnd.next_float())
+                    if self.pointInBody(self._posX[idx], self._posY[idx]):
+                        idx -= 1
+                    i += 1
+                    idx += 1
+        self._particleCount = idx
+
+    def addQuantity(self, q):                       # F8:1740
+        self._quantities.append(q)
+        self._properties.append([0.0] * self._maxParticles)
+
+    def gridToParticles(self, alpha):               # F8:1748
+        gridToParticles(self._quantities, self._properties, self._posX, self._posY, self._particleCount, alpha)
+
+    def particlesToGrid(self):                      # F8:1761
+        for t in range(len(self._quantities)):
+            self._quantities[t].fromParticles(self._particleCount, self._posX, self._posY, self._properties[t])
+            self._quantities[t].extrapolate()
+        self._counts = countParticles(self._w, self._h, self._particleCount, self._posX, self._posY)
+        self._particleCount = pruneParticles(self._w, self._h, self._particleCount, self._posX, self._posY,
+                                             self._properties, self._counts, self._MaxPerCell)
+        self._particleCount = seedParticles(self._w, self._h, self._particleCount, self._maxParticles, self._posX,
+                                            self._posY, self._properties, self._quantities, self._counts,
+                                            self._MinPerCell, self._rnd, self.pointInBody)
+
+    def advect(self, timestep, u, v):               # F8:1778
+        advect(self._posX, self._posY, self._particleCount, timestep, u, v, self._bodies, self._w, self._h, self._hx)
+
+
+class FluidSolver(_f7.FluidSolver):                 # F8:760
+    def __init__(self, w, h, rhoAir, rhoSoot, diffusion, bodies, rnd, avg=4, maxpc=12, minpc=3):     # F8:858
+        super().__init__(w, h, rhoAir, rhoSoot, diffusion, bodies)
+        self._flipAlpha = 0.001
+        self._d = FluidQuantity(w, h, 0.5, 0.5, self._hx)
+        self._t = FluidQuantity(w, h, 0.5, 0.5, self._hx)
+        self._u = FluidQuantity(w + 1, h, 0.0, 0.5, self._hx)
+        self._v = FluidQuantity(w, h + 1, 0.5, 0.0, self._hx)
+        for i in range(w * h):
+            self._t._src[i] = self._tAmb
+        self._qs = ParticleQuantities(w, h, self._hx, bodies, rnd, avg, maxpc, minpc)
+        for q in (self._d, self._t, self._u, self._v):
+            self._qs.addQuantity(q)
+        self._qs.gridToParticles(1.0)
+
+    def update(self, timestep):                     # F8:1306
+        n = self._w * self._h
+        self._d.fillSolidFields(self._bodies)
+        self._t.fillSolidFields(self._bodies)
+        self._u.fillSolidFields(self._bodies)
+        self._v.fillSolidFields(self._bodies)
+        self._qs.particlesToGrid()
+        self._d.copy()
+        self._t.copy()
+        self._u.copy()
+        self._v.copy()
+        self.addInflow(0.45, 0.2, 0.2, 0.05, 1.0, self._tAmb, 0.0, 0.0)
+        self._r[:n] = self._t._src[:n]
+        self.buildHeatDiffusionMatrix(timestep)
+        self.buildPreconditioner()
+        self.project(2000)
+        self.heatIterations, self.heatMaxError = self.lastIterations, self.lastMaxError
+        self._t._src[:n] = self._p[:n]
+        self._t.extrapolate()
+        self.addBuoyancy(timestep)
+        self.setBoundaryCondition()
+        self.buildRhs()
+        self.computeDensities()
+        self.buildPressureMatrix(timestep)
+        self.buildPreconditioner()
+        self.project(2000)
+        self.applyPressure(timestep)
+        self._d.extrapolate()
+        self._u.extrapolate()
+        self._v.extrapolate()
+        self.setBoundaryCondition()
+        a = self._flipAlpha
+        self._d.diff(a)
+        self._t.diff(a)
+        self._u.diff(a)
+        self._v.diff(a)
+        self._qs.gridToParticles(a)
+        self._d.undiff(a)
+        self._t.undiff(a)
+        self._u.undiff(a)
+        self._v.undiff(a)
+        self._qs.advect(timestep, self._u, self._v)

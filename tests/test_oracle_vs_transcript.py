@@ -60,7 +60,7 @@ def test_f3_timesteps_match_python_transcription(ifl, oracle_cls, w, h, rect):
         assert st["residual_pressure"] == j.lastMaxError, (step, st, j.lastMaxError)
         assert j.lastIterations is not None and 1 < j.lastIterations < 600
         assert st["iterations_pressure"] in (j.lastIterations, j.lastIterations + 1), (st, j.lastIterations)
-    assert np.any(np.array(j._p) != 0.0)
+    assert np.any(np.array(j._p) != 0.0) and max(j._d._src) > 0.1 and j.lastIterations > 5
 
 
 class F2Solver(jt.FluidSolver):
@@ -442,3 +442,36 @@ def test_f8_particle_bookkeeping_matches_python_transcription(ifl, oracle_cls):
     assert np.array_equal(got["x"], np.array(px[:count2])) and np.array_equal(got["y"], np.array(py[:count2]))
     for k, p in zip(("d", "t", "u", "v"), props):
         assert np.array_equal(got[k], np.array(p[:count2])), k
+
+
+def test_f8_timesteps_match_python_transcription(ifl, oracle_cls):
+    """Whole ExplicitFluid8flip timesteps (F8:1306) on the injected random stream: particle init, transfer, EMPTY-cell
+    extrapolation, prune / seed, inflow inside update(), heat solve, variable-density projection, PIC/FLIP blend and
+    particle advection -- BASELINE config 4's program."""
+    import java_f8_transcript as j8
+    abi = ifl.abi
+    w, h = 44, 40                                    # fine enough for the inflow rectangle of F8:1330 to hit cell centres
+    cfg = abi.default_config(abi.F8_FLIP, w, h)
+    recs, bodies = _transcript_bodies(ifl, scenes.F7_BODIES)
+    o = oracle_cls(abi, cfg)
+    o.set_bodies(recs)
+    rnd = j8.InjectedRandom(cfg.rng_seed)
+    j = j8.FluidSolver(w, h, cfg.density, cfg.density_soot, cfg.diffusion, bodies, rnd, cfg.particles_avg_per_cell,
+                       cfg.particles_max_per_cell, cfg.particles_min_per_cell)
+    assert cfg.flip_alpha == j._flipAlpha
+    for step in range(6):
+        st = o.update(0.0025)
+        j.update(0.0025)
+        got = o.read_particles()
+        cnt = j._qs._particleCount
+        assert got["x"].size == cnt, (step, got["x"].size, cnt)
+        assert np.array_equal(got["x"], np.array(j._qs._posX[:cnt])), step
+        assert np.array_equal(got["y"], np.array(j._qs._posY[:cnt])), step
+        for k, p in zip(("d", "t", "u", "v"), j._qs._properties):
+            assert np.array_equal(got[k], np.array(p[:cnt])), (step, k)
+        for name, arr in (("d", j._d._src), ("t", j._t._src), ("u", j._u._src), ("v", j._v._src), ("p", j._p), ("r", j._r)):
+            a, b = o.read(name), np.array(arr)
+            bad = np.flatnonzero(~((a == b) | (np.isnan(a) & np.isnan(b))))
+            assert bad.size == 0, (step, name, bad[:5], a[bad[:3]], b[bad[:3]])
+        assert st["residual_pressure"] == j.lastMaxError and st["residual_heat"] == j.heatMaxError, (step, st)
+    assert np.any(np.array(j._p) != 0.0) and max(j._d._src) > 0.1 and j.lastIterations > 5
