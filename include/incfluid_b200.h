@@ -273,13 +273,13 @@ int ifl_last_timing(ifl_solver* s, double out_ms[3]);
  * returns the average device time per launch of kernel `which` over the samples collected
  * since the last ifl_set_profiling(s, 1). */
 typedef enum ifl_kernel {
-    IFL_KERNEL_MATVEC_DOT = 0,    /* matrixVectorProduct + dotProduct        F3:544 F3:532 */
-    IFL_KERNEL_UPDATE_PR = 1,     /* scaledAdd(r) + infinityNorm             F3:608 F3:579 */
-    IFL_KERNEL_PRECON_FWD = 2,    /* applyPreconditioner, forward sweep      F3:496-507   */
-    IFL_KERNEL_PRECON_BWD = 3,    /* applyPreconditioner, backward sweep + dotProduct F3:509-521 */
-    IFL_KERNEL_UPDATE_S = 4,      /* scaledAdd(p) F3:607 (deferred) + scaledAdd(s, z, s, beta) F3:626 */
-    IFL_KERNEL_GS_SWEEP = 5,      /* one Gauss-Seidel sweep                  F1:383-417 */
-    IFL_KERNEL_COUNT = 6
+    /* the three kernels of one MIC(0)-PCG iteration (F3:603-628) */
+    IFL_KERNEL_STEP_A = 0,        /* scaledAdd(p) F3:607 + scaledAdd(s,z,s,beta) F3:626 of the previous iteration,
+                                   * matrixVectorProduct F3:544 + dotProduct F3:532 */
+    IFL_KERNEL_PRECON_FWD = 1,    /* scaledAdd(r) F3:608 + infinityNorm F3:579 + applyPreconditioner forward sweep F3:496-507 */
+    IFL_KERNEL_PRECON_BWD = 2,    /* applyPreconditioner backward sweep F3:509-521 + dotProduct F3:625 */
+    IFL_KERNEL_GS_SWEEP = 3,      /* one Gauss-Seidel sweep                  F1:383-417 */
+    IFL_KERNEL_COUNT = 4
 } ifl_kernel;
 int ifl_set_profiling(ifl_solver* s, int32_t enable);
 int ifl_kernel_timing(ifl_solver* s, int32_t which, double* avg_ms, int32_t* samples);

@@ -80,7 +80,7 @@ STAGES = {
     "particles_to_grid": 22, "grid_to_particles": 23, "advect_particles": 24,
 }
 
-KERNELS = {"matvec_dot": 0, "update_pr": 1, "precon_fwd": 2, "precon_bwd": 3, "update_s": 4, "gs_sweep": 5}
+KERNELS = {"step_a": 0, "precon_fwd": 1, "precon_bwd": 2, "gs_sweep": 3}
 
 _dp = C.POINTER(C.c_double)
 

@@ -27,6 +27,10 @@ static void set_err(const char* fmt, const char* a, const char* b, int line) {
             return IFL_ERR_CUDA;                                                          \
         }                                                                                 \
     } while (0)
+#define COMM(call)                                                                        \
+    do {                                                                                  \
+        if ((call) != 0) { snprintf(g_err, sizeof g_err, "%s", comm_last_error()); return IFL_ERR_COMM; } \
+    } while (0)
 #define INVALID(msg)                                                                      \
     do { snprintf(g_err, sizeof g_err, "invalid argument: %s", msg); return IFL_ERR_INVALID; } while (0)
 
@@ -169,6 +173,7 @@ void ifl_destroy(ifl_solver* s) {
     comm_destroy(s->comm);
     if (s->sx.bnd_f) cudaFree(s->sx.bnd_f);
     if (s->sx.strip_part) cudaFree(s->sx.strip_part);
+    if (s->sx.strip_ctr) cudaFree(s->sx.strip_ctr);
     if (s->sx.rank_max) cudaFree(s->sx.rank_max);
     if (s->sx.rowbuf) cudaFree(s->sx.rowbuf);
     if (s->sx.partials) cudaFree(s->sx.partials);
@@ -221,21 +226,21 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     g.nstrips = (s->h + 31) / 32;
     g.tl = (((s->w + IFL_SKB - 1) / IFL_SKB + 31 + 7) / 8) * 8 + 8;      /* m-rows: ceil(w/SKB)+31, padded to the staging block */
     g.ss = (long long)g.tl * 32 * IFL_SKB;
-    /* slab decomposition: rank r owns the strips [r*chunk, min((r+1)*chunk, nstrips)); arrays hold chunk*world strips */
+    /* slab decomposition: balanced contiguous ranges of strips (slab_range): no rank is ever empty */
     const int world = cfg->world_size;
-    const int chunk = (g.nstrips + world - 1) / world;
-    const int strips_alloc = chunk * world;
-    g.s0 = cfg->rank * chunk;
-    g.s1 = g.s0 + chunk < g.nstrips ? g.s0 + chunk : g.nstrips;
+    const int strips_alloc = g.nstrips;
+    slab_range(g.nstrips, world, cfg->rank, &g.s0, &g.s1);
     g.total = (long long)strips_alloc * g.ss;
     /* one all-zero strip before and after each vector: the wavefront kernels read the
      * "row above the first" / "row below the last" from there instead of branching */
     const size_t guard = (size_t)g.ss;
     const size_t per = (size_t)g.total + 2 * guard;
-    CU(cudaMalloc(&s->skew_block, sizeof(double) * per * 8));
-    CU(cudaMemset(s->skew_block, 0, sizeof(double) * per * 8));
-    double** vecs[8] = {&s->sx.r, &s->sx.p, &s->sx.z, &s->sx.s, &s->sx.adiag, &s->sx.aplusx, &s->sx.aplusy, &s->sx.precon};
-    for (int i = 0; i < 8; i++) *vecs[i] = s->skew_block + per * i + guard;
+    const int nvec = 10;
+    CU(cudaMalloc(&s->skew_block, sizeof(double) * per * nvec));
+    CU(cudaMemset(s->skew_block, 0, sizeof(double) * per * nvec));
+    double** vecs[nvec] = {&s->sx.r, &s->sx.p, &s->sx.zb[0], &s->sx.zb[1], &s->sx.sb[0], &s->sx.sb[1],
+                           &s->sx.adiag, &s->sx.aplusx, &s->sx.aplusy, &s->sx.precon};
+    for (int i = 0; i < nvec; i++) *vecs[i] = s->skew_block + per * i + guard;
     const size_t npack = (size_t)strips_alloc * g.tl * 32 * IFL_SKB * 3;
     CU(cudaMalloc(&s->sx.pack_f, sizeof(double) * npack));
     CU(cudaMalloc(&s->sx.pack_b, sizeof(double) * npack));
@@ -248,9 +253,11 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     s->sx.strips_alloc = strips_alloc;
     CU(cudaMalloc(&s->sx.strip_part, sizeof(double) * strips_alloc));
     CU(cudaMemset(s->sx.strip_part, 0, sizeof(double) * strips_alloc));
+    CU(cudaMalloc(&s->sx.strip_ctr, sizeof(unsigned) * strips_alloc));
+    CU(cudaMemset(s->sx.strip_ctr, 0, sizeof(unsigned) * strips_alloc));
     CU(cudaMalloc(&s->sx.rank_max, sizeof(unsigned long long) * (world > 16 ? world : 16) * 8));
     CU(cudaMemset(s->sx.rank_max, 0, sizeof(unsigned long long) * (world > 16 ? world : 16) * 8));
-    CU(cudaMalloc(&s->sx.rowbuf, sizeof(double) * 4 * g.w));
+    CU(cudaMalloc(&s->sx.rowbuf, sizeof(double) * 8 * g.w));
     s->sx.comm = nullptr; s->sx.peer_bnd_f_next = nullptr; s->sx.peer_bnd_b_prev = nullptr;
     if (world > 1) {
         if (comm_init(s->comm, cfg->rank, world, cfg->comm_id, s->stream)) {
@@ -268,7 +275,6 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     }
     s->sx.npartials = solve_partials_needed(g);
     CU(cudaMalloc(&s->sx.partials, sizeof(double) * s->sx.npartials));
-    s->sx.stripdot = nullptr;
     CU(cudaMalloc(&s->sx.sc, sizeof(SolveScalars)));
     CU(cudaMemset(s->sx.sc, 0, sizeof(SolveScalars)));
     CU(cudaMalloc(&s->d_maxbits, sizeof(unsigned long long)));
@@ -305,6 +311,17 @@ int ifl_create(const ifl_config* cfg, ifl_solver** out) {
     if (cfg->w < 2 || cfg->h < 2) INVALID("grid must be at least 2x2");
     if (cfg->variant < IFL_F1_MATRIXLESS || cfg->variant > IFL_F8_FLIP) INVALID("unknown variant");
     if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) INVALID("bad rank / world_size");
+    if (cfg->solver_limit < 0) INVALID("solver_limit < 0");
+    if ((long long)(cfg->w + 1) * (long long)(cfg->h + 1) > 2147483647LL) INVALID("grid too large: (w+1)*(h+1) must fit a 32-bit int, like the reference's array indices");
+    if (cfg->variant == IFL_F8_FLIP) {
+        /* ParticleQuantities sizes every particle array with w*h*_MaxPerCell (F8:1549) and indexes it with ints */
+        if (cfg->particles_avg_per_cell <= 0 || cfg->particles_max_per_cell <= 0 || cfg->particles_min_per_cell < 0)
+            INVALID("particle counts per cell must be positive");
+        if (cfg->particles_avg_per_cell > cfg->particles_max_per_cell) INVALID("particles_avg_per_cell > particles_max_per_cell");
+        if (cfg->particles_min_per_cell > cfg->particles_max_per_cell) INVALID("particles_min_per_cell > particles_max_per_cell");
+        if ((long long)cfg->w * cfg->h * cfg->particles_max_per_cell > 2147483647LL)
+            INVALID("w*h*particles_max_per_cell must fit a 32-bit int (F8:1549)");
+    }
     if (cfg->world_size > 1) {
         if (cfg->variant != IFL_F3_CONJUGATE_GRADIENTS) {
             snprintf(g_err, sizeof g_err, "slab decomposition is implemented for variant 3 (MIC(0)-PCG), not for variant %d", cfg->variant);
@@ -382,7 +399,7 @@ static int run_solver_loop(ifl_solver* s, double timestep) {
     bool done = false;
     while (enq < limit && !done) {
         int n = limit - enq < chunk ? limit - enq : chunk;
-        if (pcg) pcg_enqueue_iterations(c, n);
+        if (pcg) COMM(pcg_enqueue_iterations(c, n));
         else gs_enqueue_iterations(c, enq, n, gs_scale);
         enq += n;
         int slot = nchunks & 1;
@@ -428,17 +445,19 @@ static int stage_build_rhs(ifl_solver* s) {
 static int stage_build_matrix(ifl_solver* s, double timestep) {
     double scale = timestep / (s->cfg.density * s->hx * s->hx);             /* F3:436 */
     launch_build_matrix_f3(s->stream, s->sx.g, s->sx.adiag, s->sx.aplusx, s->sx.aplusy, scale);
-    s->sx.const_matrix = getenv("IFL_NO_CONST_MATRIX") ? 0 : 1;   /* the arrays are still filled: MIC(0) build and read_field use them */
+    s->sx.const_matrix = 1;       /* the arrays are still filled: MIC(0) build and read_field use them; writing one of
+                                   * them through ifl_write_field switches the solver to the array-reading kernels */
     s->sx.const_scale = scale;
     s->launches++;
     return IFL_OK;
 }
 static int stage_project(ifl_solver* s, double timestep) {
     SolveCtx& c = s->sx;
-    if (uses_pcg(s)) pcg_enqueue_init(c); else gs_enqueue_begin(c);
+    if (uses_pcg(s)) COMM(pcg_enqueue_init(c)); else gs_enqueue_begin(c);
     int rc = run_solver_loop(s, timestep);
     if (rc) return rc;
-    pcg_enqueue_finish(c, s->cfg.solver_limit);
+    if (uses_pcg(s)) { COMM(pcg_enqueue_finish(c, s->cfg.solver_limit)); COMM(pcg_gather_pressure(c)); }
+    else gs_enqueue_finish(c, s->cfg.solver_limit);
     return IFL_OK;
 }
 static int stage_apply_pressure(ifl_solver* s, double timestep) {
@@ -766,10 +785,10 @@ int ifl_run_stage(ifl_solver* s, int32_t stage, double timestep, ifl_step_status
         case IFL_STAGE_COMPUTE_DENSITIES: if (!has_vardens(s)) goto unsupported; rc = stage_compute_densities(s); break;
         case IFL_STAGE_APPLY_PRECON:
             if (!uses_pcg(s)) goto unsupported;
-            launch_apply_precon(s->sx, s->sx.r, s->sx.z, 0); break;
+            COMM(launch_apply_precon(s->sx)); break;
         case IFL_STAGE_MATVEC:
             if (!uses_pcg(s)) goto unsupported;
-            launch_matvec(s->sx, s->sx.s, s->sx.z); break;
+            COMM(launch_matvec(s->sx)); break;
         default: goto unsupported;
     }
     if (rc) return rc;
@@ -820,8 +839,12 @@ static int field_ptr(ifl_solver* s, int32_t field, void** ptr, size_t* count, in
         case IFL_FIELD_VDENSITY: if (!has_vardens(s)) return bad(); *ptr = s->vdens; *count = s->v.count(); return IFL_OK;
         case IFL_FIELD_P: *ptr = s->sx.p; break;
         case IFL_FIELD_R: *ptr = s->sx.r; break;
-        case IFL_FIELD_Z: *ptr = s->sx.z; break;
-        case IFL_FIELD_S: *ptr = s->sx.s; break;
+        case IFL_FIELD_Z: case IFL_FIELD_S: {          /* the current generation (SolveScalars.zpar) */
+            const int zp = solve_parity(s->sx);
+            if (zp < 0) { snprintf(g_err, sizeof g_err, "cannot read the solver state from the device"); return IFL_ERR_CUDA; }
+            *ptr = field == IFL_FIELD_Z ? s->sx.zb[zp] : s->sx.sb[zp];
+            break;
+        }
         case IFL_FIELD_PRECON: *ptr = s->sx.precon; break;
         case IFL_FIELD_ADIAG: *ptr = s->sx.adiag; break;
         case IFL_FIELD_APLUSX: *ptr = s->sx.aplusx; break;
@@ -1016,8 +1039,9 @@ int ifl_wavefront_trace(ifl_solver* s, int64_t* out, size_t capacity) {
     CU(cudaMalloc(&d, sizeof(long long) * n));
     CU(cudaMemsetAsync(d, 0, sizeof(long long) * n, s->stream));
     s->sx.trace = d;
-    launch_apply_precon(s->sx, s->sx.r, s->sx.z, 0);
+    const int trc = launch_apply_precon(s->sx);
     s->sx.trace = nullptr;
+    if (trc) { cudaFree(d); COMM(trc); }
     CU(cudaMemcpyAsync(out, d, sizeof(long long) * n, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaFree(d));

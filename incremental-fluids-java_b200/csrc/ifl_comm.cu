@@ -6,8 +6,9 @@
  * What crosses NVLink per PCG iteration:
  *   - the strip hand-over of the two triangular sweeps: the last strip of rank r stores its edge row with plain
  *     8-byte stores straight into the flag-in-data inbox of rank r+1 (peer memory, IPC-mapped);
- *   - one boundary row of s in each direction (ncclSend/ncclRecv) for the mat-vec;
- *   - per-strip partial sums of the two dot products and the per-rank max (ncclAllGather), summed by every rank in
+ *   - one boundary row of z and of s in each direction (ncclSend/ncclRecv) for the fused s-update + mat-vec;
+ *   - per-strip partial sums of the two dot products (grouped ncclBroadcast of every rank's strip range) and the
+ *     per-rank max (ncclAllGather), summed by every rank in
  *     global strip order -- so the result does not depend on the number of GPUs.
  */
 #include <dlfcn.h>
@@ -24,6 +25,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -43,6 +45,7 @@ static const char* nccl_load() {
     IFL_SYM(CommInitRank, "ncclCommInitRank")
     IFL_SYM(CommDestroy, "ncclCommDestroy")
     IFL_SYM(AllGather, "ncclAllGather")
+    IFL_SYM(Broadcast, "ncclBroadcast")
     IFL_SYM(Send, "ncclSend")
     IFL_SYM(Recv, "ncclRecv")
     IFL_SYM(GroupStart, "ncclGroupStart")
@@ -106,6 +109,19 @@ int comm_map_neighbour_inboxes(Comm& c, void* inbox_base, void* scratch_dev /* >
 
 int comm_all_gather(Comm& c, const void* send, void* recv, size_t bytes_per_rank) {
     NC(g_nccl.AllGather(send, recv, bytes_per_rank, ncclUint8, (ncclComm_t)c.nccl, c.stream));
+    return 0;
+}
+/* Per-strip values (partial sums of a dot product): every rank broadcasts the range it owns, in place, as one grouped
+ * operation.  The ranges of the balanced partition differ by at most one strip, so an all-gather does not fit. */
+int comm_all_gather_strips(Comm& c, double* strip_vals, int nstrips, size_t per_strip) {
+    NC(g_nccl.GroupStart());
+    for (int r = 0; r < c.world; r++) {
+        int s0, s1;
+        slab_range(nstrips, c.world, r, &s0, &s1);
+        NC(g_nccl.Broadcast(strip_vals + (size_t)s0 * per_strip, strip_vals + (size_t)s0 * per_strip, (size_t)(s1 - s0) * per_strip, ncclFloat64, r,
+                             (ncclComm_t)c.nccl, c.stream));
+    }
+    NC(g_nccl.GroupEnd());
     return 0;
 }
 /* exchange one packed row with each neighbour: send_up -> rank-1, send_down -> rank+1 */

@@ -53,7 +53,9 @@ struct SolveScalars {
     unsigned int ctr_b;
     unsigned int ticket_f;  /* strip tickets of the forward / backward wavefront */
     unsigned int ticket_b;
-    int p_pending;       /* 1: r has been updated by this iteration but its p += alpha*s has not been applied yet */
+    int p_pending;       /* 1: r has been updated by the last iteration but its p += alpha*s has not been applied yet */
+    unsigned int ctr_c;  /* strips that finished the fused r update of the forward sweep */
+    int zpar;            /* which generation of the z / s buffers is current (k_step_a flips it; never reset) */
 };
 
 /* slab decomposition (ifl_comm.cu): rank r owns the strips [s0, s1) of the pressure solve */
@@ -70,6 +72,14 @@ int comm_init(Comm& c, int rank, int world, const unsigned char id_bytes[128], c
 void comm_destroy(Comm& c);
 int comm_map_neighbour_inboxes(Comm& c, void* inbox_base, void* scratch_dev);
 int comm_all_gather(Comm& c, const void* send, void* recv, size_t bytes_per_rank);
+/* every rank's own range of per-strip values -> every rank (in place; ranges follow slab_range) */
+int comm_all_gather_strips(Comm& c, double* strip_vals, int nstrips, size_t per_strip);
+/* balanced slab partition: the first nstrips % world ranks own one strip more; never empty when nstrips >= world */
+static inline void slab_range(int nstrips, int world, int rank, int* s0, int* s1) {
+    const int base = nstrips / world, rem = nstrips % world;
+    *s0 = rank * base + (rank < rem ? rank : rem);
+    *s1 = *s0 + base + (rank < rem ? 1 : 0);
+}
 int comm_exchange_rows(Comm& c, const double* send_up, double* recv_up, const double* send_down, double* recv_down, size_t n);
 
 /* event-sampled kernel timing (ifl_set_profiling / ifl_kernel_timing) */
@@ -87,14 +97,15 @@ struct Profiler {
 struct SolveCtx {
     SkewGeom g;
     /* skewed N-vectors */
-    double *r, *p, *z, *s, *adiag, *aplusx, *aplusy, *precon;
+    double *r, *p, *adiag, *aplusx, *aplusy, *precon;
+    double *zb[2], *sb[2];   /* z and s, two generations each (k_step_a reads one and writes the other; SolveScalars.zpar) */
+    unsigned* strip_ctr;     /* per-strip "last block" counters of the two-level reductions, [strips_alloc] */
     /* per-solve packed operands of the triangular sweeps (products aPlusX*precon, aPlusY*precon, precon) */
     double *pack_f, *pack_b;   /* [strip][tl/16][3][16][32], see k_precon_coeffs */
     /* strip boundary rows (flag-in-data), [nstrips][w] each; two sets for GS parity */
     double *bnd_f, *bnd_b;
     double *partials;     /* per-block partial sums */
     int npartials;
-    double *stripdot;     /* per-strip partial of the dot fused into the backward sweep */
     SolveScalars* sc;
     double tolerance;
     double mic_tau, mic_sigma;
@@ -110,10 +121,10 @@ struct SolveCtx {
     Comm* comm;              /* nullptr on a single GPU */
     double* peer_bnd_f_next; /* rank+1's forward inbox (its bnd_f), IPC mapped */
     double* peer_bnd_b_prev; /* rank-1's backward inbox (its bnd_b) */
-    double* rowbuf;          /* 4 packed rows of w doubles: send up, send down, recv up, recv down */
+    double* rowbuf;          /* 8 packed rows of w doubles: z,s of my first / last row, z,s received from above / below */
     double* strip_part;      /* per-strip partial sums, [strips_alloc] */
     unsigned long long* rank_max;   /* per-rank max bits, [world] */
-    int strips_alloc;        /* chunk * world >= nstrips */
+    int strips_alloc;        /* strips every vector is allocated for (the whole grid) */
     long long* trace;     /* diagnostic: per-strip timestamps of the next apply_precon, or nullptr */
 };
 
@@ -191,13 +202,16 @@ cudaError_t flip_extrapolate(FlipCtx& f, cudaStream_t st, const SolidQ& q, doubl
                              unsigned int* d_progress, unsigned int* h_progress, int force_sequential, unsigned long long* launches);
 
 /* ---- solver kernels: ifl_solve_kernels.cu ---- */
+/* the int-returning helpers return 0, or -1 after a communication failure (comm_last_error()) */
 int  solve_partials_needed(const SkewGeom& g);
-void launch_build_precon(SolveCtx& c);
-void launch_apply_precon(SolveCtx& c, const double* src, double* dst, int with_dot_mode);
-void pcg_enqueue_init(SolveCtx& c);
-void pcg_enqueue_iterations(SolveCtx& c, int n);
-void pcg_enqueue_finish(SolveCtx& c, int limit);
-void launch_matvec(SolveCtx& c, const double* b, double* dst);
+int  solve_parity(SolveCtx& c);            /* current generation of z / s (synchronises the stream), -1 on error */
+int  launch_build_precon(SolveCtx& c);
+int  launch_apply_precon(SolveCtx& c);     /* z = M^-1 r on the current generation */
+int  pcg_enqueue_init(SolveCtx& c);
+int  pcg_enqueue_iterations(SolveCtx& c, int n);
+int  pcg_enqueue_finish(SolveCtx& c, int limit);
+int  pcg_gather_pressure(SolveCtx& c);
+int  launch_matvec(SolveCtx& c);           /* z = A s on the current generation */
 void gs_enqueue_begin(SolveCtx& c);
 void gs_enqueue_iterations(SolveCtx& c, int first_iter, int n, double scale);
 void gs_enqueue_finish(SolveCtx& c, int limit);

@@ -82,45 +82,67 @@ __device__ __forceinline__ void apply_dot_result(SolveScalars* sc, int mode, dou
     }
 }
 
-/* "last block" reduction, fixed order and independent of the slab decomposition: the partials of the blocks of one
- * strip are added in block order (per-strip sum), then the strips are added in global strip order.  On several GPUs
- * the second level runs in k_apply_dot after the per-strip sums of all ranks have been all-gathered. */
-__device__ __forceinline__ void finish_partials(double blocksum, double* partials, const SkewGeom& g, double* strip_part,
-                                                SolveScalars* sc, int mode, int single_gpu, bool* s_last) {
-    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
-    const int nblocks = gridDim.x * gridDim.y;
-    if (threadIdx.x == 0) {
-        partials[bid] = blocksum;
-        __threadfence();
-        unsigned prev = atomicAdd(&sc->ctr_a, 1u);
-        *s_last = (prev == (unsigned)nblocks - 1u);
-    }
-    __syncthreads();
-    if (*s_last) {
-        __threadfence();
-        for (int ks = threadIdx.x; ks < (int)gridDim.y; ks += EW_THREADS) {
-            double v = 0.0;
-            for (int j = 0; j < (int)gridDim.x; j++) v += ld_cg(partials + ks * gridDim.x + j);
-            strip_part[g.s0 + ks] = v;
-        }
+/* Sum of the per-strip partial sums in global strip order by the whole block: the values are staged through shared
+ * memory 256 at a time and added by thread 0 in ascending strip order (the result, valid in thread 0, does not depend on
+ * how many GPUs or blocks produced the partials). */
+__device__ __forceinline__ double ordered_strip_total(const double* strip_part, int nstrips, double* s_buf) {
+    double total = 0.0;
+    for (int base = 0; base < nstrips; base += EW_THREADS) {
+        const int kk = base + (int)threadIdx.x;
+        s_buf[threadIdx.x] = kk < nstrips ? ld_cg(strip_part + kk) : 0.0;
         __syncthreads();
         if (threadIdx.x == 0) {
-            if (single_gpu) {
-                double total = 0.0;
-                for (int kk = 0; kk < g.nstrips; kk++) total += strip_part[kk];
-                apply_dot_result(sc, mode, total);
-            }
-            sc->ctr_a = 0;
+            const int n = nstrips - base < EW_THREADS ? nstrips - base : EW_THREADS;
+            for (int i = 0; i < n; i++) total += s_buf[i];
         }
+        __syncthreads();
     }
+    return total;
+}
+
+/* Two-level "last block" reduction, fixed order and independent of the slab decomposition: the partials of the blocks
+ * of one strip are added in block order by the last block of THAT strip (one counter per strip, so no address is hit by
+ * more than gridDim.x atomics), then the last strip to finish adds the strips in global strip order.  On several GPUs
+ * the second level runs in k_apply_dot after the per-strip sums of all ranks have been all-gathered.  Returns true in
+ * every thread of the one block that finishes last (it owns the kernel's epilogue). */
+__device__ __forceinline__ bool finish_partials(double blocksum, double* partials, const SkewGeom& g, double* strip_part,
+                                                unsigned* strip_ctr, SolveScalars* sc, int mode, int single_gpu,
+                                                int* s_flag, double* s_buf) {
+    const int gx = (int)gridDim.x, by = (int)blockIdx.y;
+    if (threadIdx.x == 0) {
+        int flag = 0;
+        partials[(long long)by * gx + blockIdx.x] = blocksum;
+        __threadfence();
+        const unsigned prev = atomicAdd(&strip_ctr[by], 1u);
+        if (prev == (unsigned)gx - 1u) {
+            __threadfence();
+            double v = 0.0;
+            for (int j = 0; j < gx; j++) v += ld_cg(partials + (long long)by * gx + j);
+            strip_part[g.s0 + by] = v;
+            strip_ctr[by] = 0u;
+            __threadfence();
+            const unsigned prev2 = atomicAdd(&sc->ctr_a, 1u);
+            if (prev2 == gridDim.y - 1u) flag = 1;
+        }
+        *s_flag = flag;
+    }
+    __syncthreads();
+    if (!*s_flag) return false;
+    __threadfence();
+    if (single_gpu && mode != DOT_NONE) {
+        const double total = ordered_strip_total(strip_part, g.nstrips, s_buf);
+        if (threadIdx.x == 0) apply_dot_result(sc, mode, total);
+    }
+    if (threadIdx.x == 0) sc->ctr_a = 0;
+    return true;
 }
 /* second level of a distributed dot product: strips in global order (every rank computes the same bits) */
-__global__ void k_apply_dot(SkewGeom g, const double* __restrict__ strip_part, SolveScalars* sc, int mode, int check_done) {
+__global__ void __launch_bounds__(EW_THREADS)
+k_apply_dot(SkewGeom g, const double* __restrict__ strip_part, SolveScalars* sc, int mode, int check_done) {
+    __shared__ double s_buf[EW_THREADS];
     if (check_done && sc->done) return;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double total = 0.0;
-    for (int kk = 0; kk < g.nstrips; kk++) total += strip_part[kk];
-    apply_dot_result(sc, mode, total);
+    const double total = ordered_strip_total(strip_part, g.nstrips, s_buf);
+    if (threadIdx.x == 0) apply_dot_result(sc, mode, total);
 }
 /* convergence decision from the per-rank maxima (F3:609-619), identical on every rank */
 __global__ void k_apply_max(const unsigned long long* __restrict__ rank_max, int world, SolveScalars* sc, double tol, int init) {
@@ -135,21 +157,15 @@ __global__ void k_apply_max(const unsigned long long* __restrict__ rank_max, int
     if (err != err) { sc->done = 1; sc->nan = 1; }
 }
 
-/* z = A s fused with the partial sums of z.s   (matrixVectorProduct F3:544, dotProduct F3:532).
+/* matrixVectorProduct F3:544 on its own (IFL_STAGE_MATVEC; the solver loop uses k_step_a).
  * CONSTM (F3, whose matrix buildPressureMatrix F3:435 fills from the grid position alone): the coefficients are
  * re-derived per cell instead of read -- aDiag is `scale` added once per in-grid neighbour (the same additions, in the
  * same order, as k_build_matrix_f3), aPlusX / aPlusY are -scale wherever the guarded term exists -- so the kernel moves
  * 16 instead of 40 bytes per cell and produces the same bits. */
 template <bool CONSTM>
 __global__ void __launch_bounds__(EW_THREADS)
-k_matvec_dot(SkewGeom g, const double* __restrict__ adiag, const double* __restrict__ ax,
-             const double* __restrict__ ay, const double* __restrict__ b, double* __restrict__ dst,
-             double* partials, double* strip_part, SolveScalars* sc, int dot_mode, int check_done,
-             const unsigned char* __restrict__ fl, int single_gpu, double cscale) {
-    if (check_done && sc->done) return;
-    __shared__ double smem8[8];
-    __shared__ bool s_last;
-    double acc = 0.0;
+k_matvec(SkewGeom g, const double* __restrict__ adiag, const double* __restrict__ ax,
+         const double* __restrict__ ay, const double* __restrict__ b, double* __restrict__ dst, double cscale) {
     const double ms = -cscale;
     IFL_EW_LOOP_BEGIN(g)
         IFL_EW_NEIGHBOURS(g)
@@ -175,47 +191,85 @@ k_matvec_dot(SkewGeom g, const double* __restrict__ adiag, const double* __restr
                 if (y_ < g.h - 1) tv += ay[i_] * b[nd_];
             }
             dst[i_] = tv;                                   /* matrixVectorProduct is never masked (F6:1011) */
-            if (fl == nullptr || fl[i_]) acc += tv * bc;    /* dotProduct: fluid cells only from F6 on (F6:999) */
         }
     IFL_EW_LOOP_END
-    if (dot_mode == DOT_NONE) return;
-    double bs = block_sum_256(acc, smem8);
-    finish_partials(bs, partials, g, strip_part, sc, dot_mode, single_gpu, &s_last);
 }
 
-/* scaledAdd(_p, _p, _s, alpha) F3:607 (masked F6:1041) of the LAST iteration of a solve.  Inside the loop the update
- * of p rides on k_update_sp (p is not read by anything else in the loop, so it only has to happen before s is
- * overwritten); the iteration that converges never reaches k_update_sp, and its update is applied here. */
+/* First kernel of a PCG iteration: everything between two global reductions that is element-wise or a 5-point
+ * stencil, in ONE pass over the vectors --
+ *     p += alpha*s            scaledAdd(_p, _p, _s, alpha)   F3:607 of the PREVIOUS iteration (deferred: nothing in
+ *                             the loop reads p, so the update only has to happen before s is overwritten; the last
+ *                             iteration's update is applied by k_update_p)
+ *     s  = z + beta*s         scaledAdd(_s, _z, _s, beta)    F3:626 of the previous iteration
+ *     z  = A s                matrixVectorProduct            F3:604
+ *     z.s                     dotProduct                     F3:605  -> alpha = sigma / (z.s)
+ * The mat-vec needs the new s of the four neighbours: it is recomputed from z and the old s with the very same two
+ * operations (z[n] + s[n]*beta), so every s value has the bits the reference's separate loop produces.  Because cells
+ * read their neighbours' OLD z and s, the kernel cannot work in place: z and s live in two buffers each and the kernel
+ * reads generation `zpar`, writes generation `zpar ^ 1` and flips `zpar` (a device scalar: the host enqueues blindly).
+ * Masked scaledAdd (F6:1041) leaves s unchanged outside the fluid -- copied here; the mat-vec is never masked.
+ * In the first iteration (iterations == 0) s already is the copy of z made by k_init_s (F3:596): s is carried over
+ * unchanged and nothing is added to p.
+ * Also re-arms the strip boundary rows and tickets of the two sweeps that follow.
+ * Moves 48 B/cell for F3 (R z,s,p  W s,p,z), against 16 + 40 for separate mat-vec and update kernels. */
+template <bool CONSTM>
 __global__ void __launch_bounds__(EW_THREADS)
-k_update_p(SkewGeom g, double* __restrict__ p, const double* __restrict__ s, const SolveScalars* sc,
-           const unsigned char* __restrict__ fl) {
-    if (!sc->p_pending) return;
-    const double alpha = sc->alpha;
-    IFL_EW_LOOP_BEGIN(g)
-        if (ok_ && (fl == nullptr || fl[i_])) p[i_] = p[i_] + s[i_] * alpha;
-    IFL_EW_LOOP_END
-}
-
-/* r -= alpha z ; maxError = infinityNorm(r)   (F3:608, scaledAdd F3:570, infinityNorm F3:579); the p += alpha s of
- * F3:607 is flagged as pending (k_update_sp / k_update_p).  Also re-arms the boundary rows and tickets of the two sweeps
- * that follow.  The last block decides convergence (F3:609-619). */
-__global__ void __launch_bounds__(EW_THREADS)
-k_update_pr(SkewGeom g, double* __restrict__ r,
-            const double* __restrict__ z, double* __restrict__ bnd_f, double* __restrict__ bnd_b,
-            SolveScalars* sc, double tol, const unsigned char* __restrict__ fl,
-            unsigned long long* rank_max, int rank, int single_gpu) {
+k_step_a(SkewGeom g, const double* __restrict__ adiag, const double* __restrict__ ax, const double* __restrict__ ay,
+         double* z0, double* z1, double* s0, double* s1, double* __restrict__ p,
+         double* partials, double* strip_part, unsigned* strip_ctr, SolveScalars* sc, int dot_mode,
+         const unsigned char* __restrict__ fl, int single_gpu, double cscale,
+         double* __restrict__ bnd_f, double* __restrict__ bnd_b) {
     if (sc->done) return;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) sc->p_pending = 1;
-    __shared__ unsigned s_max[8];
-    __shared__ bool s_last;
-    const double nalpha = sc->neg_alpha;
-    unsigned m = 0;
+    __shared__ double s_buf[EW_THREADS];
+    __shared__ double smem8[8];
+    __shared__ int s_flag;
+    const int zp = sc->zpar;
+    const bool first = sc->iterations == 0;
+    const double* __restrict__ zin = zp ? z1 : z0;
+    const double* __restrict__ sin_ = zp ? s1 : s0;
+    double* __restrict__ zout = zp ? z0 : z1;
+    double* __restrict__ sout = zp ? s0 : s1;
+    const double beta = sc->beta, alpha = sc->alpha;
+    const double ms = -cscale;
+    double acc = 0.0;
+    /* s of cell i after F3:626 (masked F6:1041): the reference's two operations, or the untouched old value */
+    auto s_new = [&](long long i) -> double {
+        const double sv = sin_[i];
+        if (first || (fl != nullptr && !fl[i])) return sv;
+        return zin[i] + sv * beta;
+    };
     IFL_EW_LOOP_BEGIN(g)
-        if (ok_ && (fl == nullptr || fl[i_])) {
-            double rv = r[i_] + z[i_] * nalpha;
-            r[i_] = rv;
-            unsigned bits = absf_bits(rv);
-            m = bits > m ? bits : m;
+        IFL_EW_NEIGHBOURS(g)
+        if (ok_) {
+            const bool act = fl == nullptr || fl[i_];
+            const double sold = sin_[i_];
+            double sc_ = sold;
+            if (!first && act) {
+                p[i_] = p[i_] + sold * alpha;
+                sc_ = zin[i_] + sold * beta;
+            }
+            sout[i_] = sc_;
+            double tv;
+            if (CONSTM) {
+                double dg = 0.0;
+                if (y_ > 0) dg += cscale;
+                if (x_ > 0) dg += cscale;
+                if (x_ < g.w - 1) dg += cscale;
+                if (y_ < g.h - 1) dg += cscale;
+                tv = dg * sc_;
+                if (x_ > 0) tv += ms * s_new(nl_);
+                if (y_ > 0) tv += ms * s_new(nu_);
+                if (x_ < g.w - 1) tv += ms * s_new(nr_);
+                if (y_ < g.h - 1) tv += ms * s_new(nd_);
+            } else {
+                tv = adiag[i_] * sc_;
+                if (x_ > 0) tv += ax[nl_] * s_new(nl_);
+                if (y_ > 0) tv += ay[nu_] * s_new(nu_);
+                if (x_ < g.w - 1) tv += ax[i_] * s_new(nr_);
+                if (y_ < g.h - 1) tv += ay[i_] * s_new(nd_);
+            }
+            zout[i_] = tv;                                  /* matrixVectorProduct is never masked (F6:1011) */
+            if (act) acc += tv * sc_;                       /* dotProduct: fluid cells only from F6 on (F6:999) */
         }
         if (l_ == 0 && t_ * SKB + j_ < g.w) {
             const int xb = t_ * SKB + j_;                  /* lane 0 works on column block t_ */
@@ -226,62 +280,35 @@ k_update_pr(SkewGeom g, double* __restrict__ r,
             if (k_ == g.s1 - 1 && g.s1 < g.nstrips) bnd_b[(long long)g.s1 * g.w + xb] = sentinel();
         }
     IFL_EW_LOOP_END
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned other = __shfl_down_sync(0xffffffffu, m, o);
-        m = other > m ? other : m;
-    }
-    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; i++) m = s_max[i] > m ? s_max[i] : m;
-        atomicMax(&sc->max_bits, (unsigned long long)m);
-        __threadfence();
-        unsigned prev = atomicAdd(&sc->ctr_a, 1u);
-        s_last = (prev == gridDim.x * gridDim.y - 1u);
-        if (s_last) {
-            __threadfence();
-            unsigned long long mb = atomicMax(&sc->max_bits, 0ull);
-            if (single_gpu) {
-                double err = (double)__uint_as_float((unsigned)mb);
-                sc->max_error = err;
-                sc->iterations = sc->iterations + 1;
-                if (err < tol) sc->done = 1;
-                if (err != err) { sc->done = 1; sc->nan = 1; }
-            } else {
-                rank_max[rank] = mb;          /* decision after the all-gather, in k_apply_max */
-            }
-            sc->max_bits = 0ull;
-            sc->ctr_a = 0;
-            sc->ctr_b = 0;
-            sc->ticket_f = 0;
-            sc->ticket_b = 0;
-        }
+    const double bs = block_sum_256(acc, smem8);
+    if (finish_partials(bs, partials, g, strip_part, strip_ctr, sc, dot_mode, single_gpu, &s_flag, s_buf) && threadIdx.x == 0) {
+        sc->zpar = zp ^ 1;
+        sc->ctr_b = 0; sc->ctr_c = 0;
+        sc->ticket_f = 0; sc->ticket_b = 0;
     }
 }
 
-/* p = p + s * alpha (F3:607, deferred: see k_update_p) ; s = z + s * beta   (F3:626) */
+/* scaledAdd(_p, _p, _s, alpha) F3:607 (masked F6:1041) of the LAST iteration of a solve: inside the loop the update of p
+ * rides on the next iteration's k_step_a, which never runs for the iteration that converges or hits the limit. */
 __global__ void __launch_bounds__(EW_THREADS)
-k_update_sp(SkewGeom g, double* __restrict__ s, const double* __restrict__ z, double* __restrict__ p, SolveScalars* sc,
-            const unsigned char* __restrict__ fl) {
-    if (sc->done) return;          /* `done` is only ever set by this iteration's k_update_pr: not done => p is pending */
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) sc->p_pending = 0;
-    const double beta = sc->beta, alpha = sc->alpha;
+k_update_p(SkewGeom g, double* __restrict__ p, const double* s0, const double* s1, const SolveScalars* sc,
+           const unsigned char* __restrict__ fl) {
+    if (!sc->p_pending) return;
+    const double alpha = sc->alpha;
+    const double* __restrict__ s = sc->zpar ? s1 : s0;
     IFL_EW_LOOP_BEGIN(g)
-        if (ok_ && (fl == nullptr || fl[i_])) {
-            const double sv = s[i_];
-            p[i_] = p[i_] + sv * alpha;
-            s[i_] = z[i_] + sv * beta;
-        }
+        if (ok_ && (fl == nullptr || fl[i_])) p[i_] = p[i_] + s[i_] * alpha;
     IFL_EW_LOOP_END
 }
 
 /* start of project(): s = z (arraycopy F3:596); maxError = infinityNorm(r) (F3:598) */
 __global__ void __launch_bounds__(EW_THREADS)
-k_init_s(SkewGeom g, double* __restrict__ s, const double* __restrict__ z, const double* __restrict__ r,
+k_init_s(SkewGeom g, double* s0, double* s1, const double* z0, const double* z1, const double* __restrict__ r,
          SolveScalars* sc, double tol, const unsigned char* __restrict__ fl,
          unsigned long long* rank_max, int rank, int single_gpu) {
     __shared__ unsigned s_max[8];
+    double* __restrict__ s = sc->zpar ? s1 : s0;
+    const double* __restrict__ z = sc->zpar ? z1 : z0;
     unsigned m = 0;
     IFL_EW_LOOP_BEGIN(g)
         if (ok_) {
@@ -333,7 +360,9 @@ __global__ void k_solve_reset(SkewGeom g, double* bnd_f, double* bnd_b, SolveSca
         sc->sigma = 0.0; sc->alpha = 0.0; sc->neg_alpha = 0.0; sc->beta = 0.0; sc->zs = 0.0;
         sc->max_error = 0.0; sc->max_bits = 0ull;
         sc->iterations = 0; sc->done = 0; sc->nan = 0; sc->exceeded = 0; sc->p_pending = 0;
-        sc->ctr_a = 0; sc->ctr_b = 0; sc->ticket_f = 0; sc->ticket_b = 0;
+        sc->ctr_a = 0; sc->ctr_b = 0; sc->ctr_c = 0; sc->ticket_f = 0; sc->ticket_b = 0;
+        /* zpar is NOT reset: which z / s generation is current survives from solve to solve, like the reference's
+         * persistent _z / _s arrays (their stale values on masked cells) */
     }
 }
 
@@ -344,7 +373,7 @@ __global__ void k_sweep_rearm(SkewGeom g, double* bnd_f, double* bnd_b, SolveSca
         bnd_f[i] = sentinel();
         bnd_b[i] = sentinel();
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->ticket_f = 0; sc->ticket_b = 0; sc->ctr_b = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->ticket_f = 0; sc->ticket_b = 0; sc->ctr_b = 0; sc->ctr_c = 0; }
 }
 
 __global__ void k_solve_finish(SolveScalars* sc, int limit) {
@@ -352,20 +381,38 @@ __global__ void k_solve_finish(SolveScalars* sc, int limit) {
     if (!sc->done && sc->iterations >= limit) sc->exceeded = 1;
 }
 
-/* Reductions in the reference's serial order (bit-exact mode, small grids / tests):
- * one thread walks the cells lexicographically.  dotProduct F3:532. */
-__global__ void k_dot_sequential(SkewGeom g, const double* __restrict__ a, const double* __restrict__ b,
-                                 SolveScalars* sc, int mode, int check_done, const unsigned char* __restrict__ fl) {
+/* Reductions in the reference's serial order (bit-exact mode): dotProduct F3:532, `result += a[i]*b[i]` with i ascending.
+ * One block: the 256 threads form the products of 256 consecutive cells of a row (the loads run in parallel), thread 0
+ * then adds them strictly in the reference's order.  A cell the masked dotProduct skips (F6:1002) contributes +0.0, which
+ * leaves the running sum unchanged bit for bit (the sum starts at +0.0 and can never become -0.0).
+ * a = current z; b = b_fixed (r) or the current s. */
+__global__ void __launch_bounds__(EW_THREADS)
+k_dot_sequential(SkewGeom g, const double* z0, const double* z1, const double* b_fixed,
+                 const double* s0, const double* s1,
+                 SolveScalars* sc, int mode, int check_done, const unsigned char* __restrict__ fl) {
     if (check_done && sc->done) return;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ double s_prod[2][EW_THREADS];
+    const double* __restrict__ a = sc->zpar ? z1 : z0;
+    const double* __restrict__ b = b_fixed != nullptr ? b_fixed : (sc->zpar ? s1 : s0);
+    const long long n = (long long)g.w * g.h;
     double result = 0.0;
-    for (int y = 0; y < g.h; y++) {
-        for (int x = 0; x < g.w; x++) {
+    int buf = 0;
+    for (long long base = 0; base < n; base += EW_THREADS, buf ^= 1) {
+        const long long c = base + threadIdx.x;
+        double pr = 0.0;
+        if (c < n) {
+            const int y = (int)(c / g.w), x = (int)(c - (long long)y * g.w);
             const long long i = skew_index(g, x, y);
-            if (fl == nullptr || fl[i]) result += a[i] * b[i];
+            if (fl == nullptr || fl[i]) pr = a[i] * b[i];
+        }
+        s_prod[buf][threadIdx.x] = pr;
+        __syncthreads();                       /* two buffers: thread 0 may still be adding the previous chunk */
+        if (threadIdx.x == 0) {
+            const int m = n - base < EW_THREADS ? (int)(n - base) : EW_THREADS;
+            for (int i = 0; i < m; i++) result += s_prod[buf][i];
         }
     }
-    apply_dot_result(sc, mode, result);
+    if (threadIdx.x == 0) apply_dot_result(sc, mode, result);
 }
 
 /* ---------------------------------------------------------------------------------
@@ -797,16 +844,29 @@ __device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB],
  * Block layout: SW_WARPS strip warps (0..SW_WARPS-1) and as many loader warps; loader warp SW_WARPS+i streams the
  * operands of strip warp i into that warp's shared-memory ring with bulk copies (full/empty mbarrier pair per stage),
  * so that no copy bookkeeping sits on the strip warp's dependency chain. */
-template <int DIR, bool WITH_DOT, bool MASKED>
+/* FUSE (forward sweep inside the PCG loop only): the loader warp of every strip also performs, tile by tile and before
+ * the strip warp sees the operands,
+ *     r += (-alpha) * z            scaledAdd(_r, _r, _z, -alpha)  F3:608   (FUSE = 2: fluid cells only, F6:1041)
+ *     maxError = infinityNorm(r)   F3:609 / F6:1054, and the convergence decision F3:611-619 when the last strip is done,
+ * on the r and z (= A s) tiles the bulk copies have just staged, writes the new r back to global memory and hands the
+ * tile to the strip warp, which runs the triangular solve on it: one pass over r and z instead of a separate 24 B/cell
+ * kernel, on a warp that is otherwise idle.  z is swept in place (its tile is read before the strip warp overwrites it).
+ * If the solve turns out to have converged the sweep's output is simply not used (the reference returns before
+ * applyPreconditioner; z is dead until the next solve overwrites it). */
+template <int DIR, bool WITH_DOT, bool MASKED, int FUSE>
 __global__ void __launch_bounds__(2 * SW_WARPS * 32)
-k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restrict__ pack,
+k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, const double* __restrict__ pack,
                const double* __restrict__ rr, double* bnd, double* bnd_peer, double* strip_part,
-               SolveScalars* sc, int dot_mode, int check_done, long long* trace) {
+               SolveScalars* sc, int dot_mode, int check_done, long long* trace,
+               double tol, unsigned long long* rank_max, int rank, int single_gpu) {
+    static_assert(FUSE == 0 || (DIR > 0 && !WITH_DOT), "the r update rides on the forward sweep");
     namespace cg = cooperative_groups;
     constexpr int U = SW_U;                                           /* macro-steps per staged tile */
     constexpr int UB = SW_FG;                                         /* macro-steps per block of the loop */
     constexpr int S = SW_STAGES;
-    constexpr int STAGE = (WITH_DOT ? 2 : 1) * SW_TILE + SW_PACK;     /* doubles per stage */
+    constexpr int STAGE = ((WITH_DOT || FUSE) ? 2 : 1) * SW_TILE + SW_PACK;   /* doubles per stage */
+    constexpr int LAG = 3;                                            /* FUSE: tiles between a bulk copy and its r update (< S - 1) */
+    static_assert(LAG < SW_STAGES - 1, "the strip warp needs tile b+1 before it releases tile b");
     constexpr int E_IN = DIR > 0 ? 0 : 31;
     constexpr int E_OUT = DIR > 0 ? 31 : 0;
     extern __shared__ __align__(128) unsigned char wf_smem[];
@@ -822,6 +882,8 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     const int csize = (int)cluster.num_blocks();
     const int crank = (int)cluster.block_rank();
     if (check_done && sc->done) return;                  /* uniform over the whole grid */
+    double* const dst = sc->zpar ? dst1 : dst0;          /* the current generation of z */
+    const double* const src = src_fixed != nullptr ? src_fixed : dst;
     const long long tr_enter = trace ? (long long)globaltimer_ns() : 0;
     const int lane = threadIdx.x & 31;
     const bool loader = threadIdx.x >= SW_WARPS * 32;
@@ -829,15 +891,16 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     /* per-strip operand ring: S stages of [src tile | coefficient pack | rr tile]; then per strip S full + S empty mbarriers */
     double* ring = reinterpret_cast<double*>(wf_smem) + (size_t)warp * S * STAGE;
     unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(
-        wf_smem + (size_t)SW_WARPS * S * STAGE * sizeof(double)) + warp * 2 * S;
+        wf_smem + (size_t)SW_WARPS * S * STAGE * sizeof(double)) + warp * 3 * S;
     unsigned long long* bar_empty = bar_full + S;
+    unsigned long long* bar_ready = bar_empty + S;       /* FUSE: the loader warp has updated r in the staged tile */
     if (!loader) {
         for (int i = lane; i < 32 * XS; i += 32) s_xchg[warp][i] = 0.0;
         if (warp == 0 && lane < SW_FG * SKB) s_zero[lane] = 0.0;
         for (int i = lane; i < SW_RB * SKB; i += 32) s_inbox[warp][i] = sentinel();
         if (lane == 0) {
             s_credit[warp] = 0;
-            for (int i = 0; i < S; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+            for (int i = 0; i < S; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); mbar_init(&bar_ready[i], 1); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
@@ -859,33 +922,117 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     const int ntile = nblk * (UB / U);
     double acc = 0.0;
     if (live && loader) {
-        if (lane == 0) {
-            /* running pointers / shared addresses: this loop has to issue a tile faster than the strip warp consumes one */
-            const long long dtile = DIR > 0 ? SW_TILE : -SW_TILE;
-            const long long dpack = DIR > 0 ? SW_PACK : -SW_PACK;
-            const long long first = DIR > 0 ? 0 : ntile - 1;
-            const double* gsrc = src + (long long)k * g.ss + first * SW_TILE;
-            const double* grr = WITH_DOT ? rr + (long long)k * g.ss + first * SW_TILE : nullptr;
-            const double* gpack = pack + (long long)k * (g.tl / U) * SW_PACK + first * SW_PACK;
-            const unsigned ring0 = smem_u32(ring), full0 = smem_u32(bar_full), empty0 = smem_u32(bar_empty);
-            unsigned sdst = ring0, fb = full0, eb = empty0;
-            int st = 0;
-            unsigned ph = 1;                             /* parity of the completion that frees a stage; first lap: free */
+        /* running pointers / shared addresses: this loop has to issue a tile faster than the strip warp consumes one */
+        const long long dtile = DIR > 0 ? SW_TILE : -SW_TILE;
+        const long long dpack = DIR > 0 ? SW_PACK : -SW_PACK;
+        const long long first = DIR > 0 ? 0 : ntile - 1;
+        const double* gsrc = src + (long long)k * g.ss + first * SW_TILE;
+        /* second streamed vector: rr (dot product fused into the backward sweep) or z = A s (FUSE: the r update) */
+        const double* grr = WITH_DOT ? rr + (long long)k * g.ss + first * SW_TILE
+                                     : (FUSE ? dst + (long long)k * g.ss + first * SW_TILE : nullptr);
+        const double* gpack = pack + (long long)k * (g.tl / U) * SW_PACK + first * SW_PACK;
+        const unsigned ring0 = smem_u32(ring), full0 = smem_u32(bar_full), empty0 = smem_u32(bar_empty);
+        unsigned sdst = ring0, fb = full0, eb = empty0;
+        int st = 0;
+        unsigned ph = 1;                             /* parity of the completion that frees a stage; first lap: free */
+        auto issue_tile = [&](const int b) {         /* lane 0 only */
+            if (b >= S) mbar_wait_u32(eb, ph);
+            if (b == ntile && DIR < 0) { gsrc -= dtile; gpack -= dpack; if (WITH_DOT) grr -= dtile; }   /* stay inside */
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((unsigned)(STAGE * sizeof(double))) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sdst), "l"(gsrc), "r"((unsigned)(SW_TILE * sizeof(double))), "r"(fb) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sdst + (unsigned)(SW_TILE * sizeof(double))), "l"(gpack), "r"((unsigned)(SW_PACK * sizeof(double))), "r"(fb) : "memory");
+            if (WITH_DOT || FUSE)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sdst + (unsigned)((SW_TILE + SW_PACK) * sizeof(double))), "l"(grr), "r"((unsigned)(SW_TILE * sizeof(double))), "r"(fb) : "memory");
+            gsrc += dtile; gpack += dpack; if (WITH_DOT || FUSE) grr += dtile;
+            sdst += (unsigned)(STAGE * sizeof(double)); fb += 8u; eb += 8u;
+            if (++st == S) { st = 0; ph ^= 1u; sdst = ring0; fb = full0; eb = empty0; }
+        };
+        if (!FUSE) {
             /* one tile more than the strip has: the strip warp prefetches across every tile boundary without a test */
-            for (int b = 0; b <= ntile; b++) {
-                if (b >= S) mbar_wait_u32(eb, ph);
-                if (b == ntile && DIR < 0) { gsrc -= dtile; gpack -= dpack; if (WITH_DOT) grr -= dtile; }   /* stay inside */
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((unsigned)(STAGE * sizeof(double))) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(sdst), "l"(gsrc), "r"((unsigned)(SW_TILE * sizeof(double))), "r"(fb) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(sdst + (unsigned)(SW_TILE * sizeof(double))), "l"(gpack), "r"((unsigned)(SW_PACK * sizeof(double))), "r"(fb) : "memory");
-                if (WITH_DOT)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(sdst + (unsigned)((SW_TILE + SW_PACK) * sizeof(double))), "l"(grr), "r"((unsigned)(SW_TILE * sizeof(double))), "r"(fb) : "memory");
-                gsrc += dtile; gpack += dpack; if (WITH_DOT) grr += dtile;
-                sdst += (unsigned)(STAGE * sizeof(double)); fb += 8u; eb += 8u;
-                if (++st == S) { st = 0; ph ^= 1u; sdst = ring0; fb = full0; eb = empty0; }
+            if (lane == 0) for (int b = 0; b <= ntile; b++) issue_tile(b);
+        } else {
+            /* Lane 0 keeps issuing bulk copies LAG tiles ahead; the whole warp then updates r in the tile that arrived
+             * LAG tiles ago (lane l owns the SKB cells of row l in every m-row, like the strip warp) and releases it to
+             * the strip warp through the `ready` barrier.  Only cells inside the grid are touched: the padding of r and
+             * z stays zero whatever alpha is. */
+            const int y = k * 32 + lane;
+            const bool yok = y < g.h;
+            const double nalpha = sc->neg_alpha;
+            const unsigned ring_lane = smem_u32(ring + lane * SKB);
+            const unsigned ready0 = smem_u32(bar_ready);
+            double* const rout = const_cast<double*>(src) + (long long)k * g.ss + lane * SKB;
+            unsigned mloc = 0;
+            for (int b = 0; b <= ntile + LAG; b++) {
+                if (b <= ntile && lane == 0) issue_tile(b);
+                __syncwarp();
+                const int pb = b - LAG;
+                if (pb < 0) continue;
+                const int sp = pb % S;
+                mbar_wait_u32(full0 + 8u * (unsigned)sp, (unsigned)(pb / S) & 1u);
+                if (pb < ntile) {
+                    const unsigned tile = ring_lane + (unsigned)(sp * STAGE * (int)sizeof(double));
+#pragma unroll
+                    for (int e = 0; e < U; e++) {
+                        const int t = pb * U + e;
+                        const int x0 = (t - lane) * SKB;
+                        const unsigned a_r = tile + (unsigned)(e * 32 * SKB * (int)sizeof(double));
+                        double rv[SKB], zv[SKB], pv[SKB];
+                        lds_cells(a_r, rv);
+                        lds_cells(a_r + (unsigned)((SW_TILE + SW_PACK) * sizeof(double)), zv);
+                        if (FUSE == 2) lds_cells(a_r + 3 * SW_TILE * (unsigned)sizeof(double), pv);
+                        bool ok[SKB];
+#pragma unroll
+                        for (int j = 0; j < SKB; j++) {
+                            ok[j] = yok && x0 + j >= 0 && x0 + j < w;
+                            if (FUSE == 2) ok[j] = ok[j] && (pv[j] == pv[j]);     /* NaN precon tags a non-fluid cell */
+                            const double nv = rv[j] + zv[j] * nalpha;             /* a[i] + b[i]*s  F3:573 */
+                            if (ok[j]) {
+                                rv[j] = nv;
+                                const unsigned bits = absf_bits(nv);              /* abs((float) a[i])  F3:582 */
+                                mloc = bits > mloc ? bits : mloc;
+                            }
+                        }
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a_r), "d"(rv[0]), "d"(rv[SKB - 1]) : "memory");
+                        double* gp = rout + (long long)t * (32 * SKB);
+                        if (ok[0] && ok[SKB - 1]) *reinterpret_cast<double2*>(gp) = make_double2(rv[0], rv[SKB - 1]);
+                        else {
+#pragma unroll
+                            for (int j = 0; j < SKB; j++) if (ok[j]) gp[j] = rv[j];
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_ready[sp]);
+            }
+            /* maxError and the convergence decision (F3:609-619) once every strip of this rank has updated its r */
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned other = __shfl_down_sync(0xffffffffu, mloc, o);
+                mloc = other > mloc ? other : mloc;
+            }
+            if (lane == 0) {
+                atomicMax(&sc->max_bits, (unsigned long long)mloc);
+                __threadfence();
+                const unsigned prev = atomicAdd(&sc->ctr_c, 1u);
+                if (prev == (unsigned)nown - 1u) {
+                    __threadfence();
+                    const unsigned long long mb = atomicMax(&sc->max_bits, 0ull);
+                    if (single_gpu) {
+                        const double err = (double)__uint_as_float((unsigned)mb);
+                        sc->max_error = err;
+                        sc->iterations = sc->iterations + 1;
+                        if (err < tol) sc->done = 1;
+                        if (err != err) { sc->done = 1; sc->nan = 1; }
+                    } else {
+                        rank_max[rank] = mb;          /* decision after the all-gather, in k_apply_max */
+                    }
+                    sc->max_bits = 0ull;
+                    sc->ctr_c = 0;
+                    sc->p_pending = 1;                /* r carries this iteration's alpha, p does not yet */
+                }
             }
         }
     } else if (live) {
@@ -942,7 +1089,7 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
 
         /* tile cursor: stage st holds the tile the operand loads currently read; shared addresses kept in registers */
         const unsigned ring_lane = pin_u32(smem_u32(ring + lane * SKB));
-        const unsigned full0 = pin_u32(smem_u32(bar_full));
+        const unsigned full0 = pin_u32(smem_u32(FUSE ? bar_ready : bar_full));   /* what tells this warp that a tile is usable */
         const unsigned empty0 = pin_u32(smem_u32(bar_empty));
         const unsigned inbox0 = pin_u32(smem_u32(&s_inbox[warp][0]));
         int st = 0;
@@ -1178,7 +1325,6 @@ k_precon_sweep(SkewGeom g, const double* src, double* dst, const double* __restr
     cluster.sync();
 }
 
-#include "ifl_sweep2.cuh"
 
 /* buildPreconditioner F3:464 / masked F4:744 (=F5:858, F6:918, F7:951) -- MIC(0) with tau/sigma,
  * lexicographic recurrence on precon.  fl = skewed fluid flags (F4+: non-fluid cells are skipped and
@@ -1391,20 +1537,37 @@ k_gs_sweep(SkewGeom g, const double* __restrict__ r, double* p, double* bnd_use,
     }
 }
 
-/* slab decomposition: boundary rows of a skewed vector <-> packed rows.  rowbuf = [send up | send down | recv up | recv down] */
-__global__ void k_pack_rows(SkewGeom g, const double* __restrict__ vec, double* __restrict__ rowbuf) {
+/* slab decomposition: boundary rows of the current z and s <-> packed rows.
+ * rowbuf = [z first row | s first row | z last row | s last row | from above: z, s | from below: z, s], w doubles each */
+__global__ void k_pack_rows(SkewGeom g, const double* z0, const double* z1, const double* s0, const double* s1,
+                            const SolveScalars* sc, double* __restrict__ rowbuf) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= g.w) return;
-    rowbuf[x] = vec[skew_index(g, x, g.s0 * 32)];                                       /* my first row -> rank-1 */
+    const double* __restrict__ z = sc->zpar ? z1 : z0;
+    const double* __restrict__ s = sc->zpar ? s1 : s0;
+    const long long ifirst = skew_index(g, x, g.s0 * 32);                               /* my first row -> rank-1 */
     int ylast = g.s1 * 32 - 1;
     if (ylast > g.h - 1) ylast = g.h - 1;
-    rowbuf[g.w + x] = vec[skew_index(g, x, ylast)];                                     /* my last row -> rank+1 */
+    const long long ilast = skew_index(g, x, ylast);                                    /* my last row -> rank+1 */
+    rowbuf[x] = z[ifirst];
+    rowbuf[g.w + x] = s[ifirst];
+    rowbuf[2 * g.w + x] = z[ilast];
+    rowbuf[3 * g.w + x] = s[ilast];
 }
-__global__ void k_unpack_rows(SkewGeom g, double* __restrict__ vec, const double* __restrict__ rowbuf, int has_up, int has_down) {
+__global__ void k_unpack_rows(SkewGeom g, double* z0, double* z1, double* s0, double* s1, const SolveScalars* sc,
+                              const double* __restrict__ rowbuf, int has_up, int has_down) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= g.w) return;
-    if (has_up) vec[skew_index(g, x, g.s0 * 32 - 1)] = rowbuf[2 * g.w + x];             /* row above my slab */
-    if (has_down) vec[skew_index(g, x, g.s1 * 32)] = rowbuf[3 * g.w + x];               /* row below my slab */
+    double* __restrict__ z = sc->zpar ? z1 : z0;
+    double* __restrict__ s = sc->zpar ? s1 : s0;
+    if (has_up) {                                                                       /* row above my slab */
+        const long long i = skew_index(g, x, g.s0 * 32 - 1);
+        z[i] = rowbuf[4 * g.w + x]; s[i] = rowbuf[5 * g.w + x];
+    }
+    if (has_down) {                                                                     /* row below my slab */
+        const long long i = skew_index(g, x, g.s1 * 32);
+        z[i] = rowbuf[6 * g.w + x]; s[i] = rowbuf[7 * g.w + x];
+    }
 }
 
 /* ---------------------------------------------------------------------------------
@@ -1417,29 +1580,38 @@ static inline int rearm_blocks(const SkewGeom& g) {
     return (int)(b < 1 ? 1 : (b > 1184 ? 1184 : b));
 }
 
-void launch_build_precon(SolveCtx& c) {
+/* every enqueue helper returns 0 or -1 (communication failure, comm_last_error()); launch errors are picked up by the
+ * caller's cudaGetLastError() */
+#define IFL_TRY(call) do { if ((call) != 0) return -1; } while (0)
+
+int launch_build_precon(SolveCtx& c) {
     k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
     k_build_precon<<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.precon,
                                                                   c.bnd_f, c.sc, c.mic_tau, c.mic_sigma, c.fl);
     { SkewGeom fg = full_geom(c.g);   /* built redundantly for the whole grid on every rank */
       k_precon_coeffs<<<ew_grid(fg), EW_THREADS, 0, c.stream>>>(fg, c.aplusx, c.aplusy, c.precon, c.pack_f, c.pack_b, c.fl); }
     count(c, 3);
+    return 0;
 }
 
-static size_t sweep_smem(bool with_dot) {
-    size_t stage = ((with_dot ? 2 : 1) * SW_TILE + SW_PACK) * sizeof(double);
-    return (size_t)SW_WARPS * SW_STAGES * stage + (size_t)SW_WARPS * 2 * SW_STAGES * 8;
+static size_t sweep_smem(bool two_streams) {
+    size_t stage = ((two_streams ? 2 : 1) * SW_TILE + SW_PACK) * sizeof(double);
+    return (size_t)SW_WARPS * SW_STAGES * stage + (size_t)SW_WARPS * 3 * SW_STAGES * 8;
 }
-template <int DIR, bool WITH_DOT, bool MASKED>
-static void launch_sweep(SolveCtx& c, const double* src, double* dst, const double* pack, const double* rr, double* bnd,
+/* src == nullptr: in place on the current z generation */
+template <int DIR, bool WITH_DOT, bool MASKED, int FUSE>
+static void launch_sweep(SolveCtx& c, const double* src, const double* pack, const double* rr, double* bnd,
                          int dot_mode, int check_done, long long* trace) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_precon_sweep<DIR, WITH_DOT, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sweep_smem(WITH_DOT));
+    /* the opt-in to > 48 KB of dynamic shared memory is per device and per kernel instance */
+    static unsigned long long attr_devices = 0ull;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !((attr_devices >> dev) & 1ull)) {
+        cudaFuncSetAttribute(k_precon_sweep<DIR, WITH_DOT, MASKED, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sweep_smem(WITH_DOT || FUSE));
         if (SW_CL_MAX > 8)
-            cudaFuncSetAttribute(k_precon_sweep<DIR, WITH_DOT, MASKED>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        attr_done = true;
+            cudaFuncSetAttribute(k_precon_sweep<DIR, WITH_DOT, MASKED, FUSE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (dev < 64) __atomic_fetch_or(&attr_devices, 1ull << dev, __ATOMIC_RELAXED);
     }
     const int nown = c.g.s1 - c.g.s0;
     double* peer = nullptr;
@@ -1450,139 +1622,125 @@ static void launch_sweep(SolveCtx& c, const double* src, double* dst, const doub
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(((nblocks + cl - 1) / cl) * cl);
     cfg.blockDim = dim3(2 * SW_WARPS * 32);                        /* strip warps + loader warps */
-    cfg.dynamicSmemBytes = sweep_smem(WITH_DOT);
+    cfg.dynamicSmemBytes = sweep_smem(WITH_DOT || FUSE);
     cfg.stream = c.stream;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = cl; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_precon_sweep<DIR, WITH_DOT, MASKED>, c.g, src, dst, pack, rr, bnd, peer, c.strip_part, c.sc,
-                       dot_mode, check_done, trace);
+    cudaLaunchKernelEx(&cfg, k_precon_sweep<DIR, WITH_DOT, MASKED, FUSE>, c.g, src, c.zb[0], c.zb[1], pack, rr, bnd, peer,
+                       c.strip_part, c.sc, dot_mode, check_done, trace, c.tolerance, c.rank_max,
+                       c.comm ? c.comm->rank : 0, single_gpu(c));
 }
 
-/* the two-rows-per-lane sweep (ifl_sweep2.cuh): same launch shape, unmasked variants only */
-template <int DIR, bool WITH_DOT>
-static void launch_sweep2(SolveCtx& c, const double* src, double* dst, const double* pack, const double* rr, double* bnd,
-                          int dot_mode, int check_done, long long* trace) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_precon_sweep2<DIR, WITH_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem(WITH_DOT));
-        if (SW_CL_MAX > 8) cudaFuncSetAttribute(k_precon_sweep2<DIR, WITH_DOT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        attr_done = true;
-    }
-    const int nown = c.g.s1 - c.g.s0;
-    double* peer = nullptr;
-    if (c.comm) peer = DIR > 0 ? c.peer_bnd_f_next : c.peer_bnd_b_prev;
-    const int nblocks = (nown + SW_WARPS - 1) / SW_WARPS;
-    int cl = SW_CL_MAX;
-    while (cl > 1 && cl > nblocks) cl >>= 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(((nblocks + cl - 1) / cl) * cl);
-    cfg.blockDim = dim3(2 * SW_WARPS * 32);
-    cfg.dynamicSmemBytes = sweep_smem(WITH_DOT);
-    cfg.stream = c.stream;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = cl; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_precon_sweep2<DIR, WITH_DOT>, c.g, src, dst, pack, rr, bnd, peer, c.strip_part, c.sc,
-                       dot_mode, check_done, trace);
-}
-
-/* dst = M^-1 src: forward then backward sweep.  Boundary rows must be armed. */
 static inline void prof_mark(SolveCtx& c, int slot, int e);
-static void enqueue_precon(SolveCtx& c, const double* src, double* dst, int dot_mode, int check_done, int ps = -1) {
+static int dist_max(SolveCtx& c, int init);
+/* z = M^-1 r on the current z generation: forward then backward sweep.  Boundary rows must be armed.
+ * fuse_r_update: the forward sweep first performs r -= alpha*z (z = A s), the norm and the convergence decision. */
+static int enqueue_precon(SolveCtx& c, int fuse_r_update, int dot_mode, int check_done, int ps = -1) {
     const bool masked = c.fl != nullptr;
-    /* IFL_SWEEP2=1 selects the two-rows-per-lane kernel (ifl_sweep2.cuh; unmasked variants).  It halves the skew of a
-     * strip but its macro-step costs 1.3-1.5x, and with 80-100 KB of staged operands per strip too few strips are
-     * resident: measured slower at 16384^2 on 1 and 2 GPUs, equal at 4096^2, 10 % faster at 1024^2. */
-    static const bool want2 = getenv("IFL_SWEEP2") != nullptr;
-    const bool two_rows = !masked && want2;
-    if (masked) launch_sweep<1, false, true>(c, src, dst, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
-    else if (two_rows) launch_sweep2<1, false>(c, src, dst, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
-    else        launch_sweep<1, false, false>(c, src, dst, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
-    prof_mark(c, ps, 3);
+    if (fuse_r_update) {
+        if (!masked)                launch_sweep<1, false, false, 1>(c, c.r, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
+        else if (c.mask_vector_ops) launch_sweep<1, false, true, 2>(c, c.r, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
+        else                        launch_sweep<1, false, true, 1>(c, c.r, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
+        count(c);
+        IFL_TRY(dist_max(c, 0));
+    } else {
+        if (masked) launch_sweep<1, false, true, 0>(c, c.r, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
+        else        launch_sweep<1, false, false, 0>(c, c.r, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
+        count(c);
+    }
+    prof_mark(c, ps, 2);
     int fused_mode = c.sequential ? DOT_NONE : dot_mode;
     long long* tr2 = c.trace ? c.trace + 8 * c.g.nstrips : nullptr;
     if (dot_mode != DOT_NONE) {
-        if (masked) launch_sweep<-1, true, true>(c, dst, dst, c.pack_b, src, c.bnd_b, fused_mode, check_done, tr2);
-        else if (two_rows) launch_sweep2<-1, true>(c, dst, dst, c.pack_b, src, c.bnd_b, fused_mode, check_done, tr2);
-        else        launch_sweep<-1, true, false>(c, dst, dst, c.pack_b, src, c.bnd_b, fused_mode, check_done, tr2);
+        if (masked) launch_sweep<-1, true, true, 0>(c, nullptr, c.pack_b, c.r, c.bnd_b, fused_mode, check_done, tr2);
+        else        launch_sweep<-1, true, false, 0>(c, nullptr, c.pack_b, c.r, c.bnd_b, fused_mode, check_done, tr2);
     } else {
-        if (masked) launch_sweep<-1, false, true>(c, dst, dst, c.pack_b, nullptr, c.bnd_b, DOT_NONE, check_done, tr2);
-        else if (two_rows) launch_sweep2<-1, false>(c, dst, dst, c.pack_b, nullptr, c.bnd_b, DOT_NONE, check_done, tr2);
-        else        launch_sweep<-1, false, false>(c, dst, dst, c.pack_b, nullptr, c.bnd_b, DOT_NONE, check_done, tr2);
+        if (masked) launch_sweep<-1, false, true, 0>(c, nullptr, c.pack_b, nullptr, c.bnd_b, DOT_NONE, check_done, tr2);
+        else        launch_sweep<-1, false, false, 0>(c, nullptr, c.pack_b, nullptr, c.bnd_b, DOT_NONE, check_done, tr2);
     }
-    prof_mark(c, ps, 4);
-    count(c, 2);
+    count(c);
     if (c.sequential && dot_mode != DOT_NONE) {
-        k_dot_sequential<<<1, 32, 0, c.stream>>>(c.g, dst, src, c.sc, dot_mode, check_done, c.mask_vector_ops ? c.fl : nullptr);
+        k_dot_sequential<<<1, EW_THREADS, 0, c.stream>>>(c.g, c.zb[0], c.zb[1], c.r, nullptr, nullptr, c.sc, dot_mode, check_done,
+                                                 c.mask_vector_ops ? c.fl : nullptr);
         count(c);
     }
+    return 0;
 }
 
-void launch_apply_precon(SolveCtx& c, const double* src, double* dst, int /*with_dot_mode*/) {
+/* applyPreconditioner(z, r) on its own (IFL_STAGE_APPLY_PRECON, the wavefront trace) */
+int launch_apply_precon(SolveCtx& c) {
     k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
     count(c);
     /* slab decomposition: no neighbour may store into an inbox row before its owner has re-armed it */
-    if (!single_gpu(c)) comm_all_gather(*c.comm, c.rank_max + c.comm->rank, c.rank_max, sizeof(unsigned long long));
-    enqueue_precon(c, src, dst, DOT_NONE, 0);
+    if (!single_gpu(c)) IFL_TRY(comm_all_gather(*c.comm, c.rank_max + c.comm->rank, c.rank_max, sizeof(unsigned long long)));
+    return enqueue_precon(c, 0, DOT_NONE, 0);
 }
 
-static void enqueue_matvec(SolveCtx& c, const SkewGeom& g, const double* b, double* dst, int dot_mode, int check_done,
-                           const unsigned char* fl, int single) {
+/* z = A s on the current generation (IFL_STAGE_MATVEC) */
+int launch_matvec(SolveCtx& c) {
+    const int zp = solve_parity(c);
+    if (zp < 0) return -1;
     if (c.const_matrix)
-        k_matvec_dot<true><<<ew_grid(g), EW_THREADS, 0, c.stream>>>(g, c.adiag, c.aplusx, c.aplusy, b, dst, c.partials, c.strip_part,
-                                                                    c.sc, dot_mode, check_done, fl, single, c.const_scale);
+        k_matvec<true><<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.sb[zp], c.zb[zp], c.const_scale);
     else
-        k_matvec_dot<false><<<ew_grid(g), EW_THREADS, 0, c.stream>>>(g, c.adiag, c.aplusx, c.aplusy, b, dst, c.partials, c.strip_part,
-                                                                     c.sc, dot_mode, check_done, fl, single, 0.0);
+        k_matvec<false><<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.sb[zp], c.zb[zp], 0.0);
     count(c);
+    return 0;
 }
-void launch_matvec(SolveCtx& c, const double* b, double* dst) {
-    enqueue_matvec(c, c.g, b, dst, DOT_NONE, 0, nullptr, 1);
+
+/* which generation of z / s is current (host side: stages and field access of the tests; synchronises the stream) */
+int solve_parity(SolveCtx& c) {
+    int zp = 0;
+    if (cudaMemcpyAsync(&zp, &c.sc->zpar, sizeof(int), cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess) return -1;
+    return zp & 1;
 }
 
 /* ---- distributed pieces (no-ops on a single GPU) ---- */
-__global__ void k_apply_dot(SkewGeom g, const double* __restrict__ strip_part, SolveScalars* sc, int mode, int check_done);
-__global__ void k_apply_max(const unsigned long long* __restrict__ rank_max, int world, SolveScalars* sc, double tol, int init);
-static void dist_dot(SolveCtx& c, int mode, int check_done) {
-    if (single_gpu(c) || mode == DOT_NONE) return;
-    const int chunk = c.strips_alloc / c.comm->world;
-    comm_all_gather(*c.comm, c.strip_part + (size_t)c.comm->rank * chunk, c.strip_part, sizeof(double) * chunk);
-    k_apply_dot<<<1, 32, 0, c.stream>>>(c.g, c.strip_part, c.sc, mode, check_done);
+static int dist_dot(SolveCtx& c, int mode, int check_done) {
+    if (single_gpu(c) || mode == DOT_NONE) return 0;
+    IFL_TRY(comm_all_gather_strips(*c.comm, c.strip_part, c.g.nstrips, 1));
+    k_apply_dot<<<1, EW_THREADS, 0, c.stream>>>(c.g, c.strip_part, c.sc, mode, check_done);
     count(c);
+    return 0;
 }
-static void dist_max(SolveCtx& c, int init) {
-    if (single_gpu(c)) return;
-    comm_all_gather(*c.comm, c.rank_max + c.comm->rank, c.rank_max, sizeof(unsigned long long));
+static int dist_max(SolveCtx& c, int init) {
+    if (single_gpu(c)) return 0;
+    IFL_TRY(comm_all_gather(*c.comm, c.rank_max + c.comm->rank, c.rank_max, sizeof(unsigned long long)));
     k_apply_max<<<1, 32, 0, c.stream>>>(c.rank_max, c.comm->world, c.sc, c.tolerance, init);
     count(c);
+    return 0;
 }
-/* the mat-vec of the next iteration reads s one row above and one row below the slab */
-static void dist_halo_rows(SolveCtx& c, double* vec) {
-    if (single_gpu(c)) return;
+/* k_step_a of the next iteration reads z and s one row above and one row below the slab */
+static int dist_halo_rows(SolveCtx& c) {
+    if (single_gpu(c)) return 0;
     const int w = c.g.w;
-    k_pack_rows<<<(w + 255) / 256, 256, 0, c.stream>>>(c.g, vec, c.rowbuf);
-    comm_exchange_rows(*c.comm, c.rowbuf, c.rowbuf + 2 * w, c.rowbuf + w, c.rowbuf + 3 * w, (size_t)w);
-    k_unpack_rows<<<(w + 255) / 256, 256, 0, c.stream>>>(c.g, vec, c.rowbuf, c.comm->rank > 0, c.comm->rank < c.comm->world - 1);
+    k_pack_rows<<<(w + 255) / 256, 256, 0, c.stream>>>(c.g, c.zb[0], c.zb[1], c.sb[0], c.sb[1], c.sc, c.rowbuf);
+    /* rowbuf = [z up | s up | z down | s down | recv from above (z, s) | recv from below (z, s)] */
+    IFL_TRY(comm_exchange_rows(*c.comm, c.rowbuf, c.rowbuf + 4 * w, c.rowbuf + 2 * w, c.rowbuf + 6 * w, (size_t)2 * w));
+    k_unpack_rows<<<(w + 255) / 256, 256, 0, c.stream>>>(c.g, c.zb[0], c.zb[1], c.sb[0], c.sb[1], c.sc, c.rowbuf,
+                                                         c.comm->rank > 0, c.comm->rank < c.comm->world - 1);
     count(c, 2);
+    return 0;
 }
 
 /* project() F3:590-602: p = 0; z = M^-1 r; s = z; maxError; sigma = z.r */
-void pcg_enqueue_init(SolveCtx& c) {
+int pcg_enqueue_init(SolveCtx& c) {
     cudaMemsetAsync(c.p, 0, sizeof(double) * (size_t)c.g.total, c.stream);
     k_solve_reset<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
     count(c);
     /* every rank's inboxes must be re-armed before any neighbour starts writing into them */
-    if (!single_gpu(c)) comm_all_gather(*c.comm, c.rank_max + c.comm->rank, c.rank_max, sizeof(unsigned long long));
-    enqueue_precon(c, c.r, c.z, DOT_SIGMA_INIT, 0);
-    dist_dot(c, DOT_SIGMA_INIT, 0);
-    k_init_s<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.r, c.sc, c.tolerance, c.mask_vector_ops ? c.fl : nullptr,
+    if (!single_gpu(c)) IFL_TRY(comm_all_gather(*c.comm, c.rank_max + c.comm->rank, c.rank_max, sizeof(unsigned long long)));
+    IFL_TRY(enqueue_precon(c, 0, DOT_SIGMA_INIT, 0));
+    IFL_TRY(dist_dot(c, DOT_SIGMA_INIT, 0));
+    k_init_s<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.sb[0], c.sb[1], c.zb[0], c.zb[1], c.r, c.sc, c.tolerance,
+                                                       c.mask_vector_ops ? c.fl : nullptr,
                                                        c.rank_max, c.comm ? c.comm->rank : 0, single_gpu(c));
     count(c);
-    dist_max(c, 1);
-    dist_halo_rows(c, c.s);
+    IFL_TRY(dist_max(c, 1));
+    return dist_halo_rows(c);
 }
 
 __global__ void k_record_done(const SolveScalars* sc, int* out) { *out = sc->done; }
@@ -1601,44 +1759,47 @@ static inline void prof_mark(SolveCtx& c, int slot, int e) {
     if (slot >= 0) cudaEventRecord(c.prof->ev[slot][e], c.stream);
 }
 
-/* n iterations of the loop body F3:603-628; every kernel returns at once after convergence */
-void pcg_enqueue_iterations(SolveCtx& c, int n) {
+/* n iterations of the loop body F3:603-628 as three kernels; every kernel returns at once after convergence */
+int pcg_enqueue_iterations(SolveCtx& c, int n) {
     dim3 eg = ew_grid(c.g);
     const unsigned char* mfl = c.mask_vector_ops ? c.fl : nullptr;
-    const int rank = c.comm ? c.comm->rank : 0;
     for (int it = 0; it < n; it++) {
         const int ps = (it == 0 && !c.sequential) ? prof_begin(c, 0) : -1;
-        enqueue_matvec(c, c.g, c.s, c.z, c.sequential ? DOT_NONE : DOT_ZS, 1, mfl, single_gpu(c));
+        const int dm = c.sequential ? DOT_NONE : DOT_ZS;
+        if (c.const_matrix)
+            k_step_a<true><<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.zb[0], c.zb[1], c.sb[0], c.sb[1], c.p,
+                                                            c.partials, c.strip_part, c.strip_ctr, c.sc, dm, mfl, single_gpu(c),
+                                                            c.const_scale, c.bnd_f, c.bnd_b);
+        else
+            k_step_a<false><<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.zb[0], c.zb[1], c.sb[0], c.sb[1], c.p,
+                                                             c.partials, c.strip_part, c.strip_ctr, c.sc, dm, mfl, single_gpu(c),
+                                                             0.0, c.bnd_f, c.bnd_b);
+        count(c);
         if (c.sequential) {
-            k_dot_sequential<<<1, 32, 0, c.stream>>>(c.g, c.z, c.s, c.sc, DOT_ZS, 1, mfl);
+            k_dot_sequential<<<1, EW_THREADS, 0, c.stream>>>(c.g, c.zb[0], c.zb[1], nullptr, c.sb[0], c.sb[1], c.sc, DOT_ZS, 1, mfl);
             count(c);
         }
-        dist_dot(c, DOT_ZS, 1);
+        IFL_TRY(dist_dot(c, DOT_ZS, 1));
         prof_mark(c, ps, 1);
-        k_update_pr<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.r, c.z, c.bnd_f, c.bnd_b, c.sc, c.tolerance, mfl,
-                                                     c.rank_max, rank, single_gpu(c));
-        count(c);
-        dist_max(c, 0);
-        prof_mark(c, ps, 2);
-        enqueue_precon(c, c.r, c.z, DOT_SIGMA_NEW, 1, ps);
-        dist_dot(c, DOT_SIGMA_NEW, 1);
-        k_update_sp<<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.s, c.z, c.p, c.sc, mfl);
-        count(c);
-        dist_halo_rows(c, c.s);
-        prof_mark(c, ps, 5);
+        IFL_TRY(enqueue_precon(c, 1, DOT_SIGMA_NEW, 1, ps));
+        IFL_TRY(dist_dot(c, DOT_SIGMA_NEW, 1));
+        IFL_TRY(dist_halo_rows(c));
+        prof_mark(c, ps, 3);
     }
+    return 0;
 }
 
-void pcg_enqueue_finish(SolveCtx& c, int limit) {
-    /* the converging iteration's p += alpha*s (no-op when the loop ended on its iteration limit) */
-    k_update_p<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.p, c.s, c.sc, c.mask_vector_ops ? c.fl : nullptr);
+int pcg_enqueue_finish(SolveCtx& c, int limit) {
+    /* the last iteration's p += alpha*s */
+    k_update_p<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.p, c.sb[0], c.sb[1], c.sc, c.mask_vector_ops ? c.fl : nullptr);
     k_solve_finish<<<1, 1, 0, c.stream>>>(c.sc, limit);
     count(c, 2);
-    if (!single_gpu(c)) {
-        /* every rank needs the whole pressure field for applyPressure: in-place all-gather of the slabs */
-        const size_t chunk = (size_t)(c.strips_alloc / c.comm->world) * (size_t)c.g.ss;
-        comm_all_gather(*c.comm, c.p + (size_t)c.comm->rank * chunk, c.p, sizeof(double) * chunk);
-    }
+    return 0;
+}
+/* slab decomposition, hosts that keep whole fields on every rank: every rank's slab of p to every rank */
+int pcg_gather_pressure(SolveCtx& c) {
+    if (single_gpu(c)) return 0;
+    return comm_all_gather_strips(*c.comm, c.p, c.g.nstrips, (size_t)c.g.ss);
 }
 
 /* Gauss-Seidel project() F1:380: _p is warm-started, so only the control state is reset */
@@ -1656,6 +1817,9 @@ void gs_enqueue_iterations(SolveCtx& c, int first_iter, int n, double scale) {
         prof_mark(c, ps, 1);
     }
 }
-void gs_enqueue_finish(SolveCtx& c, int limit) { pcg_enqueue_finish(c, limit); }
+void gs_enqueue_finish(SolveCtx& c, int limit) {
+    k_solve_finish<<<1, 1, 0, c.stream>>>(c.sc, limit);
+    count(c);
+}
 
 } // namespace ifl

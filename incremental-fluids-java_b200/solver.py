@@ -274,16 +274,17 @@ class FluidSolver:
 
 
 def slab_partition(h, world_size):
-    """Strip ranges of the slab decomposition, identical to ifl_create(): the grid's 32-row strips are dealt out in
-    contiguous chunks of ceil(nstrips / world) -- rank r owns strips [r*chunk, min((r+1)*chunk, nstrips)), i.e. rows
+    """Strip ranges of the slab decomposition, identical to ifl_create() (slab_range in csrc/ifl_internal.h): the
+    grid's 32-row strips are dealt out in contiguous, balanced ranges -- base = nstrips // world, the first
+    nstrips % world ranks own one strip more -- so no rank is ever empty.  Rank r owns strips [s0, s1), i.e. rows
     [32*s0, min(32*s1, h)).  Returns a list of (s0, s1, row0, row1) per rank."""
     nstrips = (h + 31) // 32
     if world_size < 1 or nstrips < world_size:
         raise ValueError("fewer 32-row strips than ranks")
-    chunk = (nstrips + world_size - 1) // world_size
+    base, rem = divmod(nstrips, world_size)
     out = []
     for r in range(world_size):
-        s0 = r * chunk
-        s1 = min(s0 + chunk, nstrips)
-        out.append((s0, max(s1, s0), min(32 * s0, h), min(32 * max(s1, s0), h)))
+        s0 = r * base + min(r, rem)
+        s1 = s0 + base + (1 if r < rem else 0)
+        out.append((s0, s1, min(32 * s0, h), min(32 * s1, h)))
     return out

@@ -11,18 +11,18 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("h,world", [(16384, 1), (16384, 2), (16384, 8), (1024, 4), (1000, 3), (96, 3), (33, 2)])
+@pytest.mark.parametrize("h,world", [(16384, 1), (16384, 2), (16384, 8), (1024, 4), (1000, 3), (96, 3), (33, 2), (192, 4), (288, 8)])
 def test_slab_partition_covers_every_row_once(ifl, h, world):
     parts = ifl.slab_partition(h, world)
     assert len(parts) == world
     rows = []
     for (s0, s1, r0, r1) in parts:
-        assert 0 <= s0 <= s1 and r0 == min(32 * s0, h)
+        assert 0 <= s0 < s1 and r0 == min(32 * s0, h)          # no rank is ever empty (192 rows / 4 ranks, 288 / 8)
         rows += list(range(r0, r1))
     assert rows == list(range(h))
-    # equal chunks except the tail, so that the all-gathers of per-strip partials / pressure slabs are uniform
-    chunk = parts[0][1] - parts[0][0]
-    assert all(p[1] - p[0] <= chunk for p in parts)
+    # balanced: the strip counts differ by at most one, the larger ranges first
+    counts = [p[1] - p[0] for p in parts]
+    assert max(counts) - min(counts) <= 1 and counts == sorted(counts, reverse=True)
 
 
 def test_slab_partition_rejects_more_ranks_than_strips(ifl):
