@@ -284,9 +284,12 @@ typedef enum ifl_kernel {
 int ifl_set_profiling(ifl_solver* s, int32_t enable);
 int ifl_kernel_timing(ifl_solver* s, int32_t which, double* avg_ms, int32_t* samples);
 
-/* Diagnostic for profiles/: per-strip timestamps of one applyPreconditioner(z, r) on the resident
- * state.  out[(sweep*nstrips + k)*8 + i], sweep 0 = forward, 1 = backward; i: 0 enter, 1 after the
- * first block, 2 unused, 3 end (device ns), 4 unused, 5 blocks, 6 ticket slot, 7 SM id. */
+/* Diagnostic for profiles/: per-strip timestamps of the two sweep kernels of one PCG iteration (forward sweep with the
+ * fused r update, backward sweep with the fused dot product) on the resident state; r and z are modified.
+ * out[(sweep*nstrips + k)*16 + i], sweep 0 = forward, 1 = backward; i: 0 enter, 1 after the first block, 3 end (device
+ * ns), 6 ticket slot, 7 SM id; builds with -DIFL_SW_TRACE_WAITS also fill 2, 4, 5, 8 (strip warp: starved steps, time of
+ * blocks 1-3, clocks waiting for credit / edge / operand tiles) and 9-13 (loader warp: clocks waiting for bulk copies,
+ * updating r, issuing copies, total, tiles). */
 int ifl_wavefront_trace(ifl_solver* s, int64_t* out, size_t capacity);
 
 /* Human readable text for the last error on this thread. */

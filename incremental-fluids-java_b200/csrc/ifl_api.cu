@@ -1033,13 +1033,13 @@ int ifl_wavefront_trace(ifl_solver* s, int64_t* out, size_t capacity) {
     if (!s || !out) INVALID("NULL argument");
     if (!uses_pcg(s)) INVALID("wavefront trace needs a PCG variant");
     CU(cudaSetDevice(s->cfg.device));
-    size_t n = (size_t)s->sx.g.nstrips * 16;
-    if (capacity < n) INVALID("capacity < 16 * nstrips");
+    size_t n = (size_t)s->sx.g.nstrips * 32;
+    if (capacity < n) INVALID("capacity < 32 * nstrips");
     long long* d = nullptr;
     CU(cudaMalloc(&d, sizeof(long long) * n));
     CU(cudaMemsetAsync(d, 0, sizeof(long long) * n, s->stream));
     s->sx.trace = d;
-    const int trc = launch_apply_precon(s->sx);
+    const int trc = launch_apply_precon(s->sx, 1);
     s->sx.trace = nullptr;
     if (trc) { cudaFree(d); COMM(trc); }
     CU(cudaMemcpyAsync(out, d, sizeof(long long) * n, cudaMemcpyDeviceToHost, s->stream));

@@ -206,7 +206,7 @@ cudaError_t flip_extrapolate(FlipCtx& f, cudaStream_t st, const SolidQ& q, doubl
 int  solve_partials_needed(const SkewGeom& g);
 int  solve_parity(SolveCtx& c);            /* current generation of z / s (synchronises the stream), -1 on error */
 int  launch_build_precon(SolveCtx& c);
-int  launch_apply_precon(SolveCtx& c);     /* z = M^-1 r on the current generation */
+int  launch_apply_precon(SolveCtx& c, int as_in_loop = 0);     /* z = M^-1 r on the current generation */
 int  pcg_enqueue_init(SolveCtx& c);
 int  pcg_enqueue_iterations(SolveCtx& c, int n);
 int  pcg_enqueue_finish(SolveCtx& c, int limit);

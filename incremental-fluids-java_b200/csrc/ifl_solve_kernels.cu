@@ -219,7 +219,14 @@ k_step_a(SkewGeom g, const double* __restrict__ adiag, const double* __restrict_
          double* partials, double* strip_part, unsigned* strip_ctr, SolveScalars* sc, int dot_mode,
          const unsigned char* __restrict__ fl, int single_gpu, double cscale,
          double* __restrict__ bnd_f, double* __restrict__ bnd_b) {
+    static_assert(SKB == 2 && EW_THREADS == 256, "a thread owns the two cells of one lane and m-row");
+    constexpr int TR = EW_TROWS;                    /* m-rows per block */
+    constexpr int RS = 32 * SKB;                    /* doubles per m-row */
     if (sc->done) return;
+    /* the new s of the block's m-rows plus one m-row before and after (left / right / up / down neighbours inside the
+     * strip are at +-1 m-row), and of the two rows of the neighbouring strips that lanes 0 and 31 look at */
+    __shared__ __align__(16) double S[(TR + 2) * RS];
+    __shared__ __align__(16) double UP[TR * SKB], DN[TR * SKB];
     __shared__ double s_buf[EW_THREADS];
     __shared__ double smem8[8];
     __shared__ int s_flag;
@@ -231,55 +238,168 @@ k_step_a(SkewGeom g, const double* __restrict__ adiag, const double* __restrict_
     double* __restrict__ sout = zp ? s0 : s1;
     const double beta = sc->beta, alpha = sc->alpha;
     const double ms = -cscale;
-    double acc = 0.0;
+    const int k = (int)blockIdx.y + g.s0;
+    const int t0 = (int)blockIdx.x * TR;
+    const long long base = (long long)k * g.ss;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int y = k * 32 + lane;
+    const bool yok = y < g.h;
+    const int w = g.w;
     /* s of cell i after F3:626 (masked F6:1041): the reference's two operations, or the untouched old value */
     auto s_new = [&](long long i) -> double {
         const double sv = sin_[i];
         if (first || (fl != nullptr && !fl[i])) return sv;
         return zin[i] + sv * beta;
     };
-    IFL_EW_LOOP_BEGIN(g)
-        IFL_EW_NEIGHBOURS(g)
-        if (ok_) {
-            const bool act = fl == nullptr || fl[i_];
-            const double sold = sin_[i_];
-            double sc_ = sold;
-            if (!first && act) {
-                p[i_] = p[i_] + sold * alpha;
-                sc_ = zin[i_] + sold * beta;
+
+    /* ---- phase 1: p and s of the own cells (registers + shared memory), s of the halo cells (shared memory) ---- */
+    double sown[TR / 8][SKB];
+#pragma unroll
+    for (int ps = 0; ps < TR / 8; ps++) {
+        const int r = ps * 8 + wrp;                 /* m-row inside the block */
+        const int t = t0 + r;
+        const int x0 = (t - lane) * SKB;
+        const long long i = base + (long long)t * RS + lane * SKB;
+        double sn[SKB] = {0.0, 0.0};
+        if (t < g.tl) {
+            const double2 so = *reinterpret_cast<const double2*>(sin_ + i);
+            double zv[SKB] = {0.0, 0.0}, pv[SKB] = {0.0, 0.0};
+            if (!first) {
+                const double2 zz = *reinterpret_cast<const double2*>(zin + i);
+                const double2 pp = *reinterpret_cast<const double2*>(p + i);
+                zv[0] = zz.x; zv[1] = zz.y; pv[0] = pp.x; pv[1] = pp.y;
             }
-            sout[i_] = sc_;
-            double tv;
+            const double sold[SKB] = {so.x, so.y};
+            bool ok[SKB];
+#pragma unroll
+            for (int j = 0; j < SKB; j++) {
+                ok[j] = yok && x0 + j >= 0 && x0 + j < w;
+                const bool act = ok[j] && !first && (fl == nullptr || fl[i + j]);
+                sn[j] = sold[j];
+                if (act) {
+                    pv[j] = pv[j] + sold[j] * alpha;        /* scaledAdd(_p, _p, _s, alpha)   F3:607 */
+                    sn[j] = zv[j] + sold[j] * beta;         /* scaledAdd(_s, _z, _s, beta)    F3:626 */
+                }
+            }
+            if (ok[0] && ok[1]) {
+                *reinterpret_cast<double2*>(sout + i) = make_double2(sn[0], sn[1]);
+                if (!first) *reinterpret_cast<double2*>(p + i) = make_double2(pv[0], pv[1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < SKB; j++) if (ok[j]) { sout[i + j] = sn[j]; if (!first) p[i + j] = pv[j]; }
+            }
+            if (lane == 0) {                                /* lane 0 works on column block t: re-arm the boundary rows */
+#pragma unroll
+                for (int j = 0; j < SKB; j++) {
+                    const int xb = t * SKB + j;
+                    if (xb < w) {
+                        bnd_f[(long long)k * w + xb] = sentinel();
+                        bnd_b[(long long)k * w + xb] = sentinel();
+                        /* slab decomposition: the rows my neighbours write into (their edge strips) are re-armed by me */
+                        if (k == g.s0 && g.s0 > 0) bnd_f[(long long)(g.s0 - 1) * w + xb] = sentinel();
+                        if (k == g.s1 - 1 && g.s1 < g.nstrips) bnd_b[(long long)g.s1 * w + xb] = sentinel();
+                    }
+                }
+            }
+        }
+        sown[ps][0] = sn[0]; sown[ps][1] = sn[1];
+        *reinterpret_cast<double2*>(&S[(r + 1) * RS + lane * SKB]) = make_double2(sn[0], sn[1]);
+    }
+    if (wrp < 2) {                                          /* m-rows t0 - 1 and t0 + TR of this strip */
+        const int t = wrp == 0 ? t0 - 1 : t0 + TR;
+        double sn[SKB] = {0.0, 0.0};
+        if (t >= 0 && t < g.tl) {
+            const long long i = base + (long long)t * RS + lane * SKB;
+            sn[0] = s_new(i); sn[1] = s_new(i + 1);
+        }
+        *reinterpret_cast<double2*>(&S[(wrp == 0 ? 0 : TR + 1) * RS + lane * SKB]) = make_double2(sn[0], sn[1]);
+    } else if (wrp < 4) {                                   /* the cells above lane 0 / below lane 31 */
+        const int r = lane;                                 /* TR == 32 m-rows, one per thread */
+        const int t = t0 + r;
+        double sn[SKB] = {0.0, 0.0};
+        if (wrp == 2) {                                     /* (x, 32k - 1): strip k-1, lane 31, m-row t + 31 */
+            if (t + 31 < g.tl) {
+                const long long i = base - g.ss + ((long long)(t + 31) * 32 + 31) * SKB;
+                sn[0] = s_new(i); sn[1] = s_new(i + 1);
+            }
+            UP[r * SKB] = sn[0]; UP[r * SKB + 1] = sn[1];
+        } else {                                            /* (x, 32k + 32): strip k+1, lane 0, m-row t - 31 */
+            if (t - 31 >= 0 && t - 31 < g.tl) {
+                const long long i = base + g.ss + (long long)(t - 31) * 32 * SKB;
+                sn[0] = s_new(i); sn[1] = s_new(i + 1);
+            }
+            DN[r * SKB] = sn[0]; DN[r * SKB + 1] = sn[1];
+        }
+    }
+    __syncthreads();
+
+    /* ---- phase 2: z = A s (matrixVectorProduct F3:544-565, never masked) and the partial sums of z.s ---- */
+    double acc = 0.0;
+#pragma unroll
+    for (int ps = 0; ps < TR / 8; ps++) {
+        const int r = ps * 8 + wrp;
+        const int t = t0 + r;
+        if (t >= g.tl) continue;
+        const int x0 = (t - lane) * SKB;
+        const long long i = base + (long long)t * RS + lane * SKB;
+        const double* Sr = &S[(r + 1) * RS + lane * SKB];
+        const double sl0 = Sr[-RS + 1];                     /* (x0 - 1, y): previous m-row, second cell */
+        const double sr1 = Sr[RS];                          /* (x0 + 2, y): next m-row, first cell */
+        const double2 up = lane > 0 ? *reinterpret_cast<const double2*>(Sr - RS - SKB)
+                                    : *reinterpret_cast<const double2*>(&UP[r * SKB]);
+        const double2 dn = lane < 31 ? *reinterpret_cast<const double2*>(Sr + RS + SKB)
+                                     : *reinterpret_cast<const double2*>(&DN[r * SKB]);
+        const double sc_[SKB] = {sown[ps][0], sown[ps][1]};
+        const double sl[SKB] = {sl0, sc_[0]}, sr[SKB] = {sc_[1], sr1};
+        const double su[SKB] = {up.x, up.y}, sd[SKB] = {dn.x, dn.y};
+        double cd[SKB], cl[SKB], cu[SKB], cr[SKB], cdn[SKB];
+        if (!CONSTM) {
+            const double2 ad = *reinterpret_cast<const double2*>(adiag + i);
+            const double2 axc = *reinterpret_cast<const double2*>(ax + i);
+            const double2 ayc = *reinterpret_cast<const double2*>(ay + i);
+            const long long iu = lane > 0 ? i - RS - SKB : base - g.ss + ((long long)(t + 31) * 32 + 31) * SKB;
+            const double2 ayu = *reinterpret_cast<const double2*>(ay + iu);
+            cd[0] = ad.x; cd[1] = ad.y;
+            cl[0] = ax[i - RS + 1]; cl[1] = axc.x;          /* aPlusX of the left neighbour */
+            cu[0] = ayu.x; cu[1] = ayu.y;                   /* aPlusY of the upper neighbour */
+            cr[0] = axc.x; cr[1] = axc.y;
+            cdn[0] = ayc.x; cdn[1] = ayc.y;
+        }
+        double tv[SKB];
+        bool ok[SKB];
+#pragma unroll
+        for (int j = 0; j < SKB; j++) {
+            const int x = x0 + j;
+            ok[j] = yok && x >= 0 && x < w;
             if (CONSTM) {
                 double dg = 0.0;
-                if (y_ > 0) dg += cscale;
-                if (x_ > 0) dg += cscale;
-                if (x_ < g.w - 1) dg += cscale;
-                if (y_ < g.h - 1) dg += cscale;
-                tv = dg * sc_;
-                if (x_ > 0) tv += ms * s_new(nl_);
-                if (y_ > 0) tv += ms * s_new(nu_);
-                if (x_ < g.w - 1) tv += ms * s_new(nr_);
-                if (y_ < g.h - 1) tv += ms * s_new(nd_);
+                if (y > 0) dg += cscale;
+                if (x > 0) dg += cscale;
+                if (x < w - 1) dg += cscale;
+                if (y < g.h - 1) dg += cscale;
+                double v = dg * sc_[j];
+                if (x > 0) v += ms * sl[j];
+                if (y > 0) v += ms * su[j];
+                if (x < w - 1) v += ms * sr[j];
+                if (y < g.h - 1) v += ms * sd[j];
+                tv[j] = v;
             } else {
-                tv = adiag[i_] * sc_;
-                if (x_ > 0) tv += ax[nl_] * s_new(nl_);
-                if (y_ > 0) tv += ay[nu_] * s_new(nu_);
-                if (x_ < g.w - 1) tv += ax[i_] * s_new(nr_);
-                if (y_ < g.h - 1) tv += ay[i_] * s_new(nd_);
+                double v = cd[j] * sc_[j];
+                if (x > 0) v += cl[j] * sl[j];
+                if (y > 0) v += cu[j] * su[j];
+                if (x < w - 1) v += cr[j] * sr[j];
+                if (y < g.h - 1) v += cdn[j] * sd[j];
+                tv[j] = v;
             }
-            zout[i_] = tv;                                  /* matrixVectorProduct is never masked (F6:1011) */
-            if (act) acc += tv * sc_;                       /* dotProduct: fluid cells only from F6 on (F6:999) */
+            /* dotProduct: fluid cells only from F6 on (F6:999) */
+            if (ok[j] && (fl == nullptr || fl[i + j])) acc += tv[j] * sc_[j];
         }
-        if (l_ == 0 && t_ * SKB + j_ < g.w) {
-            const int xb = t_ * SKB + j_;                  /* lane 0 works on column block t_ */
-            bnd_f[(long long)k_ * g.w + xb] = sentinel();
-            bnd_b[(long long)k_ * g.w + xb] = sentinel();
-            /* slab decomposition: the rows my neighbours write into (their edge strips) are re-armed by me */
-            if (k_ == g.s0 && g.s0 > 0) bnd_f[(long long)(g.s0 - 1) * g.w + xb] = sentinel();
-            if (k_ == g.s1 - 1 && g.s1 < g.nstrips) bnd_b[(long long)g.s1 * g.w + xb] = sentinel();
+        if (ok[0] && ok[1]) *reinterpret_cast<double2*>(zout + i) = make_double2(tv[0], tv[1]);
+        else {
+#pragma unroll
+            for (int j = 0; j < SKB; j++) if (ok[j]) zout[i + j] = tv[j];
         }
-    IFL_EW_LOOP_END
+    }
     const double bs = block_sum_256(acc, smem8);
     if (finish_partials(bs, partials, g, strip_part, strip_ctr, sc, dot_mode, single_gpu, &s_flag, s_buf) && threadIdx.x == 0) {
         sc->zpar = zp ^ 1;
@@ -865,7 +985,10 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
     constexpr int UB = SW_FG;                                         /* macro-steps per block of the loop */
     constexpr int S = SW_STAGES;
     constexpr int STAGE = ((WITH_DOT || FUSE) ? 2 : 1) * SW_TILE + SW_PACK;   /* doubles per stage */
-    constexpr int LAG = 3;                                            /* FUSE: tiles between a bulk copy and its r update (< S - 1) */
+#ifndef IFL_SW_LAG
+#define IFL_SW_LAG 2
+#endif
+    constexpr int LAG = IFL_SW_LAG;                                   /* FUSE: tiles between a bulk copy and its r update (< S - 1) */
     static_assert(LAG < SW_STAGES - 1, "the strip warp needs tile b+1 before it releases tile b");
     constexpr int E_IN = DIR > 0 ? 0 : 31;
     constexpr int E_OUT = DIR > 0 ? 31 : 0;
@@ -954,59 +1077,103 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
             /* one tile more than the strip has: the strip warp prefetches across every tile boundary without a test */
             if (lane == 0) for (int b = 0; b <= ntile; b++) issue_tile(b);
         } else {
-            /* Lane 0 keeps issuing bulk copies LAG tiles ahead; the whole warp then updates r in the tile that arrived
-             * LAG tiles ago (lane l owns the SKB cells of row l in every m-row, like the strip warp) and releases it to
-             * the strip warp through the `ready` barrier.  Only cells inside the grid are touched: the padding of r and
-             * z stays zero whatever alpha is. */
+            /* Every round the whole warp first updates r in the tile whose bulk copies were issued LAG rounds ago (lane l
+             * owns the SKB cells of row l in every m-row, like the strip warp) and releases it to the strip warp through
+             * the `ready` barrier; lane 0 then issues the next tile's copies as soon as the strip warp has handed a stage
+             * back.  The update therefore runs 2-3 tiles ahead of the strip warp and never on its critical path.  Only
+             * cells inside the grid are touched: the padding of r and z stays zero whatever alpha is. */
             const int y = k * 32 + lane;
             const bool yok = y < g.h;
             const double nalpha = sc->neg_alpha;
-            const unsigned ring_lane = smem_u32(ring + lane * SKB);
-            const unsigned ready0 = smem_u32(bar_ready);
             double* const rout = const_cast<double*>(src) + (long long)k * g.ss + lane * SKB;
             unsigned mloc = 0;
+#ifdef IFL_SW_TRACE_WAITS
+            long long hw_full = 0, hw_proc = 0, hw_issue = 0;
+            const long long hw_start = clock64();
+#define IFL_HW(acc, stmt) { const long long c0_ = clock64(); stmt; acc += clock64() - c0_; }
+#else
+#define IFL_HW(acc, stmt) { stmt; }
+#endif
             for (int b = 0; b <= ntile + LAG; b++) {
-                if (b <= ntile && lane == 0) issue_tile(b);
-                __syncwarp();
                 const int pb = b - LAG;
-                if (pb < 0) continue;
-                const int sp = pb % S;
-                mbar_wait_u32(full0 + 8u * (unsigned)sp, (unsigned)(pb / S) & 1u);
-                if (pb < ntile) {
-                    const unsigned tile = ring_lane + (unsigned)(sp * STAGE * (int)sizeof(double));
+                if (pb >= 0) {
+                    const int sp = pb % S;
+                    IFL_HW(hw_full, mbar_wait_u32(full0 + 8u * (unsigned)sp, (unsigned)(pb / S) & 1u))
+#ifdef IFL_SW_TRACE_WAITS
+                    const long long hw_p0 = clock64();
+#endif
+                    if (pb < ntile) {
+                        double* const tl_r = ring + (size_t)sp * STAGE + lane * SKB;      /* r tile, this lane's cells */
+                        const double* const tl_z = tl_r + SW_TILE + SW_PACK;              /* z = A s */
+                        const double* const tl_p = tl_r + 3 * SW_TILE;                    /* precon (NaN: not fluid) */
+                        const int tbase = pb * U;
+                        /* every cell of the tile inside the grid: plain 16-byte accesses, no predicates */
+                        const bool inner = yok && (tbase - lane) >= 0 && ((tbase + U - 1 - lane) * SKB + SKB - 1) < w;
+                        if (__all_sync(0xffffffffu, inner) && FUSE == 1) {
 #pragma unroll
-                    for (int e = 0; e < U; e++) {
-                        const int t = pb * U + e;
-                        const int x0 = (t - lane) * SKB;
-                        const unsigned a_r = tile + (unsigned)(e * 32 * SKB * (int)sizeof(double));
-                        double rv[SKB], zv[SKB], pv[SKB];
-                        lds_cells(a_r, rv);
-                        lds_cells(a_r + (unsigned)((SW_TILE + SW_PACK) * sizeof(double)), zv);
-                        if (FUSE == 2) lds_cells(a_r + 3 * SW_TILE * (unsigned)sizeof(double), pv);
-                        bool ok[SKB];
+                            for (int e = 0; e < U; e++) {
+#ifndef IFL_DBG_NOPROC
+                                const double2 rv = *reinterpret_cast<const double2*>(tl_r + e * 32 * SKB);
+                                const double2 zv = *reinterpret_cast<const double2*>(tl_z + e * 32 * SKB);
+                                const double n0 = rv.x + zv.x * nalpha, n1 = rv.y + zv.y * nalpha;    /* a[i] + b[i]*s  F3:573 */
+#ifndef IFL_DBG_NOMAX
+                                const unsigned b0 = absf_bits(n0), b1 = absf_bits(n1);                /* abs((float) a[i])  F3:582 */
+                                mloc = b0 > mloc ? b0 : mloc;
+                                mloc = b1 > mloc ? b1 : mloc;
+#endif
+                                *reinterpret_cast<double2*>(tl_r + e * 32 * SKB) = make_double2(n0, n1);
+#ifndef IFL_DBG_NOSTG
+                                *reinterpret_cast<double2*>(rout + (long long)(tbase + e) * (32 * SKB)) = make_double2(n0, n1);
+#endif
+#endif
+                            }
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < SKB; j++) {
-                            ok[j] = yok && x0 + j >= 0 && x0 + j < w;
-                            if (FUSE == 2) ok[j] = ok[j] && (pv[j] == pv[j]);     /* NaN precon tags a non-fluid cell */
-                            const double nv = rv[j] + zv[j] * nalpha;             /* a[i] + b[i]*s  F3:573 */
-                            if (ok[j]) {
-                                rv[j] = nv;
-                                const unsigned bits = absf_bits(nv);              /* abs((float) a[i])  F3:582 */
-                                mloc = bits > mloc ? bits : mloc;
+                            for (int e = 0; e < U; e++) {
+                                const int t = tbase + e;
+                                const int x0 = (t - lane) * SKB;
+                                const double2 rv2 = *reinterpret_cast<const double2*>(tl_r + e * 32 * SKB);
+                                const double2 zv2 = *reinterpret_cast<const double2*>(tl_z + e * 32 * SKB);
+                                double rv[SKB] = {rv2.x, rv2.y};
+                                const double zv[SKB] = {zv2.x, zv2.y};
+                                double pv[SKB] = {0.0, 0.0};
+                                if (FUSE == 2) { const double2 q = *reinterpret_cast<const double2*>(tl_p + e * 32 * SKB); pv[0] = q.x; pv[1] = q.y; }
+                                bool ok[SKB];
+#pragma unroll
+                                for (int j = 0; j < SKB; j++) {
+                                    ok[j] = yok && x0 + j >= 0 && x0 + j < w;
+                                    if (FUSE == 2) ok[j] = ok[j] && (pv[j] == pv[j]);     /* NaN precon tags a non-fluid cell */
+                                    const double nv = rv[j] + zv[j] * nalpha;
+                                    if (ok[j]) {
+                                        rv[j] = nv;
+                                        const unsigned bits = absf_bits(nv);
+                                        mloc = bits > mloc ? bits : mloc;
+                                    }
+                                }
+                                *reinterpret_cast<double2*>(tl_r + e * 32 * SKB) = make_double2(rv[0], rv[1]);
+                                double* gp = rout + (long long)t * (32 * SKB);
+                                if (ok[0] && ok[1]) *reinterpret_cast<double2*>(gp) = make_double2(rv[0], rv[1]);
+                                else {
+#pragma unroll
+                                    for (int j = 0; j < SKB; j++) if (ok[j]) gp[j] = rv[j];
+                                }
                             }
                         }
-                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a_r), "d"(rv[0]), "d"(rv[SKB - 1]) : "memory");
-                        double* gp = rout + (long long)t * (32 * SKB);
-                        if (ok[0] && ok[SKB - 1]) *reinterpret_cast<double2*>(gp) = make_double2(rv[0], rv[SKB - 1]);
-                        else {
-#pragma unroll
-                            for (int j = 0; j < SKB; j++) if (ok[j]) gp[j] = rv[j];
-                        }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_ready[sp]);
+#ifdef IFL_SW_TRACE_WAITS
+                    hw_proc += clock64() - hw_p0;
+#endif
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_ready[sp]);
+                IFL_HW(hw_issue, if (b <= ntile && lane == 0) issue_tile(b); __syncwarp())
             }
+#ifdef IFL_SW_TRACE_WAITS
+            if (trace && lane == 0) {
+                long long* tr = trace + (long long)k * 16;
+                tr[9] = hw_full; tr[10] = hw_proc; tr[11] = hw_issue; tr[12] = clock64() - hw_start; tr[13] = ntile;
+            }
+#endif
             /* maxError and the convergence decision (F3:609-619) once every strip of this rank has updated its r */
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -1296,11 +1463,12 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
             }
         }
         if (trace && lane == 0) {
-            long long* tr = trace + (long long)k * 8;
+            long long* tr = trace + (long long)k * 16;
             tr[0] = tr_enter; tr[1] = tr_first; tr[2] = 0; tr[3] = (long long)globaltimer_ns();
             tr[4] = 0; tr[5] = nblk; tr[6] = slot; tr[7] = (long long)get_smid();
 #ifdef IFL_SW_TRACE_WAITS
             tr[2] = tw_nstarved * 1000000 + tw_nspins; tr[4] = tw_t4 - tr_first; tr[5] = tw_credit + tw_edge;
+            tr[8] = tw_op;
 #endif
         }
     }
@@ -1652,7 +1820,7 @@ static int enqueue_precon(SolveCtx& c, int fuse_r_update, int dot_mode, int chec
     }
     prof_mark(c, ps, 2);
     int fused_mode = c.sequential ? DOT_NONE : dot_mode;
-    long long* tr2 = c.trace ? c.trace + 8 * c.g.nstrips : nullptr;
+    long long* tr2 = c.trace ? c.trace + 16 * c.g.nstrips : nullptr;
     if (dot_mode != DOT_NONE) {
         if (masked) launch_sweep<-1, true, true, 0>(c, nullptr, c.pack_b, c.r, c.bnd_b, fused_mode, check_done, tr2);
         else        launch_sweep<-1, true, false, 0>(c, nullptr, c.pack_b, c.r, c.bnd_b, fused_mode, check_done, tr2);
@@ -1670,12 +1838,14 @@ static int enqueue_precon(SolveCtx& c, int fuse_r_update, int dot_mode, int chec
 }
 
 /* applyPreconditioner(z, r) on its own (IFL_STAGE_APPLY_PRECON, the wavefront trace) */
-int launch_apply_precon(SolveCtx& c) {
+int launch_apply_precon(SolveCtx& c, int as_in_loop) {
     k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
     count(c);
     /* slab decomposition: no neighbour may store into an inbox row before its owner has re-armed it */
     if (!single_gpu(c)) IFL_TRY(comm_all_gather(*c.comm, c.rank_max + c.comm->rank, c.rank_max, sizeof(unsigned long long)));
-    return enqueue_precon(c, 0, DOT_NONE, 0);
+    /* as_in_loop (wavefront trace): the kernels of a PCG iteration -- r update fused into the forward sweep, dot product
+     * fused into the backward sweep -- with whatever alpha the last solve left behind */
+    return as_in_loop ? enqueue_precon(c, 1, DOT_SIGMA_NEW, 0) : enqueue_precon(c, 0, DOT_NONE, 0);
 }
 
 /* z = A s on the current generation (IFL_STAGE_MATVEC) */

@@ -261,11 +261,11 @@ class FluidSolver:
         return ms.value, n.value
 
     def wavefront_trace(self):
-        """Per-strip timestamps of one applyPreconditioner: array [2 sweeps][nstrips][8] (see the header)."""
+        """Per-strip timestamps of the two sweep kernels of a PCG iteration: array [2 sweeps][nstrips][16] (see the header)."""
         nstrips = (self._h + 31) // 32
-        out = np.zeros(2 * nstrips * 8, dtype=np.int64)
+        out = np.zeros(2 * nstrips * 16, dtype=np.int64)
         check(self._fn["ifl_wavefront_trace"](self._h_, out.ctypes.data_as(C.POINTER(C.c_int64)), out.size))
-        return out.reshape(2, nstrips, 8)
+        return out.reshape(2, nstrips, 16)
 
     def last_timing(self):
         out = (C.c_double * 3)()
