@@ -103,7 +103,10 @@ typedef enum ifl_flags {
     /* F8 only: always replay FluidQuantity.extrapolate's LIFO stack (F8:651) with one device thread instead of the
      * level-parallel sweep.  The library switches to the replay by itself whenever two CELL_EMPTY cells touch (the
      * only case in which the reference's result depends on its stack order); the flag exists to test that path. */
-    IFL_FLAG_SEQUENTIAL_EXTRAPOLATE = 2
+    IFL_FLAG_SEQUENTIAL_EXTRAPOLATE = 2,
+    /* PCG: run scaledAdd(_r, _r, _z, -alpha) + infinityNorm (F3:608-609) as a kernel of its own instead of inside the
+     * forward triangular sweep (same operations, same bits; exists to test and time both arrangements). */
+    IFL_FLAG_SEPARATE_R_UPDATE = 4
 } ifl_flags;
 
 /* Rigid body table entry = the fields of A_SolidBody (solidBodies/A_SolidBody.java:73-87).

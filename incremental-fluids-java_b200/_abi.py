@@ -20,6 +20,7 @@ BODY_BOX, BODY_SPHERE = 0, 1
 # ifl_flags
 FLAG_SEQUENTIAL_REDUCTIONS = 1
 FLAG_SEQUENTIAL_EXTRAPOLATE = 2
+FLAG_SEPARATE_R_UPDATE = 4
 
 
 class Config(C.Structure):
