@@ -60,14 +60,14 @@ __device__ __forceinline__ double cerp(double a, double b, double c, double d, c
 
 /* ---- strip-skewed layout ------------------------------------------------------
  * Every N-vector of the pressure solve (r p z s aDiag aPlusX aPlusY precon) lives in a
- * layout made for the lexicographic recurrences.  Rows are grouped in strips of 32; in strip k
- * the cell (x, y = 32k + l) is stored at   k*SS + (x + l)*32 + l.
- * One "m-row" m = x + l is what a warp (lane l = row l) processes in one wavefront step: the
- * anti-diagonal x = m - l.  The m-row is 32 contiguous doubles (every wavefront access is one
- * coalesced 256-byte line) and a strip is one contiguous stream.  tl = m-rows per strip (>= w + 31).
- * (IFL_SKB > 1 would give every lane IFL_SKB consecutive cells per step; the kernels are written for 1:
- * lane l+1 trails lane l by one cell, the least the recurrence allows.) */
-#define IFL_SKB 1
+ * layout made for the lexicographic recurrences.  Rows are grouped in strips of 32 and
+ * columns in blocks of IFL_SKB cells; in strip k the cell (x, y = 32k + l), x = c*SKB + j,
+ * is stored at   k*SS + ((c + l)*32 + l)*SKB + j.
+ * One "m-row" m = c + l is what a warp (lane l = row l) processes in one wavefront step:
+ * every lane owns SKB consecutive cells of its row (a register-resident chain), the m-row is
+ * 32*SKB contiguous doubles, and a strip is one contiguous stream.  tl = m-rows per strip
+ * (>= ceil(w/SKB) + 31). */
+#define IFL_SKB 2
 struct SkewGeom {
     int w, h;
     int nstrips;
