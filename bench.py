@@ -72,6 +72,21 @@ A_KERNEL_BYTES = {"step_a": 48, "precon_fwd": 56, "precon_bwd": 48, "gs_sweep": 
 A_KERNEL_BYTES_MASKED = {"step_a": 48 + 24 + 1, "precon_fwd": 56, "precon_bwd": 48, "gs_sweep": 24}   # + aDiag,aPlusX,aPlusY,cell
 
 
+class quiet_stdout:
+    """NCCL prints its version banner on stdout the first time a communicator is made (whatever NCCL_DEBUG says in some
+    builds): route fd 1 to stderr meanwhile, so that stdout carries nothing but the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -276,7 +291,8 @@ def state_hash(np, arrays_with_row0):
 
 def timed_gpu_run(torch, ifl, wl, steps, warmup, local_rank, flush, barrier, max_over_ranks, comm_kw, profile=True):
     """warm-up, then `steps` timed steps with resident state; returns a dict of measurements and the live solver"""
-    g = make_gpu_solver(ifl, wl, device=local_rank, **comm_kw())
+    with quiet_stdout():
+        g = make_gpu_solver(ifl, wl, device=local_rank, **comm_kw())
     if wl.get("particles"):
         g.particle_count()                        # F8: initParticles (constructor work) outside the timed region
     for _ in range(warmup):
@@ -369,7 +385,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with quiet_stdout():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
 
     def comm_kw():
         """every slab-decomposed solver group needs its own id (an ncclUniqueId), made by rank 0 and broadcast"""
@@ -430,7 +448,8 @@ def main():
     # ------------------------------------------------------------- end-to-end arm (host state)
     e2e = None
     if not args.no_e2e:
-        g2 = make_gpu_solver(ifl, wl, device=local_rank, **comm_kw())
+        with quiet_stdout():
+            g2 = make_gpu_solver(ifl, wl, device=local_rank, **comm_kw())
         shapes = {"d": (H, W), "t": (H, W), "u": (H, W + 1), "v": (H + 1, W)}
         host = {}
         for f in wl["fields"]:

@@ -86,8 +86,9 @@ typedef struct ifl_config {
     uint64_t rng_seed;
     int32_t device;           /* CUDA device ordinal */
     /* Slab decomposition.  world_size == 1: single GPU.
-     * world_size > 1: this process owns rows [rank*h/world, (rank+1)*h/world)
-     * and comm_id holds the 128-byte ncclUniqueId all ranks share. */
+     * world_size > 1: this process (one process per rank: the strip hand-over maps the neighbours' memory with CUDA IPC)
+     * owns a contiguous range of 32-row strips, see ifl_slab_rows(); comm_id holds the 128-byte ncclUniqueId all ranks
+     * share. */
     int32_t rank;
     int32_t world_size;
     int32_t flags;            /* ifl_flags, 0 = default */
@@ -195,8 +196,10 @@ int ifl_default_config(ifl_config* cfg, int32_t variant, int32_t w, int32_t h);
 
 /* Slab decomposition (the reference has no distributed path).  Rank 0 obtains a 128-byte id
  * (an ncclUniqueId), the host program broadcasts it to the other ranks by any means, and every rank passes it in
- * ifl_config.comm_id together with its rank / world_size.  One process per GPU.  Rank r owns the 32-row strips
- * [r*chunk, (r+1)*chunk) of the pressure solve; everything outside the solve is computed redundantly per rank. */
+ * ifl_config.comm_id together with its rank / world_size.  One process per GPU.  Every rank computes only the rows it
+ * owns (ifl_slab_rows): RHS, PCG, applyPressure and the semi-Lagrangian advection, whose halo of
+ * ceil(dt * max|v| / hx) + 4 rows is sized every step from a CFL reduction over all ranks (cf. maxTimestep F1:309) and
+ * exchanged with ncclSend/ncclRecv.  Implemented for variant 3. */
 int ifl_comm_unique_id(uint8_t out[128]);
 
 /* new FluidSolver(...)  -- F1:262 F3:339 F4:594 F6:763 F7:769 F8:858 */
@@ -236,6 +239,14 @@ int ifl_field_size(const ifl_solver* s, int32_t field, size_t* count);
 /* Copy a field device -> host / host -> device.  `count` must equal ifl_field_size. */
 int ifl_read_field(ifl_solver* s, int32_t field, double* host, size_t count);
 int ifl_write_field(ifl_solver* s, int32_t field, const double* host, size_t count);
+/* Rows [row0, row0 + nrows) of a field (count = nrows * row length).  In a slab decomposition a rank holds -- and a
+ * host reads and writes -- only the rows it owns, ifl_slab_rows(); the whole-field calls above return
+ * IFL_ERR_UNSUPPORTED there. */
+int ifl_read_field_rows(ifl_solver* s, int32_t field, int32_t row0, int32_t nrows, double* host, size_t count);
+int ifl_write_field_rows(ifl_solver* s, int32_t field, int32_t row0, int32_t nrows, const double* host, size_t count);
+/* The rows of `field` this rank owns: the rows of its 32-row strips (balanced contiguous ranges: nstrips / world strips
+ * each, the first nstrips % world ranks one more); the extra last row of v / phi belongs to the last rank. */
+int ifl_slab_rows(const ifl_solver* s, int32_t field, int32_t* row0, int32_t* nrows);
 
 /* F8 particles: positions and the four per-particle properties (d,t,u,v order, F8:883-886). */
 int ifl_particle_count(ifl_solver* s, int32_t* count);

@@ -99,6 +99,9 @@ PROTOTYPES = {
     "ifl_field_size": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_size_t)]),
     "ifl_read_field": (C.c_int, [C.c_void_p, C.c_int32, _dp, C.c_size_t]),
     "ifl_write_field": (C.c_int, [C.c_void_p, C.c_int32, _dp, C.c_size_t]),
+    "ifl_read_field_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp, C.c_size_t]),
+    "ifl_write_field_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp, C.c_size_t]),
+    "ifl_slab_rows": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ifl_particle_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "ifl_read_particles": (C.c_int, [C.c_void_p] + [_dp] * 6 + [C.c_size_t]),
     "ifl_write_particles": (C.c_int, [C.c_void_p] + [_dp] * 6 + [C.c_size_t]),

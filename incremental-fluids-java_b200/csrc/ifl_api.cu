@@ -54,7 +54,9 @@ struct ifl_solver {
     cudaStream_t stream = nullptr;
     Quantity d, t, u, v;
     SolveCtx sx{};
-    double* skew_block = nullptr;      /* one allocation holding the 8 skewed N-vectors */
+    double* skew_block = nullptr;      /* one allocation holding the skewed N-vectors */
+    double* pack_alloc = nullptr;      /* packed sweep coefficients of this rank's strips (forward | backward) */
+    size_t slab_bytes = 0;             /* bytes of the solver vectors + packed coefficients on this rank */
     double* scratch = nullptr;         /* (w+1)*(h+1) doubles for layout conversions */
     SolveScalars* h_sc = nullptr;      /* pinned mirrors for convergence polling (2 in flight) */
     unsigned long long* d_maxbits = nullptr;
@@ -78,6 +80,7 @@ struct ifl_solver {
     FlipCtx flip;
     Comm comm;
     double inflow[8] = {0.45, 0.2, 0.2, 0.05, 1.0, 294.0, 0.0, 0.0};   /* F8:1330 */
+    int last_halo = 0;                 /* slab decomposition: halo rows of the last advection */
 };
 
 static bool uses_pcg(const ifl_solver* s) { return s->cfg.variant >= IFL_F3_CONJUGATE_GRADIENTS; }
@@ -168,8 +171,7 @@ void ifl_destroy(ifl_solver* s) {
     flip_free(s->flip);
     if (s->skew_block) cudaFree(s->skew_block);
     if (s->scratch) cudaFree(s->scratch);
-    if (s->sx.pack_f) cudaFree(s->sx.pack_f);
-    if (s->sx.pack_b) cudaFree(s->sx.pack_b);
+    if (s->pack_alloc) cudaFree(s->pack_alloc);
     comm_destroy(s->comm);
     if (s->sx.bnd_f) cudaFree(s->sx.bnd_f);
     if (s->sx.strip_part) cudaFree(s->sx.strip_part);
@@ -232,21 +234,32 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     slab_range(g.nstrips, world, cfg->rank, &g.s0, &g.s1);
     g.total = (long long)strips_alloc * g.ss;
     /* one all-zero strip before and after each vector: the wavefront kernels read the
-     * "row above the first" / "row below the last" from there instead of branching */
+     * "row above the first" / "row below the last" from there instead of branching.
+     * Slab decomposition: the vectors only the solver loop touches (r p z s, both generations) and the packed sweep
+     * coefficients hold this rank's strips plus one halo strip on either side; they are addressed with the GLOBAL strip
+     * index through a base pointer shifted by -s0 strips.  The matrix and the MIC(0) factor stay whole-grid: the factor
+     * is a recurrence from strip 0 that every rank repeats for itself (its inputs depend on the grid position only). */
     const size_t guard = (size_t)g.ss;
     const size_t per = (size_t)g.total + 2 * guard;
-    const int nvec = 10;
-    CU(cudaMalloc(&s->skew_block, sizeof(double) * per * nvec));
-    CU(cudaMemset(s->skew_block, 0, sizeof(double) * per * nvec));
-    double** vecs[nvec] = {&s->sx.r, &s->sx.p, &s->sx.zb[0], &s->sx.zb[1], &s->sx.sb[0], &s->sx.sb[1],
-                           &s->sx.adiag, &s->sx.aplusx, &s->sx.aplusy, &s->sx.precon};
-    for (int i = 0; i < nvec; i++) *vecs[i] = s->skew_block + per * i + guard;
-    const size_t npack = (size_t)strips_alloc * g.tl * 32 * IFL_SKB * 3;
-    CU(cudaMalloc(&s->sx.pack_f, sizeof(double) * npack));
-    CU(cudaMalloc(&s->sx.pack_b, sizeof(double) * npack));
-    CU(cudaMemset(s->sx.pack_f, 0, sizeof(double) * npack));
-    CU(cudaMemset(s->sx.pack_b, 0, sizeof(double) * npack));
-    /* both boundary-row sets in ONE allocation: it is the inbox the neighbour ranks map through CUDA IPC */
+    const int nown = g.s1 - g.s0;
+    const size_t per_slab = (size_t)(nown + 2) * g.ss;
+    const int nfull = 4, nslab = 6;
+    s->slab_bytes = sizeof(double) * (per * nfull + per_slab * nslab);
+    CU(cudaMalloc(&s->skew_block, s->slab_bytes));
+    CU(cudaMemset(s->skew_block, 0, s->slab_bytes));
+    double** full_vecs[nfull] = {&s->sx.adiag, &s->sx.aplusx, &s->sx.aplusy, &s->sx.precon};
+    for (int i = 0; i < nfull; i++) *full_vecs[i] = s->skew_block + per * i + guard;
+    double** slab_vecs[nslab] = {&s->sx.r, &s->sx.p, &s->sx.zb[0], &s->sx.zb[1], &s->sx.sb[0], &s->sx.sb[1]};
+    double* slab0 = s->skew_block + per * nfull;
+    for (int i = 0; i < nslab; i++) *slab_vecs[i] = slab0 + per_slab * i + (long long)(1 - g.s0) * g.ss;
+    s->sx.p_first = slab0 + per_slab * 1 + g.ss;            /* this rank's strips of p (what a solve starts by clearing) */
+    const size_t pstrip = (size_t)g.tl * 32 * IFL_SKB * 3;
+    const size_t npack = (size_t)nown * pstrip;
+    CU(cudaMalloc(&s->pack_alloc, sizeof(double) * npack * 2));
+    CU(cudaMemset(s->pack_alloc, 0, sizeof(double) * npack * 2));
+    s->sx.pack_f = s->pack_alloc - (long long)g.s0 * pstrip;
+    s->sx.pack_b = s->pack_alloc + npack - (long long)g.s0 * pstrip;
+    s->slab_bytes += sizeof(double) * npack * 2;
     size_t nb = (size_t)strips_alloc * g.w;
     CU(cudaMalloc(&s->sx.bnd_f, sizeof(double) * nb * 2));
     s->sx.bnd_b = s->sx.bnd_f + nb;
@@ -457,7 +470,7 @@ static int stage_project(ifl_solver* s, double timestep) {
     if (uses_pcg(s)) COMM(pcg_enqueue_init(c)); else gs_enqueue_begin(c);
     int rc = run_solver_loop(s, timestep);
     if (rc) return rc;
-    if (uses_pcg(s)) { COMM(pcg_enqueue_finish(c, s->cfg.solver_limit)); COMM(pcg_gather_pressure(c)); }
+    if (uses_pcg(s)) COMM(pcg_enqueue_finish(c, s->cfg.solver_limit));
     else gs_enqueue_finish(c, s->cfg.solver_limit);
     return IFL_OK;
 }
@@ -467,9 +480,20 @@ static int stage_apply_pressure(ifl_solver* s, double timestep) {
     s->launches++;
     return IFL_OK;
 }
+/* rows of quantity q that `rank` owns in the slab decomposition: the rows of its strips; the extra row h of v belongs to
+ * the rank that owns row h-1.  (Everything on a single GPU.) */
+static void owned_rows(const ifl_solver* s, const Quantity& q, int rank, int* r0, int* r1) {
+    int s0, s1;
+    slab_range(s->sx.g.nstrips, s->cfg.world_size, rank, &s0, &s1);
+    *r0 = 32 * s0 < s->h ? 32 * s0 : s->h;
+    *r1 = 32 * s1 < s->h ? 32 * s1 : s->h;
+    if (*r1 == s->h) *r1 = q.q.h;
+}
 static int stage_advect(ifl_solver* s, Quantity& q, double timestep) {
+    int r0, r1;
+    owned_rows(s, q, s->cfg.rank, &r0, &r1);
     launch_advect(s->stream, s->cfg.variant, q.q, q.src(), q.dst(), s->u.q, s->u.src(), s->v.q, s->v.src(),
-                  timestep, s->hx);
+                  timestep, s->hx, r0, r1);
     s->launches++;
     return IFL_OK;
 }
@@ -702,9 +726,89 @@ static int update_flip(ifl_solver* s, double timestep) {
     return IFL_OK;
 }
 
+/* ---- slab decomposition (F3) --------------------------------------------------------------------------------------- */
+/* Halo rows of one row-major quantity: every rank receives the rows [r0 - above, r1 + below) of q it does not own from
+ * their owners and sends the rows it owns that others need -- one grouped set of ncclSend/ncclRecv straight from / into
+ * the field (rows are contiguous).  `above` / `below` are the same on every rank. */
+static int slab_exchange_halo(ifl_solver* s, Quantity& q, int above, int below) {
+    const int world = s->cfg.world_size, me = s->cfg.rank;
+    std::vector<CommXfer> x;
+    int m0, m1;
+    owned_rows(s, q, me, &m0, &m1);
+    const long long width = q.q.w;
+    auto clip = [&](long long v) { return v < 0 ? 0LL : (v > q.q.h ? (long long)q.q.h : v); };
+    const long long need0 = clip((long long)m0 - above), need1 = clip((long long)m1 + below);
+    for (int p = 0; p < world; p++) {
+        if (p == me) continue;
+        int p0, p1;
+        owned_rows(s, q, p, &p0, &p1);
+        /* what I need from p */
+        long long lo = need0 > p0 ? need0 : p0, hi = need1 < p1 ? need1 : p1;
+        if (hi > lo) x.push_back(CommXfer{p, q.src() + lo * width, (size_t)((hi - lo) * width), 0});
+        /* what p needs from me */
+        const long long pn0 = clip((long long)p0 - above), pn1 = clip((long long)p1 + below);
+        lo = pn0 > m0 ? pn0 : m0; hi = pn1 < m1 ? pn1 : m1;
+        if (hi > lo) x.push_back(CommXfer{p, q.src() + lo * width, (size_t)((hi - lo) * width), 1});
+    }
+    COMM(comm_transfers(s->comm, x.data(), (int)x.size()));
+    return IFL_OK;
+}
+/* Rows a semi-Lagrangian backtrace can leave its slab by: ceil(timestep * max|v| / hx) + 4 (the three RK3 samples stay
+ * within timestep*max|v|/hx of the start, F3:255-275; the Catmull-Rom stencil adds two rows, the face offsets one).
+ * max|v| is the CFL reduction of maxTimestep (F1:309-333) restricted to the vertical component, over ALL ranks. */
+static int slab_advection_halo(ifl_solver* s, double timestep, int* halo) {
+    int r0, r1;
+    owned_rows(s, s->v, s->cfg.rank, &r0, &r1);
+    unsigned long long* slot = s->sx.rank_max + s->cfg.rank;
+    CU(cudaMemsetAsync(slot, 0, sizeof(unsigned long long), s->stream));
+    launch_max_abs_rows(s->stream, s->v.src(), s->w, r0, r1, slot);
+    s->launches++;
+    COMM(comm_all_gather_u64(s->comm, s->sx.rank_max));
+    unsigned long long h_bits[64];
+    CU(cudaMemcpyAsync(h_bits, s->sx.rank_max, sizeof(unsigned long long) * s->cfg.world_size, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    double vmax = 0.0;
+    bool bad = false;
+    for (int r = 0; r < s->cfg.world_size; r++) {
+        double v; memcpy(&v, &h_bits[r], sizeof v);
+        if (!(v == v) || v > 1e300) bad = true;
+        if (v > vmax) vmax = v;
+    }
+    const double cells = std::fabs(timestep) * vmax / s->hx;
+    *halo = (bad || cells > (double)s->h) ? s->h : (int)std::ceil(cells) + 4;
+    s->last_halo = *halo;
+    return IFL_OK;
+}
+/* FluidSolver.update F3:361 on a slab: every rank computes only the rows it owns */
+static int update_slab(ifl_solver* s, double timestep) {
+    int rc;
+    CU(cudaEventRecord(s->ev[0], s->stream));
+    if ((rc = slab_exchange_halo(s, s->v, 0, 1))) return rc;        /* buildRhs of my last row reads v of the row below */
+    stage_build_rhs(s);
+    stage_build_matrix(s, timestep);
+    launch_build_precon(s->sx);
+    if ((rc = stage_project(s, timestep))) return rc;
+    COMM(pcg_exchange_pressure_halo(s->sx));                        /* applyPressure of my first row reads p of the row above */
+    stage_apply_pressure(s, timestep);
+    CU(cudaEventRecord(s->ev[1], s->stream));
+    int halo = 0;
+    if ((rc = slab_advection_halo(s, timestep, &halo))) return rc;
+    for (Quantity* q : {&s->d, &s->u, &s->v})
+        if ((rc = slab_exchange_halo(s, *q, halo, halo + 1))) return rc;
+    stage_advect(s, s->d, timestep);
+    stage_advect(s, s->u, timestep);
+    stage_advect(s, s->v, timestep);
+    s->d.swap(); s->u.swap(); s->v.swap();
+    CU(cudaEventRecord(s->ev[2], s->stream));
+    s->ev_valid = true;
+    CU(cudaGetLastError());
+    return IFL_OK;
+}
+
 static int update_impl(ifl_solver* s, double timestep) {
     if (is_flip(s)) return update_flip(s, timestep);
     if (has_solids(s)) return update_solid(s, timestep);
+    if (s->cfg.world_size > 1) return update_slab(s, timestep);
     /* FluidSolver.update  F1:276 / F2:322 / F3:361 */
     CU(cudaEventRecord(s->ev[0], s->stream));
     stage_build_rhs(s);
@@ -820,23 +924,26 @@ int ifl_max_timestep(ifl_solver* s, double* out) {
 
 /* field lookup: device pointer, element count and storage kind */
 enum { KIND_ROWS = 0, KIND_SKEW = 1, KIND_U8 = 2, KIND_I32 = 3 };
-static int field_ptr(ifl_solver* s, int32_t field, void** ptr, size_t* count, int* kind) {
+static int field_ptr(ifl_solver* s, int32_t field, void** ptr, size_t* count, int* kind, size_t* width = nullptr) {
     *kind = KIND_ROWS;
     size_t n = (size_t)s->w * s->h;
+    size_t wdummy;
+    if (!width) width = &wdummy;
+    *width = (size_t)s->w;                        /* row length; u-shaped fields and phi set their own */
     auto bad = [&]() {
         snprintf(g_err, sizeof g_err, "field %d does not exist for variant %d", field, s->cfg.variant);
         return IFL_ERR_INVALID;
     };
     switch (field) {
         case IFL_FIELD_D: *ptr = s->d.src(); *count = s->d.count(); return IFL_OK;
-        case IFL_FIELD_U: *ptr = s->u.src(); *count = s->u.count(); return IFL_OK;
+        case IFL_FIELD_U: *ptr = s->u.src(); *count = s->u.count(); *width = (size_t)s->w + 1; return IFL_OK;
         case IFL_FIELD_V: *ptr = s->v.src(); *count = s->v.count(); return IFL_OK;
         case IFL_FIELD_D_DST: *ptr = s->d.dst(); *count = s->d.count(); return IFL_OK;
-        case IFL_FIELD_U_DST: *ptr = s->u.dst(); *count = s->u.count(); return IFL_OK;
+        case IFL_FIELD_U_DST: *ptr = s->u.dst(); *count = s->u.count(); *width = (size_t)s->w + 1; return IFL_OK;
         case IFL_FIELD_V_DST: *ptr = s->v.dst(); *count = s->v.count(); return IFL_OK;
         case IFL_FIELD_T: if (!has_heat(s)) return bad(); *ptr = s->t.src(); *count = s->t.count(); return IFL_OK;
         case IFL_FIELD_T_DST: if (!has_heat(s)) return bad(); *ptr = s->t.dst(); *count = s->t.count(); return IFL_OK;
-        case IFL_FIELD_UDENSITY: if (!has_vardens(s)) return bad(); *ptr = s->udens; *count = s->u.count(); return IFL_OK;
+        case IFL_FIELD_UDENSITY: if (!has_vardens(s)) return bad(); *ptr = s->udens; *count = s->u.count(); *width = (size_t)s->w + 1; return IFL_OK;
         case IFL_FIELD_VDENSITY: if (!has_vardens(s)) return bad(); *ptr = s->vdens; *count = s->v.count(); return IFL_OK;
         case IFL_FIELD_P: *ptr = s->sx.p; break;
         case IFL_FIELD_R: *ptr = s->sx.r; break;
@@ -856,6 +963,7 @@ static int field_ptr(ifl_solver* s, int32_t field, void** ptr, size_t* count, in
             Quantity* q = qi == 0 ? &s->d : qi == 1 ? &s->t : qi == 2 ? &s->u : &s->v;
             if (!q->present) return bad();
             *count = q->count();
+            *width = (size_t)q->q.w;
             switch (grp) {
                 case 0: if (s->cfg.variant < IFL_F5_CURVED_BOUNDARIES) return bad(); *ptr = q->sq.volume; return IFL_OK;
                 case 1: *ptr = q->sq.normalX; return IFL_OK;
@@ -863,7 +971,7 @@ static int field_ptr(ifl_solver* s, int32_t field, void** ptr, size_t* count, in
                 case 3: *ptr = q->sq.cell; *kind = KIND_U8; return IFL_OK;
                 case 4: *ptr = q->sq.body; *kind = KIND_I32; return IFL_OK;
                 case 5: if (s->cfg.variant < IFL_F5_CURVED_BOUNDARIES) return bad();
-                        *ptr = q->sq.phi; *count = (size_t)(q->q.w + 1) * (q->q.h + 1); return IFL_OK;
+                        *ptr = q->sq.phi; *count = (size_t)(q->q.w + 1) * (q->q.h + 1); *width = (size_t)q->q.w + 1; return IFL_OK;
             }
             return bad();
         }
@@ -879,42 +987,78 @@ int ifl_field_size(const ifl_solver* s, int32_t field, size_t* count) {
     return field_ptr(const_cast<ifl_solver*>(s), field, &p, count, &kind);
 }
 
-int ifl_read_field(ifl_solver* s, int32_t field, double* host, size_t count) {
+/* rows [row0, row0 + nrows) of a field; nrows < 0: the whole field */
+static int field_io(ifl_solver* s, int32_t field, double* host, size_t count, long long row0, long long nrows, bool write) {
     if (!s || !host) INVALID("NULL argument");
     CU(cudaSetDevice(s->cfg.device));
-    void* p; size_t n; int kind;
-    int rc = field_ptr(s, field, &p, &n, &kind);
+    void* p; size_t n, width; int kind;
+    int rc = field_ptr(s, field, &p, &n, &kind, &width);
     if (rc) return rc;
-    if (n != count) INVALID("count does not match ifl_field_size");
-    const double* srcp = (const double*)p;
-    if (kind == KIND_SKEW) { launch_skew_to_rows(s->stream, s->sx.g, (const double*)p, s->scratch); srcp = s->scratch; s->launches++; }
-    else if (kind == KIND_U8) { launch_u8_to_double(s->stream, (const unsigned char*)p, s->scratch, n); srcp = s->scratch; s->launches++; }
-    else if (kind == KIND_I32) { launch_i32_to_double(s->stream, (const int*)p, s->scratch, n); srcp = s->scratch; s->launches++; }
-    CU(cudaMemcpyAsync(host, srcp, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
+    const bool whole = nrows < 0;
+    if (whole && s->cfg.world_size > 1) {
+        snprintf(g_err, sizeof g_err, "slab decomposition: a rank holds only its rows of field %d -- use ifl_%s_field_rows", field,
+                 write ? "write" : "read");
+        return IFL_ERR_UNSUPPORTED;
+    }
+    const size_t total_rows = n / width;
+    if (whole) { row0 = 0; nrows = (long long)total_rows; }
+    if (row0 < 0 || nrows < 0 || (size_t)(row0 + nrows) > total_rows) INVALID("row range outside the field");
+    if ((size_t)nrows * width != count) INVALID(whole ? "count does not match ifl_field_size" : "count does not match nrows * row length");
+    if (kind == KIND_SKEW && s->cfg.world_size > 1) {
+        const long long o0 = 32LL * s->sx.g.s0, o1 = 32LL * s->sx.g.s1 < s->h ? 32LL * s->sx.g.s1 : (long long)s->h;
+        if (row0 < o0 || row0 + nrows > o1) INVALID("slab decomposition: a solver vector holds only the rows this rank owns (ifl_slab_rows)");
+    }
+    if (write) {
+        if (kind == KIND_U8 || kind == KIND_I32) {
+            snprintf(g_err, sizeof g_err, "field %d (cell/body) is derived by fillSolidFields and is read-only", field);
+            return IFL_ERR_UNSUPPORTED;
+        }
+        if (field == IFL_FIELD_ADIAG || field == IFL_FIELD_APLUSX || field == IFL_FIELD_APLUSY) s->sx.const_matrix = 0;
+        if (kind == KIND_SKEW) {
+            CU(cudaMemcpyAsync(s->scratch, host, sizeof(double) * count, cudaMemcpyHostToDevice, s->stream));
+            launch_rows_to_skew(s->stream, s->sx.g, s->scratch, (double*)p, (int)row0, (int)(row0 + nrows));
+            s->launches++;
+        } else {
+            CU(cudaMemcpyAsync((double*)p + (size_t)row0 * width, host, sizeof(double) * count, cudaMemcpyHostToDevice, s->stream));
+        }
+        CU(cudaStreamSynchronize(s->stream));
+        return IFL_OK;
+    }
+    const double* srcp = (const double*)p + (size_t)row0 * width;
+    if (kind == KIND_SKEW) {
+        launch_skew_to_rows(s->stream, s->sx.g, (const double*)p, s->scratch, (int)row0, (int)(row0 + nrows));
+        srcp = s->scratch; s->launches++;
+    } else if (kind == KIND_U8) {
+        launch_u8_to_double(s->stream, (const unsigned char*)p, s->scratch, n); srcp = s->scratch + (size_t)row0 * width; s->launches++;
+    } else if (kind == KIND_I32) {
+        launch_i32_to_double(s->stream, (const int*)p, s->scratch, n); srcp = s->scratch + (size_t)row0 * width; s->launches++;
+    }
+    CU(cudaMemcpyAsync(host, srcp, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return IFL_OK;
 }
-
+int ifl_read_field(ifl_solver* s, int32_t field, double* host, size_t count) { return field_io(s, field, host, count, 0, -1, false); }
 int ifl_write_field(ifl_solver* s, int32_t field, const double* host, size_t count) {
-    if (!s || !host) INVALID("NULL argument");
-    CU(cudaSetDevice(s->cfg.device));
-    void* p; size_t n; int kind;
-    int rc = field_ptr(s, field, &p, &n, &kind);
+    return field_io(s, field, const_cast<double*>(host), count, 0, -1, true);
+}
+int ifl_read_field_rows(ifl_solver* s, int32_t field, int32_t row0, int32_t nrows, double* host, size_t count) {
+    if (nrows < 0) INVALID("nrows < 0");
+    return field_io(s, field, host, count, row0, nrows, false);
+}
+int ifl_write_field_rows(ifl_solver* s, int32_t field, int32_t row0, int32_t nrows, const double* host, size_t count) {
+    if (nrows < 0) INVALID("nrows < 0");
+    return field_io(s, field, const_cast<double*>(host), count, row0, nrows, true);
+}
+int ifl_slab_rows(const ifl_solver* s, int32_t field, int32_t* row0, int32_t* nrows) {
+    if (!s || !row0 || !nrows) INVALID("NULL argument");
+    void* p; size_t n, width; int kind;
+    int rc = field_ptr(const_cast<ifl_solver*>(s), field, &p, &n, &kind, &width);
     if (rc) return rc;
-    if (n != count) INVALID("count does not match ifl_field_size");
-    if (kind == KIND_U8 || kind == KIND_I32) {
-        snprintf(g_err, sizeof g_err, "field %d (cell/body) is derived by fillSolidFields and is read-only", field);
-        return IFL_ERR_UNSUPPORTED;
-    }
-    if (field == IFL_FIELD_ADIAG || field == IFL_FIELD_APLUSX || field == IFL_FIELD_APLUSY) s->sx.const_matrix = 0;
-    if (kind == KIND_SKEW) {
-        CU(cudaMemcpyAsync(s->scratch, host, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-        launch_rows_to_skew(s->stream, s->sx.g, s->scratch, (double*)p);
-        s->launches++;
-    } else {
-        CU(cudaMemcpyAsync(p, host, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
-    }
-    CU(cudaStreamSynchronize(s->stream));
+    int s0, s1;
+    slab_range(s->sx.g.nstrips, s->cfg.world_size, s->cfg.rank, &s0, &s1);
+    int r0 = 32 * s0 < s->h ? 32 * s0 : s->h, r1 = 32 * s1 < s->h ? 32 * s1 : s->h;
+    if (r1 == s->h) r1 = (int)(n / width);           /* v and phi have one row more: it belongs to the last rank */
+    *row0 = r0; *nrows = r1 - r0;
     return IFL_OK;
 }
 

@@ -140,3 +140,21 @@ int comm_exchange_rows(Comm& c, const double* send_up, double* recv_up, const do
 }
 
 } // namespace ifl
+
+namespace ifl {
+int comm_transfers(Comm& c, const CommXfer* x, int n) {
+    if (n <= 0) return 0;
+    NC(g_nccl.GroupStart());
+    for (int i = 0; i < n; i++) {
+        if (x[i].count == 0) continue;
+        if (x[i].send) NC(g_nccl.Send(x[i].ptr, x[i].count, ncclFloat64, x[i].peer, (ncclComm_t)c.nccl, c.stream));
+        else           NC(g_nccl.Recv(x[i].ptr, x[i].count, ncclFloat64, x[i].peer, (ncclComm_t)c.nccl, c.stream));
+    }
+    NC(g_nccl.GroupEnd());
+    return 0;
+}
+int comm_all_gather_u64(Comm& c, unsigned long long* vals) {
+    NC(g_nccl.AllGather(vals + c.rank, vals, 1, ncclUint64, (ncclComm_t)c.nccl, c.stream));
+    return 0;
+}
+} // namespace ifl

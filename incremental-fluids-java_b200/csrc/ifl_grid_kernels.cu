@@ -67,11 +67,11 @@ __device__ __forceinline__ double cerp_grid(const FieldView& f, double x, double
  * (RungeKutta3 F2:253 / F3:255 + cerpGrid).  One thread per destination sample. */
 template <bool RK3>
 __global__ void __launch_bounds__(256)
-k_advect(FieldView q, FieldView u, FieldView v, double* __restrict__ dst, double timestep, double hx) {
+k_advect(FieldView q, FieldView u, FieldView v, double* __restrict__ dst, double timestep, double hx, int row0, int row1) {
     const HxDiv hd = make_hxdiv(hx);
     int ix = blockIdx.x * blockDim.x + threadIdx.x;
-    int iy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (ix >= q.w || iy >= q.h) return;
+    int iy = row0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (ix >= q.w || iy >= row1) return;
     double x = ix + q.ox;
     double y = iy + q.oy;
     double out;
@@ -100,15 +100,17 @@ k_advect(FieldView q, FieldView u, FieldView v, double* __restrict__ dst, double
     dst[(size_t)iy * q.w + ix] = out;
 }
 
+/* rows [row0, row1) of the destination (the whole field on a single GPU, the rows a rank owns in a slab decomposition) */
 void launch_advect(cudaStream_t st, int variant, QGeom q, const double* src, double* dst,
-                   QGeom qu, const double* u, QGeom qv, const double* v, double timestep, double hx) {
+                   QGeom qu, const double* u, QGeom qv, const double* v, double timestep, double hx, int row0, int row1) {
+    if (row1 <= row0) return;
     dim3 block(32, 8);
-    dim3 grid((q.w + 31) / 32, (q.h + 7) / 8);
+    dim3 grid((q.w + 31) / 32, (row1 - row0 + 7) / 8);
     FieldView fq = make_view(src, q), fu = make_view(u, qu), fv = make_view(v, qv);
     if (variant == IFL_F1_MATRIXLESS)
-        k_advect<false><<<grid, block, 0, st>>>(fq, fu, fv, dst, timestep, hx);
+        k_advect<false><<<grid, block, 0, st>>>(fq, fu, fv, dst, timestep, hx, row0, row1);
     else
-        k_advect<true><<<grid, block, 0, st>>>(fq, fu, fv, dst, timestep, hx);
+        k_advect<true><<<grid, block, 0, st>>>(fq, fu, fv, dst, timestep, hx, row0, row1);
 }
 
 /* FluidQuantity.addInflow: F1:202 (hard rectangle) / F2:230 (=F3:232 ...) smooth pulse.
@@ -160,20 +162,26 @@ void launch_add_inflow(cudaStream_t st, int variant, QGeom q, double* src, doubl
  * Kernels that touch both layouts run one thread per cell (x, y) in row-major order and address the
  * skewed side through skew_index(); they run once per step, so their strided skewed accesses are noise. */
 struct SkewPos { int x, y; long long i; bool ok; };
-__device__ __forceinline__ SkewPos skew_pos(const SkewGeom& g) {
+__device__ __forceinline__ SkewPos skew_pos(const SkewGeom& g, int row0 = 0, int row1 = 0x7fffffff) {
     SkewPos s;
     s.x = blockIdx.x * blockDim.x + threadIdx.x;
-    s.y = blockIdx.y * blockDim.y + threadIdx.y;
-    s.ok = s.x < g.w && s.y < g.h;
+    s.y = row0 + blockIdx.y * blockDim.y + threadIdx.y;
+    s.ok = s.x < g.w && s.y < g.h && s.y < row1;
     s.i = s.ok ? skew_index(g, s.x, s.y) : 0;
     return s;
 }
 static dim3 skew_grid(const SkewGeom& g) { return dim3((g.w + 31) / 32, (g.h + 7) / 8); }
+static dim3 rows_grid(const SkewGeom& g, int row0, int row1) { return dim3((g.w + 31) / 32, (row1 - row0 + 7) / 8); }
+/* the rows of the strips [s0, s1) a rank owns */
+static inline void own_rows(const SkewGeom& g, int* row0, int* row1) {
+    *row0 = g.s0 * 32;
+    *row1 = g.s1 * 32 < g.h ? g.s1 * 32 : g.h;
+}
 
 /* FluidSolver.buildRhs  F1:364 (=F2:379, F3:420) */
 __global__ void k_build_rhs(SkewGeom g, const double* __restrict__ u, const double* __restrict__ v,
-                            double* __restrict__ r, double scale) {
-    SkewPos s = skew_pos(g);
+                            double* __restrict__ r, double scale, int row0, int row1) {
+    SkewPos s = skew_pos(g, row0, row1);
     if (!s.ok) return;
     int x = s.x, y = s.y, w = g.w;
     double u1 = u[(size_t)(x + 1) + (size_t)y * (w + 1)], u0 = u[(size_t)x + (size_t)y * (w + 1)];
@@ -181,7 +189,9 @@ __global__ void k_build_rhs(SkewGeom g, const double* __restrict__ u, const doub
     r[s.i] = -scale * (u1 - u0 + v1 - v0);
 }
 void launch_build_rhs(cudaStream_t st, const SkewGeom& g, const double* u, const double* v, double* r, double hx) {
-    k_build_rhs<<<skew_grid(g), dim3(32, 8), 0, st>>>(g, u, v, r, 1.0 / hx);
+    int row0, row1;
+    own_rows(g, &row0, &row1);          /* the whole grid on a single GPU */
+    k_build_rhs<<<rows_grid(g, row0, row1), dim3(32, 8), 0, st>>>(g, u, v, r, 1.0 / hx, row0, row1);
 }
 
 /* FluidSolver.buildPressureMatrix F3:435 in gather form.  The reference scatters in
@@ -207,11 +217,11 @@ void launch_build_matrix_f3(cudaStream_t st, const SkewGeom& g, double* adiag, d
  * reference first adds scale*p of the cell before it, then subtracts scale*p of its own
  * cell; afterwards the four domain edges are zeroed (F1:444-451). */
 __global__ void k_apply_pressure(SkewGeom g, const double* __restrict__ p, double* __restrict__ u,
-                                 double* __restrict__ v, double scale) {
+                                 double* __restrict__ v, double scale, int row0, int row1) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int y = row0 + blockIdx.y * blockDim.y + threadIdx.y;
     int w = g.w, h = g.h;
-    if (x > w || y > h) return;
+    if (x > w || y >= row1) return;
     double pc = 0.0, pl = 0.0, pu = 0.0;
     if (x < w && y < h) pc = p[skew_index(g, x, y)];
     if (y < h) {  /* u face (x, y), x in [0, w] */
@@ -235,27 +245,37 @@ __global__ void k_apply_pressure(SkewGeom g, const double* __restrict__ p, doubl
         v[iv] = val;
     }
 }
+/* faces of the rows a rank owns: u rows [row0, row1), v rows [row0, row1), and v row h on the rank that owns row h-1
+ * (needs p of row row0-1: the last row of the previous rank, see pcg_exchange_pressure_halo) */
 void launch_apply_pressure(cudaStream_t st, const SkewGeom& g, const double* p, double* u, double* v, double scale) {
+    int row0, row1;
+    own_rows(g, &row0, &row1);
+    if (row1 == g.h) row1 = g.h + 1;
     dim3 block(32, 8);
-    dim3 grid((g.w + 1 + 31) / 32, (g.h + 1 + 7) / 8);
-    k_apply_pressure<<<grid, block, 0, st>>>(g, p, u, v, scale);
+    dim3 grid((g.w + 1 + 31) / 32, (row1 - row0 + 7) / 8);
+    k_apply_pressure<<<grid, block, 0, st>>>(g, p, u, v, scale, row0, row1);
 }
 
-__global__ void k_skew_to_rows(SkewGeom g, const double* __restrict__ skew, double* __restrict__ rows) {
-    SkewPos s = skew_pos(g);
+/* rows [row0, row1) of a skewed vector <-> a row-major buffer whose first row is row0 */
+__global__ void k_skew_to_rows(SkewGeom g, const double* __restrict__ skew, double* __restrict__ rows, int row0, int row1) {
+    SkewPos s = skew_pos(g, row0, row1);
     if (!s.ok) return;
-    rows[(size_t)s.x + (size_t)s.y * g.w] = skew[s.i];
+    rows[(size_t)s.x + (size_t)(s.y - row0) * g.w] = skew[s.i];
 }
-__global__ void k_rows_to_skew(SkewGeom g, const double* __restrict__ rows, double* __restrict__ skew) {
-    SkewPos s = skew_pos(g);
+__global__ void k_rows_to_skew(SkewGeom g, const double* __restrict__ rows, double* __restrict__ skew, int row0, int row1) {
+    SkewPos s = skew_pos(g, row0, row1);
     if (!s.ok) return;
-    skew[s.i] = rows[(size_t)s.x + (size_t)s.y * g.w];
+    skew[s.i] = rows[(size_t)s.x + (size_t)(s.y - row0) * g.w];
 }
-void launch_skew_to_rows(cudaStream_t st, const SkewGeom& g, const double* skew, double* rows) {
-    k_skew_to_rows<<<skew_grid(g), dim3(32, 8), 0, st>>>(g, skew, rows);
+void launch_skew_to_rows(cudaStream_t st, const SkewGeom& g, const double* skew, double* rows, int row0, int row1) {
+    if (row1 < 0) { row0 = 0; row1 = g.h; }
+    if (row1 <= row0) return;
+    k_skew_to_rows<<<rows_grid(g, row0, row1), dim3(32, 8), 0, st>>>(g, skew, rows, row0, row1);
 }
-void launch_rows_to_skew(cudaStream_t st, const SkewGeom& g, const double* rows, double* skew) {
-    k_rows_to_skew<<<skew_grid(g), dim3(32, 8), 0, st>>>(g, rows, skew);
+void launch_rows_to_skew(cudaStream_t st, const SkewGeom& g, const double* rows, double* skew, int row0, int row1) {
+    if (row1 < 0) { row0 = 0; row1 = g.h; }
+    if (row1 <= row0) return;
+    k_rows_to_skew<<<rows_grid(g, row0, row1), dim3(32, 8), 0, st>>>(g, rows, skew, row0, row1);
 }
 
 /* FluidSolver.maxTimestep F1:309: max over cells of |(u,v)| sampled at cell centres.
@@ -277,6 +297,26 @@ __global__ void k_max_velocity(FieldView u, FieldView v, int w, int h, unsigned 
     }
     if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0) atomicMax(out_bits, bits);
 }
+/* slab decomposition: max |v| over the v faces of rows [row0, row1) -- the CFL number that sizes the advection halo
+ * (cf. maxTimestep F1:309-333; only the vertical component moves a backtrace across slab boundaries) */
+__global__ void k_max_abs_rows(const double* __restrict__ v, int w, int row0, int row1, unsigned long long* out_bits) {
+    const long long n = (long long)(row1 - row0) * w;
+    const double* p = v + (long long)row0 * w;
+    double m = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmax(m, fabs(p[i]));
+    unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_down_sync(0xffffffffu, bits, o);
+        bits = other > bits ? other : bits;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, bits);
+}
+void launch_max_abs_rows(cudaStream_t st, const double* v, int w, int row0, int row1, unsigned long long* out_bits) {
+    if (row1 <= row0) return;
+    k_max_abs_rows<<<592, 256, 0, st>>>(v, w, row0, row1, out_bits);
+}
+
 /* FluidSolver.toImage: the integers of one frame (see include/incfluid_b200.h).  One thread per cell; with render_heat
  * the frame is 2w wide, heat panel at x, density panel at x + w (idxl / idxr of F6:1263-1264). */
 __global__ void k_to_image(int variant, int w, int h, const double* __restrict__ d, const double* __restrict__ t,

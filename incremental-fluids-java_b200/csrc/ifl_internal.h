@@ -81,6 +81,10 @@ static inline void slab_range(int nstrips, int world, int rank, int* s0, int* s1
     *s1 = *s0 + base + (rank < rem ? 1 : 0);
 }
 int comm_exchange_rows(Comm& c, const double* send_up, double* recv_up, const double* send_down, double* recv_down, size_t n);
+/* one grouped set of point-to-point transfers (halo rows of the row-major fields) */
+struct CommXfer { int peer; double* ptr; size_t count; int send; };
+int comm_transfers(Comm& c, const CommXfer* x, int n);
+int comm_all_gather_u64(Comm& c, unsigned long long* vals /* [world], own value at [rank] */);
 
 /* event-sampled kernel timing (ifl_set_profiling / ifl_kernel_timing) */
 struct Profiler {
@@ -98,6 +102,7 @@ struct SolveCtx {
     SkewGeom g;
     /* skewed N-vectors */
     double *r, *p, *adiag, *aplusx, *aplusy, *precon;
+    double* p_first;         /* first owned strip of p */
     double *zb[2], *sb[2];   /* z and s, two generations each (k_step_a reads one and writes the other; SolveScalars.zpar) */
     unsigned* strip_ctr;     /* per-strip "last block" counters of the two-level reductions, [strips_alloc] */
     /* per-solve packed operands of the triangular sweeps (products aPlusX*precon, aPlusY*precon, precon) */
@@ -131,14 +136,16 @@ struct SolveCtx {
 
 /* ---- grid (row-major) kernels: ifl_grid_kernels.cu ---- */
 void launch_advect(cudaStream_t st, int variant, QGeom q, const double* src, double* dst,
-                   QGeom qu, const double* u, QGeom qv, const double* v, double timestep, double hx);
+                   QGeom qu, const double* u, QGeom qv, const double* v, double timestep, double hx, int row0, int row1);
+void launch_max_abs_rows(cudaStream_t st, const double* v, int w, int row0, int row1, unsigned long long* out_bits);
 void launch_add_inflow(cudaStream_t st, int variant, QGeom q, double* src, double hx,
                        double x0, double y0, double x1, double y1, double value);
 void launch_build_rhs(cudaStream_t st, const SkewGeom& g, const double* u, const double* v, double* r, double hx);
 void launch_build_matrix_f3(cudaStream_t st, const SkewGeom& g, double* adiag, double* aplusx, double* aplusy, double scale);
 void launch_apply_pressure(cudaStream_t st, const SkewGeom& g, const double* p, double* u, double* v, double scale);
-void launch_skew_to_rows(cudaStream_t st, const SkewGeom& g, const double* skew, double* rows);
-void launch_rows_to_skew(cudaStream_t st, const SkewGeom& g, const double* rows, double* skew);
+/* row1 < 0: every row; otherwise rows [row0, row1) <-> a row-major buffer that starts at row0 */
+void launch_skew_to_rows(cudaStream_t st, const SkewGeom& g, const double* skew, double* rows, int row0 = 0, int row1 = -1);
+void launch_rows_to_skew(cudaStream_t st, const SkewGeom& g, const double* rows, double* skew, int row0 = 0, int row1 = -1);
 void launch_max_velocity(cudaStream_t st, int w, int h, const double* u, const double* v, unsigned long long* out_bits);
 void launch_to_image(cudaStream_t st, int variant, int w, int h, const double* d, const double* t, const double* volume,
                      const unsigned char* cell, double t_ambient, int render_heat, int* rgb);
@@ -211,7 +218,7 @@ int  launch_apply_precon(SolveCtx& c, int as_in_loop = 0);     /* z = M^-1 r on 
 int  pcg_enqueue_init(SolveCtx& c);
 int  pcg_enqueue_iterations(SolveCtx& c, int n);
 int  pcg_enqueue_finish(SolveCtx& c, int limit);
-int  pcg_gather_pressure(SolveCtx& c);
+int  pcg_exchange_pressure_halo(SolveCtx& c);   /* the last row of p of rank-1 -> the row above my slab */
 int  launch_matvec(SolveCtx& c);           /* z = A s on the current generation */
 void gs_enqueue_begin(SolveCtx& c);
 void gs_enqueue_iterations(SolveCtx& c, int first_iter, int n, double scale);

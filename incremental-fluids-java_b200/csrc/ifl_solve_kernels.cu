@@ -37,7 +37,6 @@ static constexpr int SKB = IFL_SKB;    /* cells per lane per wavefront macro-ste
 static dim3 ew_grid(const SkewGeom& g) { return dim3((g.tl + EW_TROWS - 1) / EW_TROWS, g.s1 - g.s0); }
 int solve_partials_needed(const SkewGeom& g) { return (int)(((g.tl + EW_TROWS - 1) / EW_TROWS) * g.nstrips); }
 static inline void count(SolveCtx& c, int n = 1) { if (c.launches) *c.launches += n; }
-static inline SkewGeom full_geom(const SkewGeom& g) { SkewGeom f = g; f.s0 = 0; f.s1 = g.nstrips; return f; }
 static inline int single_gpu(const SolveCtx& c) { return c.comm == nullptr; }
 
 /* iteration helper of the element-wise kernels: a thread handles 8 elements; the 256 threads of a block cover
@@ -1806,8 +1805,9 @@ int launch_build_precon(SolveCtx& c) {
     k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
     k_build_precon<<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.precon,
                                                                   c.bnd_f, c.sc, c.mic_tau, c.mic_sigma, c.fl);
-    { SkewGeom fg = full_geom(c.g);   /* built redundantly for the whole grid on every rank */
-      k_precon_coeffs<<<ew_grid(fg), EW_THREADS, 0, c.stream>>>(fg, c.aplusx, c.aplusy, c.precon, c.pack_f, c.pack_b, c.fl); }
+    /* the MIC(0) factor is built for the whole grid on every rank (a recurrence from strip 0); the packed products only
+     * for the strips this rank sweeps */
+    k_precon_coeffs<<<ew_grid(c.g), EW_THREADS, 0, c.stream>>>(c.g, c.aplusx, c.aplusy, c.precon, c.pack_f, c.pack_b, c.fl);
     count(c, 3);
     return 0;
 }
@@ -1956,7 +1956,7 @@ static int dist_halo_rows(SolveCtx& c) {
 
 /* project() F3:590-602: p = 0; z = M^-1 r; s = z; maxError; sigma = z.r */
 int pcg_enqueue_init(SolveCtx& c) {
-    cudaMemsetAsync(c.p, 0, sizeof(double) * (size_t)c.g.total, c.stream);
+    cudaMemsetAsync(c.p_first, 0, sizeof(double) * (size_t)(c.g.s1 - c.g.s0) * (size_t)c.g.ss, c.stream);
     k_solve_reset<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
     count(c);
     /* every rank's inboxes must be re-armed before any neighbour starts writing into them */
@@ -2024,12 +2024,33 @@ int pcg_enqueue_finish(SolveCtx& c, int limit) {
     count(c, 2);
     return 0;
 }
-/* slab decomposition, hosts that keep whole fields on every rank: every rank's slab of p to every rank */
-int pcg_gather_pressure(SolveCtx& c) {
-    if (single_gpu(c)) return 0;
-    return comm_all_gather_strips(*c.comm, c.p, c.g.nstrips, (size_t)c.g.ss);
+/* slab decomposition: applyPressure of the first row of a slab reads p of the row above it (F3:640-643 in gather form);
+ * every rank sends the last row of its p to the next rank */
+__global__ void k_pack_last_row(SkewGeom g, const double* __restrict__ vec, double* __restrict__ rowbuf) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= g.w) return;
+    int ylast = g.s1 * 32 - 1;
+    if (ylast > g.h - 1) ylast = g.h - 1;
+    rowbuf[x] = vec[skew_index(g, x, ylast)];
 }
-
+__global__ void k_unpack_row_above(SkewGeom g, double* __restrict__ vec, const double* __restrict__ rowbuf) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= g.w) return;
+    vec[skew_index(g, x, g.s0 * 32 - 1)] = rowbuf[x];
+}
+int pcg_exchange_pressure_halo(SolveCtx& c) {
+    if (single_gpu(c)) return 0;
+    const int w = c.g.w, rank = c.comm->rank, world = c.comm->world;
+    k_pack_last_row<<<(w + 255) / 256, 256, 0, c.stream>>>(c.g, c.p, c.rowbuf);
+    CommXfer x[2];
+    int n = 0;
+    if (rank < world - 1) x[n++] = CommXfer{rank + 1, c.rowbuf, (size_t)w, 1};
+    if (rank > 0) x[n++] = CommXfer{rank - 1, c.rowbuf + w, (size_t)w, 0};
+    IFL_TRY(comm_transfers(*c.comm, x, n));
+    if (rank > 0) k_unpack_row_above<<<(w + 255) / 256, 256, 0, c.stream>>>(c.g, c.p, c.rowbuf + w);
+    count(c, 2);
+    return 0;
+}
 /* Gauss-Seidel project() F1:380: _p is warm-started, so only the control state is reset */
 void gs_enqueue_begin(SolveCtx& c) {
     k_solve_reset<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);

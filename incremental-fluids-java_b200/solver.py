@@ -220,6 +220,24 @@ class FluidSolver:
         arr = np.ascontiguousarray(values, dtype=np.float64).ravel()
         check(self._fn["ifl_write_field"](self._h_, _abi.FIELDS[name], arr.ctypes.data_as(_dp), arr.size))
 
+    def slab_rows(self, name):
+        """(row0, nrows) of field `name` this rank owns in a slab decomposition (everything on a single GPU)."""
+        r0, nr = C.c_int32(), C.c_int32()
+        check(self._fn["ifl_slab_rows"](self._h_, _abi.FIELDS[name], C.byref(r0), C.byref(nr)))
+        return r0.value, nr.value
+
+    def read_field_rows(self, name, row0, nrows, out=None):
+        width = self.field_size(name) // (self._h + (1 if name.startswith(("v", "phi")) else 0))
+        if out is None:
+            out = np.empty(nrows * width, dtype=np.float64)
+        assert out.dtype == np.float64 and out.size == nrows * width and out.flags.c_contiguous
+        check(self._fn["ifl_read_field_rows"](self._h_, _abi.FIELDS[name], row0, nrows, out.ctypes.data_as(_dp), out.size))
+        return out
+
+    def write_field_rows(self, name, row0, nrows, values):
+        arr = np.ascontiguousarray(values, dtype=np.float64).ravel()
+        check(self._fn["ifl_write_field_rows"](self._h_, _abi.FIELDS[name], row0, nrows, arr.ctypes.data_as(_dp), arr.size))
+
     # snake_case aliases (used by the parity tests)
     read = read_field
     write = write_field

@@ -1,4 +1,6 @@
 cd /root/repo
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-for f in 0 4; do timeout 200 python tools/tune_pcg.py - 16384 40 $f 2>&1 | tail -1; done | tee gpurun_out/r2_tune10.log
-timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -4
+mkdir -p gpurun_out
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+timeout 300 $T --master-port 29512 tools/slab_check.py 1000 1100 2 40 2>&1 | grep -v "^W\|^\*\*\*\|^$\|OMP_NUM" | tail -6 | tee gpurun_out/r2_slab_n2.log
+timeout 600 $T --master-port 29513 tools/slab_check.py 8192 4096 2 30 2>&1 | grep -v "^W\|^\*\*\*\|^$\|OMP_NUM" | tail -6 | tee -a gpurun_out/r2_slab_n2.log
+timeout 900 $T --master-port 29514 bench.py --gpus 2 --steps 2 --warmup 3 2> gpurun_out/r2_b_n2.err > gpurun_out/r2_b_n2.json; head -c 300 gpurun_out/r2_b_n2.json; echo; tail -3 gpurun_out/r2_b_n2.err
