@@ -74,6 +74,8 @@ struct ifl_solver {
     unsigned char* extrap_state = nullptr;
     unsigned int* d_progress = nullptr;
     unsigned int* h_progress = nullptr;
+    unsigned int* d_extrap_ctl = nullptr;          /* [4]: three rotating progress counters + the finished flag (k_extrap_sweep) */
+    unsigned int* h_extrap_flag = nullptr;         /* pinned, [2] */
     SolveScalars* sc_heat = nullptr;                /* device copy of the heat solve's final scalars */
     SolveScalars* h_sc_heat = nullptr;
     /* F8 */
@@ -163,7 +165,8 @@ void ifl_destroy(ifl_solver* s) {
         void* ptrs[] = {q->sq.phi, q->sq.volume, q->sq.normalX, q->sq.normalY, q->sq.cell, q->sq.body, q->sq.mask};
         for (void* p : ptrs) if (p) cudaFree(p);
     }
-    void* extra[] = {s->d_bodies, s->udens, s->vdens, s->extrap_state, s->d_progress, s->sc_heat,
+    if (s->h_extrap_flag) cudaFreeHost(s->h_extrap_flag);
+    void* extra[] = {s->d_bodies, s->udens, s->vdens, s->extrap_state, s->d_progress, s->d_extrap_ctl, s->sc_heat,
                      s->sx.fl ? (void*)(s->sx.fl - s->sx.g.ss) : nullptr};
     for (void* p : extra) if (p) cudaFree(p);
     if (s->h_progress) cudaFreeHost(s->h_progress);
@@ -218,6 +221,8 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     if (has_solids(s)) {
         CU(cudaMalloc(&s->extrap_state, (size_t)(s->w + 1) * (s->h + 1)));
         CU(cudaMalloc(&s->d_progress, sizeof(unsigned int)));
+        CU(cudaMalloc(&s->d_extrap_ctl, 4 * sizeof(unsigned int)));
+        CU(cudaMallocHost(&s->h_extrap_flag, 2 * sizeof(unsigned int)));
         CU(cudaMallocHost(&s->h_progress, sizeof(unsigned int)));
         CU(cudaMalloc(&s->sc_heat, sizeof(SolveScalars))); CU(cudaMemset(s->sc_heat, 0, sizeof(SolveScalars)));
         CU(cudaMallocHost(&s->h_sc_heat, sizeof(SolveScalars))); memset(s->h_sc_heat, 0, sizeof(SolveScalars));
@@ -414,7 +419,7 @@ static int run_solver_loop(ifl_solver* s, double timestep) {
     while (enq < limit && !done) {
         int n = limit - enq < chunk ? limit - enq : chunk;
         if (pcg) COMM(pcg_enqueue_iterations(c, n));
-        else gs_enqueue_iterations(c, enq, n, gs_scale);
+        else n = gs_enqueue_iterations(c, enq, n, gs_scale, limit);
         enq += n;
         int slot = nchunks & 1;
         CU(cudaMemcpyAsync(&s->h_sc[slot], c.sc, sizeof(SolveScalars), cudaMemcpyDeviceToHost, s->stream));
@@ -432,7 +437,8 @@ static int run_solver_loop(ifl_solver* s, double timestep) {
 
 static int fetch_status(ifl_solver* s, ifl_step_status* st) {
     CU(cudaMemcpyAsync(&s->h_sc[0], s->sx.sc, sizeof(SolveScalars), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    if (has_heat(s)) CU(cudaMemcpyAsync(s->h_sc_heat, s->sc_heat, sizeof(SolveScalars), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));                       /* the one host wait of a step, and only when asked for */
     const SolveScalars& h = s->h_sc[0];
     if (is_flip(s)) s->last.particle_count = s->flip.count;
     s->last.iterations_pressure = h.iterations;
@@ -440,7 +446,6 @@ static int fetch_status(ifl_solver* s, ifl_step_status* st) {
     s->last.exceeded_budget = h.exceeded ? 1 : 0;
     s->last.nan_residual = h.nan;
     if (has_heat(s)) {
-        CU(cudaMemcpy(s->h_sc_heat, s->sc_heat, sizeof(SolveScalars), cudaMemcpyDeviceToHost));
         const SolveScalars& hh = *s->h_sc_heat;
         s->last.iterations_heat = hh.iterations;
         s->last.residual_heat = hh.max_error;
@@ -570,19 +575,29 @@ static int stage_apply_pressure_solid(ifl_solver* s, double timestep) {
     s->launches++;
     return IFL_OK;
 }
-/* FluidQuantity.extrapolate F4:452: sweeps until no pending solid cell can be filled any more */
+/* FluidQuantity.extrapolate F4:452: sweeps until no pending solid cell can be filled any more.  The sweeps are enqueued
+ * in chunks; a sweep that finds the previous one idle raises a device flag and every later one returns at once, so the
+ * host only polls the flag of the chunk before last (two chunks in flight, the device never waits for the host). */
 static int stage_extrapolate(ifl_solver* s, Quantity& q) {
     launch_extrap_fill_mask(s->stream, q.sq, s->extrap_state);
+    CU(cudaMemsetAsync(s->d_extrap_ctl, 0, 4 * sizeof(unsigned int), s->stream));
     s->launches++;
-    const int batch = 4;
-    const int max_batches = (q.q.w + q.q.h) / batch + 2;
-    for (int b = 0; b < max_batches; b++) {
-        CU(cudaMemsetAsync(s->d_progress, 0, sizeof(unsigned int), s->stream));
-        for (int i = 0; i < batch; i++) launch_extrap_sweep(s->stream, q.sq, q.src(), s->extrap_state, s->d_progress);
-        s->launches += batch;
-        CU(cudaMemcpyAsync(s->h_progress, s->d_progress, sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-        if (*s->h_progress == 0) break;
+    const int chunk = 16;
+    const int max_sweeps = q.q.w + q.q.h + 2;
+    int k = 0, nchunks = 0;
+    bool done = false;
+    while (k < max_sweeps && !done) {
+        for (int i = 0; i < chunk; i++, k++) launch_extrap_sweep(s->stream, q.sq, q.src(), s->extrap_state, s->d_extrap_ctl, k);
+        s->launches += chunk;
+        const int slot = nchunks & 1;
+        CU(cudaMemcpyAsync(&s->h_extrap_flag[slot], s->d_extrap_ctl + 3, sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaEventRecord(s->ev_chunk[slot], s->stream));
+        nchunks++;
+        if (nchunks >= 2) {
+            const int older = (nchunks - 2) & 1;
+            CU(cudaEventSynchronize(s->ev_chunk[older]));
+            if (s->h_extrap_flag[older]) done = true;
+        }
     }
     return IFL_OK;
 }

@@ -38,16 +38,22 @@ __device__ __forceinline__ double lerp(double a, double b, double x) { return (1
 
 /* Catmull-Rom weights of math/Interpolation.java:145-149.  The four polynomials do not
  * depend on the samples, so they are evaluated once per coordinate and reused for every
- * row; each is the literal expression of the reference, term by term, left to right. */
+ * row.  Each is the reference's expression, term by term and left to right, with the
+ * operations that cannot change a bit folded away; x is the fractional part of a clamped
+ * coordinate, i.e. finite and in [0, 1) (a NaN still propagates through every weight):
+ *   1.0*xsq == xsq;   0.0*x == +0.0 and t + (+0.0) == t for the t >= +0.0 it is added to;
+ *   0.0 - 0.5*x + xsq  == xsq - 0.5*x   ((-h) + q and q - h are the same IEEE operation; for x == 0 both give +0.0);
+ *   0.0 + 0.5*x        == 0.5*x         (0.5*x is +0.0 or positive);
+ *   (0.0 + 0.0*x) - 0.5*xsq + 0.5*xcu == 0.5*xcu - 0.5*xsq   (again (-h) + q == q - h; zeros come out +0.0 either way). */
 struct CerpW { double a, b, c, d; };
 __device__ __forceinline__ CerpW cerp_weights(double x) {
     double xsq = x * x;
     double xcu = xsq * x;
     CerpW w;
-    w.a = 0.0 - 0.5 * x + 1.0 * xsq - 0.5 * xcu;
-    w.b = 1.0 + 0.0 * x - 2.5 * xsq + 1.5 * xcu;
-    w.c = 0.0 + 0.5 * x + 2.0 * xsq - 1.5 * xcu;
-    w.d = 0.0 + 0.0 * x - 0.5 * xsq + 0.5 * xcu;
+    w.a = (xsq - 0.5 * x) - 0.5 * xcu;              /* 0.0 - 0.5*x + 1.0*xsq - 0.5*xcu */
+    w.b = (1.0 - 2.5 * xsq) + 1.5 * xcu;            /* 1.0 + 0.0*x - 2.5*xsq + 1.5*xcu */
+    w.c = (0.5 * x + 2.0 * xsq) - 1.5 * xcu;        /* 0.0 + 0.5*x + 2.0*xsq - 1.5*xcu */
+    w.d = 0.5 * xcu - 0.5 * xsq;                    /* 0.0 + 0.0*x - 0.5*xsq + 0.5*xcu */
     return w;
 }
 /* math/Interpolation.java:135-152 */

@@ -167,7 +167,7 @@ void launch_apply_pressure_solid(cudaStream_t st, const SkewGeom& g, const unsig
 void launch_add_buoyancy(cudaStream_t st, int w, int h, const double* dsrc, const double* tsrc, double* v,
                          double timestep, double gravity, double rho_air, double rho_soot, double t_amb);
 void launch_extrap_fill_mask(cudaStream_t st, const SolidQ& q, unsigned char* state);
-void launch_extrap_sweep(cudaStream_t st, const SolidQ& q, double* src, unsigned char* state, unsigned int* progress);
+void launch_extrap_sweep(cudaStream_t st, const SolidQ& q, double* src, unsigned char* state, unsigned int* ctl /* [4] */, int k);
 void launch_advect_solid(cudaStream_t st, QGeom q, const double* src, double* dst, QGeom qu, const double* u, QGeom qv,
                          const double* v, const unsigned char* cell, const int* body, const ifl_body* bodies,
                          double timestep, double hx);
@@ -221,7 +221,7 @@ int  pcg_enqueue_finish(SolveCtx& c, int limit);
 int  pcg_exchange_pressure_halo(SolveCtx& c);   /* the last row of p of rank-1 -> the row above my slab */
 int  launch_matvec(SolveCtx& c);           /* z = A s on the current generation */
 void gs_enqueue_begin(SolveCtx& c);
-void gs_enqueue_iterations(SolveCtx& c, int first_iter, int n, double scale);
+int  gs_enqueue_iterations(SolveCtx& c, int first_iter, int n, double scale, int limit);   /* iterations enqueued */
 void gs_enqueue_finish(SolveCtx& c, int limit);
 
 } // namespace ifl

@@ -409,7 +409,18 @@ __global__ void k_extrap_fill_mask(SolidQ q, unsigned char* __restrict__ state) 
     }
     state[idx] = stt;
 }
-__global__ void k_extrap_sweep(SolidQ q, double* src, unsigned char* state, unsigned int* progress) {
+/* Sweep number k of one extrapolate(): fills every pending solid cell whose upstream cells are ready.  Progress is
+ * counted on the device in three rotating slots (sweep k adds to slot k%3, reads slot (k-1)%3 and clears slot (k+1)%3):
+ * once a sweep has filled nothing, ctl[3] is raised and this and every later sweep of the call returns at once, so the
+ * host can enqueue sweeps blindly (ifl_api.cu polls ctl[3] two chunks behind, like the PCG loop). */
+__global__ void k_extrap_sweep(SolidQ q, double* src, unsigned char* state, unsigned int* ctl, int k) {
+    if (ctl[3]) return;
+    if (k > 0 && ctl[(k + 2) % 3] == 0) {                      /* the previous sweep made no progress: finished */
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) ctl[3] = 1;
+        return;
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) ctl[(k + 1) % 3] = 0;
+    unsigned int* progress = ctl + (k % 3);
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     bool did = false;
@@ -437,9 +448,9 @@ void launch_extrap_fill_mask(cudaStream_t st, const SolidQ& q, unsigned char* st
     dim3 block(32, 8), grid((q.w + 31) / 32, (q.h + 7) / 8);
     k_extrap_fill_mask<<<grid, block, 0, st>>>(q, state);
 }
-void launch_extrap_sweep(cudaStream_t st, const SolidQ& q, double* src, unsigned char* state, unsigned int* progress) {
+void launch_extrap_sweep(cudaStream_t st, const SolidQ& q, double* src, unsigned char* state, unsigned int* progress, int k) {
     dim3 block(32, 8), grid((q.w + 31) / 32, (q.h + 7) / 8);
-    k_extrap_sweep<<<grid, block, 0, st>>>(q, src, state, progress);
+    k_extrap_sweep<<<grid, block, 0, st>>>(q, src, state, progress, k);
 }
 
 /* ---- masked advection F4:268 (=F5:402, F6:417, F7:423) with backProject F4:249 --------------- */

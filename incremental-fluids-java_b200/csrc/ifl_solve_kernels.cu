@@ -1754,6 +1754,122 @@ k_gs_sweep(SkewGeom g, const double* __restrict__ r, double* p, double* bnd_use,
     }
 }
 
+/* project() F1:380 (=F2:395) for grids whose pressure fits in shared memory (config 1: 128x128): ALL Gauss-Seidel
+ * iterations of a solve in ONE launch of ONE block.  p lives in shared memory for the whole solve; warp k owns the strip of
+ * rows 32k..32k+31 (lane l = row l) and walks the anti-diagonals x = m - l with a one-cell skew, so that the cell to the
+ * left is its own previous result, the cell above the previous result of lane l-1 (one shuffle) and the cells to the right
+ * and below still hold the values of the previous iteration -- exactly the operands of the reference's in-place
+ * lexicographic loop, hence the same bits.  Strip k+1 trails strip k by 32 cells (a progress counter in shared memory),
+ * which is what makes the row above its first row new and the row below the last row of strip k old.  After every sweep
+ * the block reduces maxDelta (F1:414, a max: order independent) and decides like F1:420.
+ * A sweep costs (w + 31 + 32*(strips-1)) dependent cell steps -- about 20 us at 128x128 instead of one 100-180 us kernel
+ * launch per sweep. */
+__global__ void __launch_bounds__(1024)
+k_gs_resident(SkewGeom g, const double* __restrict__ r, double* __restrict__ p, SolveScalars* sc, double scale, double tol, int limit) {
+    extern __shared__ double sp[];                      /* p, row-major [h][w] */
+    __shared__ volatile int s_prog[32];                 /* columns a strip has finished in the current sweep */
+    __shared__ unsigned long long s_max[32];
+    __shared__ int s_done;
+    const int w = g.w, h = g.h;
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5, nst = blockDim.x >> 5;
+    const int y = k * 32 + lane;
+    const bool yok = y < h;
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) sp[i] = p[skew_index(g, i % w, i / w)];
+    if (threadIdx.x < 32) s_prog[threadIdx.x] = 0;
+    __syncthreads();
+    /* r of my row in the skewed layout: (x, y) sits at strip*ss + (((x >> 1) + l) * 32 + l) * 2 + (x & 1) */
+    static_assert(IFL_SKB == 2, "index arithmetic of the skewed layout");
+    const double* const rrow = r + (long long)k * g.ss + (long long)(lane * 32 + lane) * 2;
+    auto r_at = [&](int x) { return rrow[((x >> 1) << 6) + (x & 1)]; };
+    volatile double* const vsp = sp;                    /* rows other warps write are read through volatile accesses */
+    int iterations = 0;
+    double max_error = 0.0;
+    bool done = false;
+    const int nsteps = w + 31;
+    constexpr int PF = 4;                               /* r is fetched PF steps ahead (it stays in L1 / L2) */
+    const int yc = yok ? y : h - 1;                     /* rows below the grid compute on a copy of the last row; nothing is stored */
+    const bool has_up = yc > 0, has_dn = yc < h - 1;
+    for (int it = 0; it < limit && !done; it++) {
+        double pl = 0.0, pnew = 0.0;
+        unsigned long long mbits = 0ull;
+        double rq[PF];
+#pragma unroll
+        for (int i = 0; i < PF; i++) { const int xq = i - lane; rq[i] = (yok && xq >= 0 && xq < w) ? r_at(xq) : 0.0; }
+        int seen = 0;                                   /* columns of the strip above known to be finished */
+        for (int m0 = 0; m0 < nsteps; m0 += PF) {
+#pragma unroll
+            for (int i = 0; i < PF; i++) {
+                const int m = m0 + i;
+                const int x = m - lane;
+                const bool act = yok && x >= 0 && x < w && m < nsteps;
+                /* the row above my strip must be finished up to column m (lane 0 needs p(x = m, 32k - 1) of this sweep) */
+                if (k > 0 && seen <= m && m < w) { do { seen = s_prog[k - 1]; } while (seen <= m); }
+                double pu = __shfl_up_sync(0xffffffffu, pnew, 1);
+                const double rv = rq[i];
+                { const int xq = m + PF - lane; rq[i] = (yok && xq >= 0 && xq < w) ? r_at(xq) : 0.0; }
+                /* branch-free: out-of-grid lanes work on a clamped cell and store nothing; a term the reference skips
+                 * (x > 0 ... F1:399-410) enters as +0.0, which changes neither diag (>= +0.0) nor offDiag (never -0.0) */
+                const int xc = x < 0 ? 0 : (x > w - 1 ? w - 1 : x);
+                const int idx = yc * w + xc;
+                const double pup = lane == 0 ? (has_up ? vsp[idx - (has_up ? w : 0)] : 0.0) : pu;
+                const double pold = sp[idx];
+                const double prt = sp[idx + (xc < w - 1 ? 1 : 0)];
+                const double pdn = lane == 31 ? vsp[idx + (has_dn ? w : 0)] : sp[idx + (has_dn ? w : 0)];
+                const bool cl = xc > 0, cu = has_up, cr = xc < w - 1, cd = has_dn;
+                double diag = 0.0, offDiag = 0.0;
+                diag += cl ? scale : 0.0; offDiag -= cl ? scale * pl : 0.0;
+                diag += cu ? scale : 0.0; offDiag -= cu ? scale * pup : 0.0;
+                diag += cr ? scale : 0.0; offDiag -= cr ? scale * prt : 0.0;
+                diag += cd ? scale : 0.0; offDiag -= cd ? scale * pdn : 0.0;
+                const double newP = (rv - offDiag) / diag;
+                /* F1:414: old p rounded through float, difference taken in double */
+                const double delta = fabs(jfloat(pold) - newP);
+                const unsigned long long db = (unsigned long long)__double_as_longlong(delta);
+                if (act) {
+                    mbits = db > mbits ? db : mbits;
+                    sp[idx] = newP;
+                    pl = newP; pnew = newP;
+                }
+                __syncwarp();
+                /* lane 31 has finished the columns up to m - 31: the strip below may use them (and their old values are no
+                 * longer needed here).  Published every 8 steps: one fence per 8 cells instead of per cell. */
+                if (lane == 31 && m >= 31 && m < nsteps && ((m - 31) & 7) == 7) { __threadfence_block(); s_prog[k] = m - 30; }
+            }
+        }
+        if (lane == 31) { __threadfence_block(); s_prog[k] = w; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_down_sync(0xffffffffu, mbits, o);
+            mbits = other > mbits ? other : mbits;
+        }
+        if (lane == 0) s_max[k] = mbits;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long mb = 0ull;
+            for (int i = 0; i < nst; i++) mb = s_max[i] > mb ? s_max[i] : mb;
+            const double md = __longlong_as_double((long long)mb);
+            s_done = md < tol ? 1 : 0;
+            *(double*)&s_max[0] = md;
+        }
+        if (threadIdx.x < 32) s_prog[threadIdx.x] = 0;
+        __syncthreads();
+        iterations++;
+        max_error = *(double*)&s_max[0];
+        done = s_done != 0;
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) p[skew_index(g, i % w, i / w)] = sp[i];
+    if (threadIdx.x == 0) {
+        sc->iterations = iterations;
+        sc->max_error = max_error;
+        sc->done = done ? 1 : 0;
+    }
+}
+/* does the resident Gauss-Seidel kernel apply?  (p in shared memory, one warp per strip) */
+static inline bool gs_fits_resident(const SkewGeom& g) {
+    return (size_t)g.w * g.h * sizeof(double) <= 200 * 1024 && g.nstrips <= 32;
+}
+
 /* slab decomposition: boundary rows of the current z and s <-> packed rows.
  * rowbuf = [z first row | s first row | z last row | s last row | from above: z, s | from below: z, s], w doubles each */
 __global__ void k_pack_rows(SkewGeom g, const double* z0, const double* z1, const double* s0, const double* s1,
@@ -2056,7 +2172,24 @@ void gs_enqueue_begin(SolveCtx& c) {
     k_solve_reset<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
     count(c);
 }
-void gs_enqueue_iterations(SolveCtx& c, int first_iter, int n, double scale) {
+/* returns the number of iterations it has enqueued: `n`, or everything up to `limit` at once when the whole solve runs
+ * in the resident kernel */
+int gs_enqueue_iterations(SolveCtx& c, int first_iter, int n, double scale, int limit) {
+    if (gs_fits_resident(c.g) && first_iter == 0) {
+        const size_t smem = (size_t)c.g.w * c.g.h * sizeof(double);
+        static unsigned long long attr_devices = 0ull;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 64 || !((attr_devices >> dev) & 1ull)) {
+            cudaFuncSetAttribute(k_gs_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (dev < 64) __atomic_fetch_or(&attr_devices, 1ull << dev, __ATOMIC_RELAXED);
+        }
+        const int ps = prof_begin(c, 1);
+        k_gs_resident<<<1, 32 * c.g.nstrips, smem, c.stream>>>(c.g, c.r, c.p, c.sc, scale, c.tolerance, limit);
+        count(c);
+        prof_mark(c, ps, 1);
+        return limit;
+    }
     for (int it = first_iter; it < first_iter + n; it++) {
         double* use = (it & 1) ? c.bnd_b : c.bnd_f;
         double* rearm = (it & 1) ? c.bnd_f : c.bnd_b;
@@ -2065,6 +2198,7 @@ void gs_enqueue_iterations(SolveCtx& c, int first_iter, int n, double scale) {
         count(c);
         prof_mark(c, ps, 1);
     }
+    return n;
 }
 void gs_enqueue_finish(SolveCtx& c, int limit) {
     k_solve_finish<<<1, 1, 0, c.stream>>>(c.sc, limit);

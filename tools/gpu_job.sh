@@ -1,6 +1,5 @@
 cd /root/repo
-mkdir -p gpurun_out
-T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-timeout 300 $T --master-port 29512 tools/slab_check.py 1000 1100 2 40 2>&1 | grep -v "^W\|^\*\*\*\|^$\|OMP_NUM" | tail -6 | tee gpurun_out/r2_slab_n2.log
-timeout 600 $T --master-port 29513 tools/slab_check.py 8192 4096 2 30 2>&1 | grep -v "^W\|^\*\*\*\|^$\|OMP_NUM" | tail -6 | tee -a gpurun_out/r2_slab_n2.log
-timeout 900 $T --master-port 29514 bench.py --gpus 2 --steps 2 --warmup 3 2> gpurun_out/r2_b_n2.err > gpurun_out/r2_b_n2.json; head -c 300 gpurun_out/r2_b_n2.json; echo; tail -3 gpurun_out/r2_b_n2.err
+timeout 300 python -m pytest tests/test_parity_gpu.py tests/test_golden.py -q -m gpu -x -k "gauss or f1 or F1 or golden or F2" 2>&1 | tail -2
+timeout 300 python bench.py --workload c1 --steps 40 --warmup 5 --no-cpu-baseline --no-hash --no-e2e 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('c1 value %.3e ms/step %.2f kernel_ms %s its %s' % (d['value'], d['ms_per_step'], d['kernel_ms'], d['config']['solver_iterations_per_step'][:5]))"
