@@ -1,0 +1,54 @@
+/* ExplicitFluid3conjugateGradients of the reference (physics/EulerianFluids/ExplicitFluid3conjugateGradients.java) with FluidSolver delegating to the CUDA library:
+ * same package, class, nested-class and method names and signatures (constructor F3:339, update F3:361, addInflow F3:385,
+ * toImage F3:397), the same driver loop (F3:59-92).  All arithmetic of the reference's FluidSolver /
+ * FluidQuantity runs on the device behind include/incfluid_b200.h (variant IFL_F3_CONJUGATE_GRADIENTS).
+ * Source only: this repository's image has no JDK (INTEGRATION.md). */
+package physics.EulerianFluids;
+
+import java.io.File;
+import java.io.IOException;
+import physics.b200.IncFluidB200;
+
+class ExplicitFluid3conjugateGradients {
+
+    public static void main(String args[]) {
+        final int sizeX = 128, sizeY = 128;
+        final double density = 0.1;
+        final double timestep = 0.005;
+        final FluidSolver solver = new FluidSolver(sizeX, sizeY, density);
+        double time = 0.0;
+        for (int frame = 1; time < 8.0; frame++) {
+            for (int i = 0; i < 4; i++, time += timestep) {
+                solver.addInflow(0.45, 0.2, 0.15, 0.03, 1.0, 0.0, 3.0);
+                solver.update(timestep);
+            }
+            try {
+                solver.toImage(new File("Frame" + frame + ".ppm"));
+            } catch (IOException ex) {
+                ex.printStackTrace();
+            }
+        }
+    }
+
+    static class FluidSolver {
+        private final IncFluidB200 gpu;
+        private final int _w, _h;
+
+        FluidSolver(int w, int h, double density) {
+            _w = w; _h = h;
+            gpu = new IncFluidB200(IncFluidB200.F3_CONJUGATE_GRADIENTS, w, h, density);
+        }
+
+        private void update(double timestep) {
+            gpu.update(timestep);
+        }
+
+        private void addInflow(double x, double y, double w, double h, double d, double u, double v) {
+            gpu.addInflow(x, y, w, h, d, 0.0, u, v);
+        }
+
+        private void toImage(File destination) throws IOException {
+            gpu.toImage(destination, false);
+        }
+    }
+}

@@ -67,14 +67,3 @@ def test_product_never_loads_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in text.lower(), os.path.join(dirpath, f)
-
-
-def test_java_binding_file_matches_integration_listing():
-    """java/physics/b200/IncFluidB200.java is the listing of INTEGRATION.md section 2 (neither can be compiled here: no
-    JDK), and every C symbol it binds is declared in the header."""
-    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
-    listing = re.search(r"```java\n(package physics\.b200;.*?)```", text, re.S).group(1)
-    src = open(os.path.join(ROOT, "java", "physics", "b200", "IncFluidB200.java")).read()
-    assert src.endswith(listing)
-    bound = set(re.findall(r'fn\("(ifl_[a-z_0-9]+)"', src))
-    assert len(bound) >= 10 and bound <= set(declared_symbols()), bound - set(declared_symbols())
