@@ -198,6 +198,20 @@ class FluidSolver:
         check(self._fn["ifl_run_steps"](self._h_, n, timestep, *rect, st), allow=(_abi.ERR_NAN,))
         return self.status.as_dict() if want_status else None
 
+    def run_adaptive(self, t_end, rect, dt_max, cfl_fraction=1.0, max_steps=1000000):
+        """Adaptive-timestep driver on top of maxTimestep() (F1:309-333, which the reference defines and never calls):
+        until `t_end`, every step takes dt = min(dt_max, cfl_fraction * maxTimestep(), time left), then addInflow(*rect)
+        and update(dt) like the body of main().  Returns the list of timesteps taken.  On a slab decomposition the same
+        CFL reduction sizes the advection halo inside update()."""
+        t, taken = 0.0, []
+        while t < t_end and len(taken) < max_steps:
+            dt = min(dt_max, cfl_fraction * self.maxTimestep(), t_end - t)
+            self.addInflow(*rect)
+            self.update(dt, want_status=False)
+            taken.append(dt)
+            t += dt
+        return taken
+
     def run_stage(self, stage, timestep=0.0, want_status=False):
         st = C.byref(self.status) if want_status else None
         check(self._fn["ifl_run_stage"](self._h_, _abi.STAGES[stage], timestep, st), allow=(_abi.ERR_NAN,))
