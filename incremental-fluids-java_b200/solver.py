@@ -200,13 +200,14 @@ class FluidSolver:
 
     def run_adaptive(self, t_end, rect, dt_max, cfl_fraction=1.0, max_steps=1000000):
         """Adaptive-timestep driver on top of maxTimestep() (F1:309-333, which the reference defines and never calls):
-        until `t_end`, every step takes dt = min(dt_max, cfl_fraction * maxTimestep(), time left), then addInflow(*rect)
-        and update(dt) like the body of main().  Returns the list of timesteps taken.  On a slab decomposition the same
+        until `t_end`, every step does addInflow(*rect), takes dt = min(dt_max, cfl_fraction * maxTimestep(), time left)
+        from the state it is about to advance, and update(dt) -- the body of main() with a CFL-limited timestep.
+        Returns the list of timesteps taken.  On a slab decomposition the same
         CFL reduction sizes the advection halo inside update()."""
         t, taken = 0.0, []
         while t < t_end and len(taken) < max_steps:
-            dt = min(dt_max, cfl_fraction * self.maxTimestep(), t_end - t)
             self.addInflow(*rect)
+            dt = min(dt_max, cfl_fraction * self.maxTimestep(), t_end - t)
             self.update(dt, want_status=False)
             taken.append(dt)
             t += dt

@@ -215,15 +215,15 @@ def test_pcg_iteration_limit_keeps_the_last_p_update(ifl, oracle_cls, limit):
 
 
 def test_adaptive_timestep_driver_follows_max_timestep(ifl, oracle_cls):
-    """run_adaptive: dt = min(dt_max, maxTimestep()) every step (F1:309-333).  The oracle, driven by the same rule with its
+    """run_adaptive: addInflow, then dt = min(dt_max, maxTimestep()) every step (F1:309-333).  The oracle, driven by the same rule with its
     own maxTimestep, must take the same timesteps and reach the same state bit for bit (F1: no sums anywhere)."""
     g, o = pair(ifl, oracle_cls, ifl.abi.F1_MATRIXLESS, 96, 64)
     rect = scenes.F1_INFLOW[:5] + scenes.F1_INFLOW[6:]
     taken = g.run_adaptive(0.1, rect, 0.02)
     t, mine = 0.0, []
     while t < 0.1:
-        dt = min(0.02, o.max_timestep(), 0.1 - t)
         o.add_inflow(*scenes.F1_INFLOW)
+        dt = min(0.02, o.max_timestep(), 0.1 - t)
         o.update(dt)
         mine.append(dt); t += dt
     assert taken == mine and len(taken) >= 5

@@ -1,5 +1,4 @@
 cd /root/repo
-timeout 300 python -m pytest tests/test_parity_gpu.py tests/test_golden.py -q -m gpu -x -k "gauss or f1 or F1 or golden or F2" 2>&1 | tail -2
-timeout 300 python bench.py --workload c1 --steps 40 --warmup 5 --no-cpu-baseline --no-hash --no-e2e 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('c1 value %.3e ms/step %.2f kernel_ms %s its %s' % (d['value'], d['ms_per_step'], d['kernel_ms'], d['config']['solver_iterations_per_step'][:5]))"
+timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -4
+timeout 600 python bench.py --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline > gpurun_out/r2_b_n1_s2.json 2>gpurun_out/r2_b_n1_s2.err; python -c "
+import json; d=json.loads(open('gpurun_out/r2_b_n1_s2.json').read()); print(d['value'], d['ms_per_step'], d['config']['state_hash'], d['e2e']['value'], d['roofline']['traffic'])"
