@@ -177,6 +177,7 @@ void ifl_destroy(ifl_solver* s) {
     if (s->pack_alloc) cudaFree(s->pack_alloc);
     comm_destroy(s->comm);
     if (s->sx.bnd_f) cudaFree(s->sx.bnd_f);
+    if (s->sx.inbox_f) cudaFree(s->sx.inbox_f);
     if (s->sx.strip_part) cudaFree(s->sx.strip_part);
     if (s->sx.strip_ctr) cudaFree(s->sx.strip_ctr);
     if (s->sx.rank_max) cudaFree(s->sx.rank_max);
@@ -268,6 +269,11 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     size_t nb = (size_t)strips_alloc * g.w;
     CU(cudaMalloc(&s->sx.bnd_f, sizeof(double) * nb * 2));
     s->sx.bnd_b = s->sx.bnd_f + nb;
+    /* both inbox-row sets of the sweeps in ONE allocation: the neighbour ranks map it through CUDA IPC */
+    s->sx.inbox_len = 2 * (g.tl + 64);
+    const size_t nin = (size_t)strips_alloc * s->sx.inbox_len;
+    CU(cudaMalloc(&s->sx.inbox_f, sizeof(double) * nin * 2));
+    s->sx.inbox_b = s->sx.inbox_f + nin;
     s->sx.strips_alloc = strips_alloc;
     CU(cudaMalloc(&s->sx.strip_part, sizeof(double) * strips_alloc));
     CU(cudaMemset(s->sx.strip_part, 0, sizeof(double) * strips_alloc));
@@ -276,19 +282,19 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     CU(cudaMalloc(&s->sx.rank_max, sizeof(unsigned long long) * (world > 16 ? world : 16) * 8));
     CU(cudaMemset(s->sx.rank_max, 0, sizeof(unsigned long long) * (world > 16 ? world : 16) * 8));
     CU(cudaMalloc(&s->sx.rowbuf, sizeof(double) * 8 * g.w));
-    s->sx.comm = nullptr; s->sx.peer_bnd_f_next = nullptr; s->sx.peer_bnd_b_prev = nullptr;
+    s->sx.comm = nullptr; s->sx.peer_inbox_f_next = nullptr; s->sx.peer_inbox_b_prev = nullptr;
     if (world > 1) {
         if (comm_init(s->comm, cfg->rank, world, cfg->comm_id, s->stream)) {
             snprintf(g_err, sizeof g_err, "%s", comm_last_error());
             return IFL_ERR_COMM;
         }
-        if (comm_map_neighbour_inboxes(s->comm, s->sx.bnd_f, s->sx.rank_max)) {
+        if (comm_map_neighbour_inboxes(s->comm, s->sx.inbox_f, s->sx.rank_max)) {
             snprintf(g_err, sizeof g_err, "%s", comm_last_error());
             return IFL_ERR_COMM;
         }
         s->sx.comm = &s->comm;
-        if (s->comm.peer_next_base) s->sx.peer_bnd_f_next = (double*)s->comm.peer_next_base;
-        if (s->comm.peer_prev_base) s->sx.peer_bnd_b_prev = (double*)s->comm.peer_prev_base + nb;
+        if (s->comm.peer_next_base) s->sx.peer_inbox_f_next = (double*)s->comm.peer_next_base;
+        if (s->comm.peer_prev_base) s->sx.peer_inbox_b_prev = (double*)s->comm.peer_prev_base + nin;
         CU(cudaMemset(s->sx.rank_max, 0, sizeof(unsigned long long) * (world > 16 ? world : 16) * 8));
     }
     s->sx.npartials = solve_partials_needed(g);

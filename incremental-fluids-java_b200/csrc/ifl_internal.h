@@ -63,7 +63,7 @@ struct Comm {
     int rank = 0, world = 1;
     void* nccl = nullptr;             /* ncclComm_t */
     cudaStream_t stream = nullptr;
-    void* peer_prev_base = nullptr;   /* IPC mapping of rank-1's / rank+1's inbox allocation (bnd_f | bnd_b) */
+    void* peer_prev_base = nullptr;   /* IPC mapping of rank-1's / rank+1's inbox allocation (inbox_f | inbox_b) */
     void* peer_next_base = nullptr;
 };
 const char* comm_last_error();
@@ -107,8 +107,11 @@ struct SolveCtx {
     unsigned* strip_ctr;     /* per-strip "last block" counters of the two-level reductions, [strips_alloc] */
     /* per-solve packed operands of the triangular sweeps (products aPlusX*precon, aPlusY*precon, precon) */
     double *pack_f, *pack_b;   /* [strip][tl/16][3][16][32], see k_precon_coeffs */
-    /* strip boundary rows (flag-in-data), [nstrips][w] each; two sets for GS parity */
+    /* strip boundary rows (flag-in-data) of the MIC(0) build and Gauss-Seidel wavefronts, [nstrips][w] each; two sets for GS parity */
     double *bnd_f, *bnd_b;
+    /* global inbox rows of the triangular sweeps (strip hand-over between clusters / GPUs), [nstrips][inbox_len] each */
+    double *inbox_f, *inbox_b;
+    int inbox_len;
     double *partials;     /* per-block partial sums */
     int npartials;
     SolveScalars* sc;
@@ -125,8 +128,8 @@ struct SolveCtx {
     Profiler* prof;
     /* slab decomposition */
     Comm* comm;              /* nullptr on a single GPU */
-    double* peer_bnd_f_next; /* rank+1's forward inbox (its bnd_f), IPC mapped */
-    double* peer_bnd_b_prev; /* rank-1's backward inbox (its bnd_b) */
+    double* peer_inbox_f_next; /* rank+1's forward inbox rows (its inbox_f), IPC mapped */
+    double* peer_inbox_b_prev; /* rank-1's backward inbox rows (its inbox_b) */
     double* rowbuf;          /* 8 packed rows of w doubles: z,s of my first / last row, z,s received from above / below */
     double* strip_part;      /* per-strip partial sums, [strips_alloc] */
     unsigned long long* rank_max;   /* per-rank max bits, [world] */

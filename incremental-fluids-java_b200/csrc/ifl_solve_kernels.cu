@@ -209,15 +209,13 @@ k_matvec(SkewGeom g, const double* __restrict__ adiag, const double* __restrict_
  * Masked scaledAdd (F6:1041) leaves s unchanged outside the fluid -- copied here; the mat-vec is never masked.
  * In the first iteration (iterations == 0) s already is the copy of z made by k_init_s (F3:596): s is carried over
  * unchanged and nothing is added to p.
- * Also re-arms the strip boundary rows and tickets of the two sweeps that follow.
  * Moves 48 B/cell for F3 (R z,s,p  W s,p,z), against 16 + 40 for separate mat-vec and update kernels. */
 template <bool CONSTM>
 __global__ void __launch_bounds__(EW_THREADS)
 k_step_a(SkewGeom g, const double* __restrict__ adiag, const double* __restrict__ ax, const double* __restrict__ ay,
          double* z0, double* z1, double* s0, double* s1, double* __restrict__ p,
          double* partials, double* strip_part, unsigned* strip_ctr, SolveScalars* sc, int dot_mode,
-         const unsigned char* __restrict__ fl, int single_gpu, double cscale,
-         double* __restrict__ bnd_f, double* __restrict__ bnd_b) {
+         const unsigned char* __restrict__ fl, int single_gpu, double cscale) {
     static_assert(SKB == 2 && EW_THREADS == 256, "a thread owns the two cells of one lane and m-row");
     constexpr int TR = EW_TROWS;                    /* m-rows per block */
     constexpr int RS = 32 * SKB;                    /* doubles per m-row */
@@ -286,19 +284,6 @@ k_step_a(SkewGeom g, const double* __restrict__ adiag, const double* __restrict_
             } else {
 #pragma unroll
                 for (int j = 0; j < SKB; j++) if (ok[j]) { sout[i + j] = sn[j]; if (!first) p[i + j] = pv[j]; }
-            }
-            if (lane == 0) {                                /* lane 0 works on column block t: re-arm the boundary rows */
-#pragma unroll
-                for (int j = 0; j < SKB; j++) {
-                    const int xb = t * SKB + j;
-                    if (xb < w) {
-                        bnd_f[(long long)k * w + xb] = sentinel();
-                        bnd_b[(long long)k * w + xb] = sentinel();
-                        /* slab decomposition: the rows my neighbours write into (their edge strips) are re-armed by me */
-                        if (k == g.s0 && g.s0 > 0) bnd_f[(long long)(g.s0 - 1) * w + xb] = sentinel();
-                        if (k == g.s1 - 1 && g.s1 < g.nstrips) bnd_b[(long long)g.s1 * w + xb] = sentinel();
-                    }
-                }
             }
         }
         sown[ps][0] = sn[0]; sown[ps][1] = sn[1];
@@ -519,13 +504,17 @@ k_init_s(SkewGeom g, double* s0, double* s1, const double* z0, const double* z1,
     }
 }
 
-/* (re)arm scalars, tickets and both boundary-row sets before a solve */
-__global__ void k_solve_reset(SkewGeom g, double* bnd_f, double* bnd_b, SolveScalars* sc) {
-    long long n = (long long)g.nstrips * g.w;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        bnd_f[i] = sentinel();
-        bnd_b[i] = sentinel();
-    }
+/* (re)arm scalars, tickets, the boundary rows of the MIC(0) build / Gauss-Seidel wavefronts ([nstrips][w]) and the
+ * global inbox rows of the triangular sweeps ([nstrips][inbox_len]) before a solve.  (Inside a solve the sweeps re-arm
+ * what they consume.) */
+__device__ __forceinline__ void arm_rows(SkewGeom g, double* bnd_f, double* bnd_b, double* inbox_f, double* inbox_b, int inbox_len) {
+    const long long n = (long long)g.nstrips * g.w, ni = (long long)g.nstrips * inbox_len;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) { bnd_f[i] = sentinel(); bnd_b[i] = sentinel(); }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ni; i += stride) { inbox_f[i] = sentinel(); inbox_b[i] = sentinel(); }
+}
+__global__ void k_solve_reset(SkewGeom g, double* bnd_f, double* bnd_b, double* inbox_f, double* inbox_b, int inbox_len, SolveScalars* sc) {
+    arm_rows(g, bnd_f, bnd_b, inbox_f, inbox_b, inbox_len);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         sc->sigma = 0.0; sc->alpha = 0.0; sc->neg_alpha = 0.0; sc->beta = 0.0; sc->zs = 0.0;
         sc->max_error = 0.0; sc->max_bits = 0ull;
@@ -536,13 +525,9 @@ __global__ void k_solve_reset(SkewGeom g, double* bnd_f, double* bnd_b, SolveSca
     }
 }
 
-/* re-arm only the boundary rows/tickets (between two stand-alone sweeps) */
-__global__ void k_sweep_rearm(SkewGeom g, double* bnd_f, double* bnd_b, SolveScalars* sc) {
-    long long n = (long long)g.nstrips * g.w;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        bnd_f[i] = sentinel();
-        bnd_b[i] = sentinel();
-    }
+/* re-arm only the rows / tickets (before a stand-alone wavefront) */
+__global__ void k_sweep_rearm(SkewGeom g, double* bnd_f, double* bnd_b, double* inbox_f, double* inbox_b, int inbox_len, SolveScalars* sc) {
+    arm_rows(g, bnd_f, bnd_b, inbox_f, inbox_b, inbox_len);
     if (blockIdx.x == 0 && threadIdx.x == 0) { sc->ticket_f = 0; sc->ticket_b = 0; sc->ctr_b = 0; sc->ctr_c = 0; }
 }
 
@@ -682,7 +667,6 @@ static constexpr int SW_WARPS = IFL_SW_WARPS;       /* strips per block of the s
 static constexpr int SW_TILE = SW_U * 32 * SKB;     /* doubles per array per block (2 KB) */
 static constexpr int SW_PACK = 3 * SW_TILE;         /* packed coefficient block: 3 arrays (6 KB) */
 static constexpr int SW_FG = 8;                     /* macro-steps per block of the sweep loop (edge-feed group, hand-over granularity) */
-static constexpr int SW_GV = SW_FG * SKB;           /* edge values per block */
 static_assert(SW_FG % SW_U == 0 && SW_FG % 2 == 0, "a block is a whole, even number of staged tiles");
 
 /* Packed sweep coefficients.  applyPreconditioner multiplies `aPlusX[i]*precon[i]` and
@@ -738,133 +722,19 @@ static constexpr int SW_RB = 128;                  /* ring slots per strip inbox
 /* sentinel test on the high word only (0xFFF8B200: a NaN payload no arithmetic produces) */
 __device__ __forceinline__ bool is_sentinel_hi(double v) { return __double2hiint(v) == (int)0xFFF8B200; }
 
-/* Incoming edge values of one group of SW_FG macro-steps (SKB values each).  In ring mode the values of a producer
- * macro-step live in slots (producer step & 127)*SKB + j, and the producer's step is the consumer's step + 31; in
- * global-row mode the index is the column. */
-struct EdgeSrc {
-    const double* src;        /* global boundary row, or this warp's shared-memory ring (generic address) */
-    double* ring;             /* the ring, writable (re-arm); nullptr in global mode */
-    int w;
-    bool feeder;              /* this lane reads the edge values */
-    int mode;                 /* 0 none, 1 global row, 2 ring */
-    __device__ __forceinline__ int index(int x, int sc, int j) const {
-        return mode == 2 ? (((sc + 31) & (SW_RB - 1)) * SKB + j) : x;
-    }
-    /* c0 / sc0: column block and consumer step count of the group's first macro-step; they advance by (dir, +1) */
-    __device__ __forceinline__ void fetch(double (&v)[SW_GV], int c0, int sc0, int dir) const {
-#pragma unroll
-        for (int s = 0; s < SW_FG; s++)
-#pragma unroll
-            for (int j = 0; j < SKB; j++) {
-                const int x = (c0 + dir * s) * SKB + j;
-                v[s * SKB + j] = (feeder && x >= 0 && x < w) ? ld_volatile(src + index(x, sc0 + s, j)) : 0.0;
-            }
-    }
-    /* ring mode, every column of the block valid: the SW_GV values are consecutive, 16-byte aligned slots */
-    __device__ __forceinline__ void fetch_ring(double (&v)[SW_GV], int sc0) const {
-        const double* p = src + ((sc0 + 31) & (SW_RB - 1)) * SKB;
-#pragma unroll
-        for (int i = 0; i < SW_GV; i += 2) {
-            double2 t;
-            asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(smem_u32(p + i)));
-            v[i] = t.x; v[i + 1] = t.y;
-        }
-    }
-    /* tight poll on the value that is stored last, then the whole block again (the caller re-checks every value:
-     * stores of one thread to different addresses need not become visible in order) */
-    __device__ __forceinline__ void wait_ring(double (&v)[SW_GV], int sc0) const {
-        const unsigned last_hi = smem_u32(src + ((sc0 + 31) & (SW_RB - 1)) * SKB + (SW_GV - 1)) + 4u;
-        unsigned hi, spins = 0;
-        do {
-            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(hi) : "r"(last_hi));
-        } while (hi == 0xFFF8B200u && ++spins < (1u << 24));
-        fetch_ring(v, sc0);
-    }
-    __device__ __forceinline__ void rearm_ring(int sc0) const {
-        double* p = ring + ((sc0 + 31) & (SW_RB - 1)) * SKB;
-        const double sv = sentinel();
-#pragma unroll
-        for (int i = 0; i < SW_GV; i += 2) *reinterpret_cast<double2*>(p + i) = make_double2(sv, sv);
-    }
-    __device__ __forceinline__ bool ready(const double (&v)[SW_GV]) const {
-        bool ok = true;
-#pragma unroll
-        for (int i = 0; i < SW_GV; i++) ok = ok && !is_sentinel_hi(v[i]);
-        return __all_sync(0xffffffffu, ok);
-    }
-    /* spin (bounded) until every value of the group has arrived */
-    __device__ __forceinline__ void wait(double (&v)[SW_GV], int c0, int sc0, int dir) const {
-        for (unsigned spins = 0;; spins++) {
-            bool ok = true;
-#pragma unroll
-            for (int i = 0; i < SW_GV; i++) ok = ok && !is_sentinel_hi(v[i]);
-            ok = ok || spins > (1u << 24);
-            if (__all_sync(0xffffffffu, ok)) break;
-#pragma unroll
-            for (int s = 0; s < SW_FG; s++)
-#pragma unroll
-                for (int j = 0; j < SKB; j++)
-                    if (is_sentinel_hi(v[s * SKB + j]))
-                        v[s * SKB + j] = ld_volatile(src + index((c0 + dir * s) * SKB + j, sc0 + s, j));
-        }
-#pragma unroll
-        for (int i = 0; i < SW_GV; i++) if (is_sentinel_hi(v[i])) v[i] = 0.0;     /* gave up: dead producer */
-    }
-    __device__ __forceinline__ void rearm(int c0, int sc0, int dir) const {
-        if (mode != 2 || !feeder) return;
-#pragma unroll
-        for (int s = 0; s < SW_FG; s++)
-#pragma unroll
-            for (int j = 0; j < SKB; j++) {
-                const int x = (c0 + dir * s) * SKB + j;
-                if (x >= 0 && x < w) ring[((sc0 + 31 + s) & (SW_RB - 1)) * SKB + j] = sentinel();
-            }
-    }
-};
-
-/* the SKB adjacent cells of one lane and macro-step (16-byte aligned in every skewed array and staged tile) */
-__device__ __forceinline__ void load_cells(const double* p, double* out) {
-    if (SKB == 2) { const double2 t = *reinterpret_cast<const double2*>(p); out[0] = t.x; out[SKB - 1] = t.y; }
-    else {
-#pragma unroll
-        for (int j = 0; j < SKB; j++) out[j] = p[j];
-    }
+__device__ __forceinline__ void ld_volatile_v2(const double* p, double& a, double& b) {      /* generic address */
+    asm volatile("ld.volatile.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p) : "memory");
 }
-__device__ __forceinline__ void store_cells(double* p, const double (&d)[SKB]) {
-    if (SKB == 2) *reinterpret_cast<double2*>(p) = make_double2(d[0], d[SKB - 1]);
-    else {
-#pragma unroll
-        for (int j = 0; j < SKB; j++) p[j] = d[j];
-    }
+__device__ __forceinline__ void st_v2(double* p, double a, double b) {                      /* generic address */
+    asm volatile("st.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
-
-/* operands of one macro-step of one lane: SKB adjacent cells of every staged array (one 16-byte shared-memory load
- * per array for SKB = 2).  They are fetched one macro-step ahead of their use: with one warp per scheduler nothing
- * else hides a shared-memory load that sits between two dependent FP64 operations. */
-struct CellOps {
-    double a[SKB], cx[SKB], cy[SKB], pr[SKB], rr[SKB];
-};
+/* predicated 16-byte store without a branch (written as `if`, a store under a lane predicate becomes a divergent branch) */
+__device__ __forceinline__ void st_v2_if(bool p, double* addr, double a, double b) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.v2.f64 [%1], {%2, %3};\n}" ::"r"((unsigned)p), "l"(addr), "d"(a), "d"(b) : "memory");
+}
 __device__ __forceinline__ void lds_cells(unsigned addr, double* out) {
     static_assert(SKB == 2, "one 16-byte shared-memory load per array and macro-step");
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(out[0]), "=d"(out[1]) : "r"(addr));
-}
-/* stage layout: [src tile | cx | cy | pr | rr tile]; `tile` = shared address of this lane's cells of the tile's first row */
-template <int DIR, bool WITH_DOT>
-__device__ __forceinline__ void load_step(CellOps& o, unsigned tile, int row) {
-    const unsigned p = tile + (unsigned)((DIR > 0 ? row : SW_U - 1 - row) * (32 * SKB) * sizeof(double));
-    lds_cells(p, o.a);
-    lds_cells(p + SW_TILE * (unsigned)sizeof(double), o.cx);
-    lds_cells(p + 2 * SW_TILE * (unsigned)sizeof(double), o.cy);
-    lds_cells(p + 3 * SW_TILE * (unsigned)sizeof(double), o.pr);
-    if (WITH_DOT) lds_cells(p + (SW_TILE + SW_PACK) * (unsigned)sizeof(double), o.rr);
-}
-
-/* predicated stores without a branch (a divergent branch plus reconvergence costs more than a macro-step's arithmetic) */
-__device__ __forceinline__ void st_if(bool p, double* addr, double v) {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.f64 [%1], %2;\n}" ::"r"((unsigned)p), "l"(addr), "d"(v));
-}
-__device__ __forceinline__ void st_int_if(bool p, volatile int* addr, int v) {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.volatile.s32 [%1], %2;\n}" ::"r"((unsigned)p), "l"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_if(bool p, unsigned bar) {
     asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q mbarrier.arrive.shared::cta.b64 _, [%1];\n}" ::"r"((unsigned)p), "r"(bar) : "memory");
@@ -883,138 +753,38 @@ __device__ __forceinline__ void mbar_wait_u32(unsigned bar, unsigned parity) {
 /* keeps a value in a register: the compiler would otherwise re-derive shared-memory addresses from the thread id on
  * every use, which costs issue slots on a one-warp-per-scheduler critical path */
 __device__ __forceinline__ unsigned pin_u32(unsigned v) { asm volatile("mov.u32 %0, %0;" : "+r"(v)); return v; }
-__device__ __forceinline__ unsigned mapa_u32(unsigned local_addr, unsigned cta_rank) {
-    unsigned r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
-    return r;
-}
 
-/* ---- per-macro-step edge feed from this strip's shared-memory ring ------------------------------------------------
- * Every lane reads the same slot pair (a broadcast), so the flag-in-data test is warp uniform: no vote, no divergence.
- * The pair is requested one macro-step before it is tested; when it has not arrived the warp re-reads it (bounded).
- * Re-arming stores the sentinel's high word over both values (every lane, same address, same data). */
-__device__ __forceinline__ void ring_peek(unsigned slot_addr, double (&v)[SKB]) {
-    static_assert(SKB == 2, "one 16-byte slot pair per macro-step");
-    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(slot_addr) : "memory");
-}
-__device__ __forceinline__ void ring_rearm(unsigned slot_addr, unsigned sent_hi) {
-    asm volatile("st.volatile.shared.u32 [%0+4], %1;\n\tst.volatile.shared.u32 [%0+12], %1;" ::"r"(slot_addr), "r"(sent_hi) : "memory");
-}
-/* need0 / need1: which of the two values exist (a column block can straddle the right edge of the grid) */
-#ifdef IFL_SW_TRACE_WAITS
-#define IFL_TW_ARGS , long long& tw_nstarved, long long& tw_nspins
-#define IFL_TW_PASS , tw_nstarved, tw_nspins
-#else
-#define IFL_TW_ARGS
-#define IFL_TW_PASS
-#endif
-__device__ __forceinline__ void ring_wait(unsigned slot_addr, double (&v)[SKB], bool need0, bool need1 IFL_TW_ARGS) {
-    if (__builtin_expect((need0 && is_sentinel_hi(v[0])) || (need1 && is_sentinel_hi(v[SKB - 1])), 0)) {
-        unsigned spins = 0;
-        do { ring_peek(slot_addr, v); }
-        while (((need0 && is_sentinel_hi(v[0])) || (need1 && is_sentinel_hi(v[SKB - 1]))) && ++spins < (1u << 22));
-#ifdef IFL_SW_TRACE_WAITS
-        tw_nstarved++; tw_nspins += spins + 1;
-#endif
-    }
-}
-
-/* One macro-step of one lane: the SKB cells x = (m - lane)*SKB + j of its row, in the sweep's direction.  The left/right
- * neighbour is the previous cell of the same lane (a register); the upper/lower neighbours `dn` are the SKB results of
- * the adjacent lane's PREVIOUS macro-step.
- * Lane-to-lane hand-over goes through shared memory: every lane stores each result, as soon as it exists, into its own
- * exchange slot (the lane at the outgoing edge of a ring-out strip: straight into the next strip's ring slot) and loads
- * the adjacent lane's slot (the lane at the incoming edge: this strip's ring slot, or a zero slot) -- one 8-byte store and
- * one 8-byte load per cell, and the loaded values land in an aligned register pair.  xw / xr: this macro-step's store
- * slot (generic address: it may be a mapped, remote ring slot) and load slot (shared address).  `edge_next`: incoming
- * edge values held in registers (global boundary row), injected by the lane at the incoming edge; nullptr = none.
- * OUTRING: the outgoing edge went to a ring through xw; otherwise it is also stored at po (global boundary row). */
-__device__ __forceinline__ void xchg_store(double* slot, double v) {
-    asm volatile("st.f64 [%0], %1;" ::"l"(slot), "d"(v) : "memory");
-}
-__device__ __forceinline__ double xchg_load(unsigned addr) {
-    double v;
-    asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
-    return v;
-}
-template <int DIR, bool WITH_DOT, bool CHECKED, bool MASKED, bool OUTRING>
-__device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB], const double* edge_next, const int m,
-                                           const int lane, const bool is_out, const int w, const bool yok,
-                                           double* pd, double* po, double* dummy, double (&dprev)[SKB], double& cxprev,
-                                           double& acc, double* xw, const unsigned xr, const bool is_in_feed) {
-    double dl = DIR > 0 ? dprev[SKB - 1] : dprev[0];
-    bool fl[SKB];
-    double dnn[SKB];
-#pragma unroll
-    for (int jj = 0; jj < SKB; jj++) {
-        const int j = DIR > 0 ? jj : SKB - 1 - jj;
-        const double pr = op.pr[j];
-        double v = op.a[j];
-        if (DIR > 0) {
-            v = v - cxprev * dl;         /* (aPlusX[i-1]*precon[i-1]) * dst[i-1]   F3:500 */
-            v = v - op.cy[j] * dn[j];    /* (aPlusY[i-w]*precon[i-w]) * dst[i-w]   F3:503 */
-            cxprev = op.cx[j];
-        } else {
-            v = v - op.cx[j] * dl;       /* (aPlusX[i]*precon[i]) * dst[i+1]       F3:514 */
-            v = v - op.cy[j] * dn[j];    /* (aPlusY[i]*precon[i]) * dst[i+w]       F3:517 */
-        }
-        double d = v * pr;
-        fl[j] = MASKED ? (pr == pr) : true;              /* NaN precon tags a non-fluid cell (k_precon_coeffs) */
-        if (MASKED) d = fl[j] ? d : 0.0;                 /* skipped cell: dst stays, neighbours see +0.0 */
-        /* store, then load, in program order: the warp is converged here and its shared-memory accesses are performed in
-         * order, so the load of lane l sees the store of lane l-1 of the same macro-step */
-        xchg_store(xw + j, d);                           /* hand the result to the adjacent lane right away */
-        dnn[j] = xchg_load(xr + (unsigned)(j * sizeof(double)));
-        if (edge_next != nullptr) dnn[j] = is_in_feed ? edge_next[j] : dnn[j];      /* edge values held in registers */
-        /* inactive lanes hold +0.0 and rr is zero in the padding: adding them is exact */
-        if (WITH_DOT) acc += d * op.rr[j];
-        dprev[j] = d;
-        dl = d;
-    }
-    if (CHECKED) {
-        const int xb = (m - lane) * SKB;
-#pragma unroll
-        for (int j = 0; j < SKB; j++) {
-            const int x = xb + j;
-            const bool inx = x >= 0 && x < w;
-            st_if(yok && inx && fl[j], pd + j, dprev[j]);
-            if (!OUTRING) st_if(inx && is_out, po + j, dprev[j]);           /* the edge value is published for every column */
-        }
-    } else {
-        /* interior block: only rows y >= h are inactive; they hold +0.0, and storing +0.0 into
-         * their (zero) padding cells keeps the padding zero -- no predicate needed.  Lanes that have nothing to
-         * store (not the edge lane; a non-fluid cell) store into a per-lane dummy slot instead: an unconditional
-         * store with a selected address, because a predicated store is turned into a divergent branch. */
-        if (MASKED) {
-#pragma unroll
-            for (int j = 0; j < SKB; j++) *(fl[j] ? pd + j : dummy + j) = dprev[j];
-        } else {
-            store_cells(pd, dprev);
-        }
-        if (OUTRING) {}
-        else {
-#pragma unroll
-            for (int j = 0; j < SKB; j++) po[j] = dprev[j];   /* po: the edge lane's slot, the dummy slot for the others */
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < SKB; j++) dn[j] = dnn[j];
-}
-
-/* applyPreconditioner F3:495: DIR=+1 forward substitution (first loop nest), DIR=-1
- * backward substitution (second loop nest).  WITH_DOT (backward only) accumulates
- * dotProduct(dst, rr) per strip (F3:602 / F3:625).
+/* applyPreconditioner F3:495: DIR=+1 forward substitution (first loop nest), DIR=-1 backward substitution (second loop
+ * nest).  WITH_DOT (backward only) accumulates dotProduct(dst, rr) per strip (F3:602 / F3:625).
  *
- * The reference guards the two neighbour terms with x>0 / y>0 (x<w-1 / y<h-1).  Here the
- * guards are implicit: every skewed array is zero outside the grid (padding cells, plus one
- * all-zero strip before and after), and inactive lanes provably carry +0.0, so the guarded
- * products are +0.0 and `v - (+0.0)` returns v bit-for-bit (also for v = -0.0).  For the
- * backward sweep aPlusX(w-1,y) and aPlusY(x,h-1) are +0.0 by construction (F3:447,454).
+ * A warp owns a strip of 32 rows (lane l = row l) and at macro-step m works on the two cells of column block c = m - l
+ * (one 512-byte m-row of the skewed layout): the left neighbour of its first cell is its own previous result (a
+ * register), the upper neighbours are lane l-1's results of its previous macro-step (two 64-bit shuffles issued at the
+ * start of the macro-step, off the dependency chain).  Any schedule that respects the left/up dependencies performs
+ * exactly the reference's per-cell operations, so the results are bit-identical to the lexicographic loops.  A macro-step
+ * is nothing but the recurrence (10 FP64 operations), the shuffles, five 16-byte operand loads for the NEXT macro-step and
+ * two 16-byte stores.
  *
- * Block layout: SW_WARPS strip warps (0..SW_WARPS-1) and as many loader warps; loader warp SW_WARPS+i streams the
- * operands of strip warp i into that warp's shared-memory ring with bulk copies (full/empty mbarrier pair per stage),
- * so that no copy bookkeeping sits on the strip warp's dependency chain. */
-/* FUSE (forward sweep inside the PCG loop only): the loader warp of every strip also performs, tile by tile and before
+ * The reference guards the two neighbour terms with x>0 / y>0 (x<w-1 / y<h-1).  Here the guards are implicit: every
+ * skewed array is zero outside the grid (padding cells, plus one all-zero strip before and after), inactive lanes
+ * provably carry +0.0, so the guarded products are +0.0 and `v - (+0.0)` returns v bit-for-bit (also for v = -0.0); for
+ * the backward sweep aPlusX(w-1,y) and aPlusY(x,h-1) are +0.0 by construction (F3:447,454).  Storing the +0.0 of an
+ * inactive lane into its padding cell keeps the padding zero.  Hence ONE code path, without a per-cell predicate, for
+ * every block of every strip.
+ *
+ * Strips run on consecutive warps of a thread-block cluster (SW_CL blocks x SW_WARPS strip warps; every strip warp has
+ * a loader warp that streams its operands with bulk copies into a shared-memory ring, full/empty mbarrier pair per
+ * stage).  Strip k+1 consumes the edge row of strip k -- the results of its last lane -- through an INBOX indexed by
+ * the producer's macro-step + 1: consumer macro-step c needs the pair of producer macro-step c + 31.  Inside a cluster
+ * the inbox is a 128-pair ring in the consumer's shared memory, written with distributed-shared-memory stores; between
+ * clusters and between GPUs it is a row of global memory (CUDA-IPC-mapped peer memory over NVLink on the next GPU).
+ * Flag-in-data: a slot holds a NaN sentinel until the value is stored; the consumer takes the 8 pairs of a block of 8
+ * macro-steps at once (requested one block ahead, polled only if late) and re-arms them; a credit word written back into
+ * the producer's shared memory keeps the producer from lapping a ring.  No fences on the critical path, every spin is
+ * bounded.  Clusters take an atomic ticket, so a waiting cluster's predecessor has always started (deadlock-free
+ * without a cooperative launch).
+ *
+ * FUSE (forward sweep inside the PCG loop only): the loader warp of every strip also performs, tile by tile and before
  * the strip warp sees the operands,
  *     r += (-alpha) * z            scaledAdd(_r, _r, _z, -alpha)  F3:608   (FUSE = 2: fluid cells only, F6:1041)
  *     maxError = infinityNorm(r)   F3:609 / F6:1054, and the convergence decision F3:611-619 when the last strip is done,
@@ -1026,10 +796,11 @@ __device__ __forceinline__ void sweep_step(const CellOps& op, double (&dn)[SKB],
 template <int DIR, bool WITH_DOT, bool MASKED, int FUSE>
 __global__ void __launch_bounds__(2 * SW_WARPS * 32)
 k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, const double* __restrict__ pack,
-               const double* __restrict__ rr, double* bnd, double* bnd_peer, double* strip_part,
+               const double* __restrict__ rr, double* inbox, double* inbox_peer, int inbox_len, double* strip_part,
                SolveScalars* sc, int dot_mode, int check_done, long long* trace,
                double tol, unsigned long long* rank_max, int rank, int single_gpu) {
     static_assert(FUSE == 0 || (DIR > 0 && !WITH_DOT), "the r update rides on the forward sweep");
+    static_assert(SKB == 2 && SW_U == SW_FG && SW_FG == 8, "a block of the strip loop is one staged tile of 8 macro-steps");
     namespace cg = cooperative_groups;
     constexpr int U = SW_U;                                           /* macro-steps per staged tile */
     constexpr int UB = SW_FG;                                         /* macro-steps per block of the loop */
@@ -1044,12 +815,8 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
     constexpr int E_OUT = DIR > 0 ? 31 : 0;
     extern __shared__ __align__(128) unsigned char wf_smem[];
     __shared__ __align__(16) double s_inbox[SW_WARPS][SW_RB * SKB];   /* edge-row rings of this block's strips */
-    __shared__ volatile int s_credit[SW_WARPS];          /* steps of MINE the strip after me has consumed */
-    __shared__ __align__(16) double s_dummy[SW_WARPS][32][SKB];       /* where lanes with nothing to publish store */
-    __shared__ __align__(16) double s_scratch[SW_WARPS][SW_FG * SKB]; /* ... when the edge row goes to a ring (one block of slots) */
-    constexpr int XS = SW_FG * SKB + 1;                               /* doubles per lane: one slot per macro-step of a block, */
-    __shared__ __align__(16) double s_xchg[SW_WARPS][32 * XS];        /* odd stride (conflict-free 8-byte accesses)            */
-    __shared__ __align__(16) double s_zero[SW_FG * SKB];              /* what the lane at an edge without a neighbour reads     */
+    __shared__ volatile int s_credit[SW_WARPS];          /* macro-steps of MINE the strip after me has consumed */
+    __shared__ __align__(16) double s_dummy[SW_WARPS][32][SKB];           /* where a non-fluid cell (MASKED) stores */
     __shared__ int s_ticket;
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks();
@@ -1068,8 +835,7 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
     unsigned long long* bar_empty = bar_full + S;
     unsigned long long* bar_ready = bar_empty + S;       /* FUSE: the loader warp has updated r in the staged tile */
     if (!loader) {
-        for (int i = lane; i < 32 * XS; i += 32) s_xchg[warp][i] = 0.0;
-        if (warp == 0 && lane < SW_FG * SKB) s_zero[lane] = 0.0;
+        s_dummy[warp][lane][0] = 0.0; s_dummy[warp][lane][SKB - 1] = 0.0;
         for (int i = lane; i < SW_RB * SKB; i += 32) s_inbox[warp][i] = sentinel();
         if (lane == 0) {
             s_credit[warp] = 0;
@@ -1252,273 +1018,232 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
             }
         }
     } else if (live) {
-        const int y = k * 32 + lane;
-        const bool yok = y < g.h;
-        const int tfirst = DIR > 0 ? 0 : nblk * UB - 1;
+        const int nsteps = nblk * UB;                                     /* macro-steps of a strip (>= column blocks + 31) */
+        const int tfirst = DIR > 0 ? 0 : nsteps - 1;
         const bool has_prev = DIR > 0 ? (k > 0) : (k < g.nstrips - 1);
+        const bool has_next = DIR > 0 ? (k < g.nstrips - 1) : (k > 0);
         const bool is_out = lane == E_OUT;
-        const bool lane0 = lane == 0;
-
-        /* incoming edge: my own ring unless I am the first strip of the cluster (then a global boundary row) */
-        const bool in_ring = cslot > 0;
-        EdgeSrc feed;
-        feed.mode = !has_prev ? 0 : (in_ring ? 2 : 1);
-        feed.src = in_ring ? &s_inbox[warp][0] : (has_prev ? bnd + (long long)(k - DIR) * w : nullptr);
-        feed.ring = in_ring ? &s_inbox[warp][0] : nullptr;
-        feed.w = w;
-        feed.feeder = lane == E_IN && feed.mode != 0;                     /* the lane that consumes the edge values */
-        const bool use_feed = feed.mode != 0;                             /* warp uniform */
-        const bool ring_feed = feed.mode == 2;
-        /* outgoing edge: the next strip's ring (mapped shared memory of its block) unless I am the last strip of
-         * the cluster / of my slab (then the global boundary row, possibly in the neighbour GPU's memory) */
-        const bool out_ring = (cslot < csize * SW_WARPS - 1) && (slot + 1 < nown);
-        const bool to_peer = bnd_peer != nullptr && (DIR > 0 ? k == g.s1 - 1 : k == g.s0);
-        double* out_base;
-        volatile int* credit_of_prev = nullptr;
-        if (out_ring) out_base = cluster.map_shared_rank(&s_inbox[(cslot + 1) % SW_WARPS][0], (cslot + 1) / SW_WARPS);
-        else out_base = (to_peer ? bnd_peer : bnd) + (long long)k * w;
-        if (in_ring) credit_of_prev = cluster.map_shared_rank((int*)&s_credit[(cslot - 1) % SW_WARPS], (cslot - 1) / SW_WARPS);
-        const bool pub_credit = lane0 && credit_of_prev != nullptr;
-        /* shared::cluster addresses of the next strip's ring and of my scratch slots */
-        double* const oscratch = &s_scratch[warp][0];
         const bool is_in = lane == E_IN;
-        double* const xw_own = &s_xchg[warp][lane * XS];
-        const unsigned xr_nb = pin_u32(smem_u32(&s_xchg[warp][((lane - DIR) & 31) * XS]));
-        const unsigned xr_zero = pin_u32(smem_u32(&s_zero[0]));
-        /* per macro-step the edge lane's store moves by +1 slot group in a ring, by DIR column blocks in a global row */
+        const bool lane0 = lane == 0;
+        /* incoming edge values: my shared-memory ring if my predecessor runs in this cluster, else my global inbox row */
+        const bool in_ring = cslot > 0;
+        const double* const in_base = !has_prev ? nullptr : (in_ring ? &s_inbox[warp][0] : inbox + (long long)k * inbox_len);
+        const unsigned in_mask = in_ring ? (unsigned)(SW_RB - 1) : 0xffffffffu;
+        const unsigned in_ring_addr = in_ring ? smem_u32(&s_inbox[warp][0]) : 0u;
+        /* outgoing edge values: the next strip's ring (mapped shared memory of its block), or its global inbox row --
+         * in the neighbour GPU's memory when the next strip belongs to the next rank */
+        const bool out_ring = (cslot < csize * SW_WARPS - 1) && (slot + 1 < nown);
+        double* out_base = nullptr;
+        unsigned out_mask = 0xffffffffu;
+        if (out_ring) {
+            out_base = cluster.map_shared_rank(&s_inbox[(cslot + 1) % SW_WARPS][0], (cslot + 1) / SW_WARPS);
+            out_mask = (unsigned)(SW_RB - 1);
+        } else if (has_next) {
+            const bool to_peer = inbox_peer != nullptr && (DIR > 0 ? k == g.s1 - 1 : k == g.s0);
+            out_base = (to_peer ? inbox_peer : inbox) + (long long)(k + DIR) * inbox_len;
+        }
+        const bool can_pub = out_base != nullptr;
+        volatile int* const credit_of_prev =
+            in_ring ? cluster.map_shared_rank((int*)&s_credit[(cslot - 1) % SW_WARPS], (cslot - 1) / SW_WARPS) : nullptr;
+        double* const dummy = &s_dummy[warp][lane][0];
+        const int last_edge_block = nblk - 4;           /* the producer's last real macro-step is taken in this block */
 
-        double* pdst = dst + (long long)k * g.ss + ((long long)tfirst * 32 + lane) * SKB;
-        double dprev[SKB];
+        /* edge values of block b: consumer macro-steps 8b .. 8b+7 = producer macro-steps 8b+31 .. 8b+38 = pair slots
+         * 8b+32 .. 8b+39.  Every lane reads the same addresses (a broadcast), so the flag-in-data test is warp uniform. */
+        auto edge_fetch = [&](double (&e)[UB * SKB], const int b) {
+            if (in_base != nullptr && b <= last_edge_block) {
+                const unsigned slot0 = (unsigned)(b * UB + 32) & in_mask;
+                if (in_ring) {                              /* warp uniform */
+                    const unsigned q = in_ring_addr + slot0 * (unsigned)(SKB * sizeof(double));
 #pragma unroll
-        for (int j = 0; j < SKB; j++) dprev[j] = 0.0;
-        double cxprev = 0.0;
-        long long tr_first = 0;
-#ifdef IFL_SW_TRACE_WAITS
-        long long tw_edge = 0, tw_op = 0, tw_credit = 0;      /* clocks spent waiting: incoming edge, operand tiles, ring credit */
-        long long tw_nstarved = 0, tw_nspins = 0, tw_t4 = 0;  /* macro-steps that found no edge value yet; re-reads; time at block 4 */
-#define IFL_TW_BEGIN const long long tw_c0_ = clock64();
-#define IFL_TW_END(acc) acc += clock64() - tw_c0_;
-#else
-#define IFL_TW_BEGIN
-#define IFL_TW_END(acc)
-#endif
+                    for (int i = 0; i < UB * SKB; i += 2)
+                        asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e[i]), "=d"(e[i + 1]) : "r"(q + 8u * i) : "memory");
+                } else {
+                    const double* q = in_base + (size_t)slot0 * SKB;
+#pragma unroll
+                    for (int i = 0; i < UB * SKB; i += 2) ld_volatile_v2(q + i, e[i], e[i + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < UB * SKB; i++) e[i] = 0.0;   /* no neighbour, or columns right / left of the grid */
+            }
+        };
+        auto edge_wait = [&](double (&e)[UB * SKB], const int b) {
+            if (in_base == nullptr || b > last_edge_block) return;
+            for (unsigned spins = 0;; spins++) {
+                bool ok = true;
+#pragma unroll
+                for (int i = 0; i < UB * SKB; i++) ok = ok && !is_sentinel_hi(e[i]);
+                if (ok) break;
+                if (spins > (1u << 22)) {                  /* dead producer: give up instead of hanging the GPU */
+#pragma unroll
+                    for (int i = 0; i < UB * SKB; i++) if (is_sentinel_hi(e[i])) e[i] = 0.0;
+                    break;
+                }
+                edge_fetch(e, b);
+            }
+            if (lane0) {                                    /* re-arm what was taken */
+                double* q = const_cast<double*>(in_base) + (size_t)((unsigned)(b * UB + 32) & in_mask) * SKB;
+                const double sv = sentinel();
+#pragma unroll
+                for (int i = 0; i < UB * SKB; i += 2) st_v2(q + i, sv, sv);
+            }
+        };
+        /* credit: the last macro-step of the next two blocks must not lap the consumer's ring */
+        auto credit_wait = [&](const int last_step) {
+            if (!out_ring) return;
+            for (unsigned spins = 0; last_step - s_credit[warp] >= SW_RB && spins < (1u << 24); spins++) {}
+        };
 
-        /* tile cursor: stage st holds the tile the operand loads currently read; shared addresses kept in registers */
+        /* operands of one macro-step: the two adjacent cells of every staged array (one 16-byte shared-memory load per
+         * array), fetched one macro-step ahead of their use */
+        struct Ops { double a[SKB], cx[SKB], cy[SKB], pr[SKB], rr[SKB]; };
+        auto load_step = [&](Ops& o, const unsigned tile, const int row) {
+            const unsigned p = tile + (unsigned)((DIR > 0 ? row : U - 1 - row) * (32 * SKB) * (int)sizeof(double));
+            lds_cells(p, o.a);
+            lds_cells(p + SW_TILE * (unsigned)sizeof(double), o.cx);
+            lds_cells(p + 2 * SW_TILE * (unsigned)sizeof(double), o.cy);
+            lds_cells(p + 3 * SW_TILE * (unsigned)sizeof(double), o.pr);
+            if (WITH_DOT) lds_cells(p + (SW_TILE + SW_PACK) * (unsigned)sizeof(double), o.rr);
+        };
+        double d0 = 0.0, d1 = 0.0, cxp = 0.0;
+        double sh0 = 0.0, sh1 = 0.0;                      /* the adjacent lane's results of its previous macro-step */
+        /* running pointer to this lane's cells of the current block's first macro-step */
+        double* pd = dst + (long long)k * g.ss + ((long long)tfirst * 32 + lane) * SKB;
+
         const unsigned ring_lane = pin_u32(smem_u32(ring + lane * SKB));
         const unsigned full0 = pin_u32(smem_u32(FUSE ? bar_ready : bar_full));   /* what tells this warp that a tile is usable */
         const unsigned empty0 = pin_u32(smem_u32(bar_empty));
-        const unsigned inbox0 = pin_u32(smem_u32(&s_inbox[warp][0]));
         int st = 0;
         unsigned ph = 0;
-        unsigned tile = ring_lane;
-        /* edge-out stores are unconditional: the edge lane's pointer walks the ring / boundary row, every other lane
-         * keeps storing into its own dummy slot */
-        double* const dummy = &s_dummy[warp][lane][0];
-
-        CellOps ops[2];
+        Ops ops[2];
 #pragma unroll
         for (int i = 0; i < 2; i++)
 #pragma unroll
             for (int j = 0; j < SKB; j++) { ops[i].a[j] = 0.0; ops[i].cx[j] = 0.0; ops[i].cy[j] = 0.0; ops[i].pr[j] = 0.0; ops[i].rr[j] = 0.0; }
-        mbar_wait_u32(full0, 0);
-        load_step<DIR, WITH_DOT>(ops[0], tile, 0);
+        double eA[UB * SKB], eB[UB * SKB];
+        long long tr_first = 0;
 
-        /* UB macro-steps, fully unrolled and branch-free: operands of macro-step s+1 are fetched before macro-step s
-         * is computed; at a tile boundary the next stage is awaited first and the finished one handed back after */
-        /* RINGFEED: the incoming edge values come from this strip's ring, macro-step by macro-step.  Consumer step c
-         * reads slot (c + 31) & 127; while computing macro-step s of the block the values of macro-step s+1 are taken, so
-         * a block takes the slots of its steps 1..8 (8 consecutive slots, the group does not wrap), and the rotation
-         * registers dn are carried from block to block.  Otherwise the values are in ecur (none / global boundary row). */
-        double dn[SKB], epk[2][SKB];          /* epk[q & 1]: edge values of macro-step q of the block (requested a step ahead) */
-#pragma unroll
-        for (int j = 0; j < SKB; j++) { dn[j] = 0.0; epk[0][j] = 0.0; epk[1][j] = 0.0; }
-        const unsigned sent_hi = pin_u32(0xFFF8B200u);
-        /* Blocks of UB macro-steps.  Hand-over protocol of a ring (the same for every producer / consumer pair):
-         *   - the producer publishes every macro-step from its 24th on (block 3 onwards; steps 24..30 carry the +0.0 of
-         *     cells left of the grid) into slot (step & 127), and 8 more zero pairs after its last macro-step;
-         *   - the consumer first waits for slots 24..31, re-arms them and starts from slot 31 (its macro-step c uses the
-         *     producer's macro-step c + 31); it then takes one slot per macro-step up to block nblk-4 and feeds zeros
-         *     afterwards (those columns lie right of the grid).
-         * So there is no per-step "does this edge value exist" decision, and the first and last blocks of a strip run
-         * the SAME code as the interior ones: cells outside the grid are zero padding, they provably produce +0.0, and
-         * storing +0.0 into padding keeps it zero.  (The first 31 macro-steps of every strip are on the critical path of
-         * the whole sweep.)  CHECKED blocks (per-cell predicates) remain only where the edge row goes to a global
-         * boundary row, which has no padding: the last strip of a cluster / slab. */
-        auto run_block = [&](auto checked_tag, auto ringfeed_tag, auto outring_tag, const int t0, const int sc0,
-                             const double (&ecur)[SW_GV], double* po_lane, const int ostep_l, double* xw_b) {
-            constexpr bool CHECKED = decltype(checked_tag)::value;
-            constexpr bool RINGFEED = decltype(ringfeed_tag)::value;
-            constexpr bool OUTRING = decltype(outring_tag)::value;
-            const unsigned in_rest = inbox0 + (unsigned)(((sc0 + 32) & (SW_RB - 1)) * SKB * (int)sizeof(double));
-            const unsigned in_next = inbox0 + (unsigned)(((sc0 + UB + 32) & (SW_RB - 1)) * SKB * (int)sizeof(double));
-            const int cin0 = t0 - E_IN;                                    /* column block the edge lane needs at step 0 */
-            double ecar[SKB];
-            /* the lane at the incoming edge reads the ring slots of the block's steps 1..8 (or zeros); values from a global
-             * boundary row are in registers (ecur) and replace what it read */
-            const bool is_in_feed = is_in && use_feed && !RINGFEED;
-            const unsigned xr_b = is_in ? (RINGFEED ? in_rest : xr_zero) : xr_nb;
-            if (!RINGFEED) {
-#pragma unroll
-                for (int j = 0; j < SKB; j++) dn[j] = is_in_feed ? ecur[j] : dn[j];
+        /* One block = one staged tile = 8 macro-steps, fully unrolled: the recurrence, two shuffles, the operand loads of the
+         * next macro-step (from the next tile at the last one, which is awaited first; the loader provides one tile more
+         * than the strip has) and two stores per macro-step.  The edge lane's pairs go to slots s0+1 .. s0+8 of the next
+         * strip's inbox: the first seven are consecutive (`pf`), only the last one can wrap around a ring (`pl`); every
+         * other lane stores into its own dummy slots. */
+        auto run_block = [&](const double (&e)[UB * SKB], const int b) {
+            const int s0 = b * UB;
+            const bool pub = is_out && can_pub && b >= 3;       /* only the lane at the outgoing edge stores (predicated) */
+            double* pf = dummy;
+            double* pl = dummy;
+            if (pub) {
+                pf = out_base + (size_t)((unsigned)(s0 + 1) & out_mask) * SKB;
+                pl = out_base + (size_t)((unsigned)(s0 + UB) & out_mask) * SKB;
             }
+            const unsigned tile = ring_lane + (unsigned)(st * STAGE * (int)sizeof(double));
+            unsigned done_bar = 0, tnext = tile;
 #pragma unroll
-            for (int s = 0; s < UB; s++) {
-                const int r = (s + 1) % U;
-                /* values of macro-step s+1: requested one macro-step ago into epk[(s+1)&1]; tested in the middle of this
-                 * macro-step (see sweep_step), then those of s+2 are requested */
-                auto edge_ready = [&]() {
-                    if (RINGFEED) {
-                        const unsigned a = in_rest + (unsigned)(s * SKB * (int)sizeof(double));
-                        double (&e)[SKB] = epk[(s + 1) & 1];
-                        ring_wait(a, e, true, true IFL_TW_PASS);
-                        if (CHECKED) {                                      /* the producer's padding cells hold +0.0 anyway */
-                            const int c = cin0 + DIR * (s + 1);
-#pragma unroll
-                            for (int j = 0; j < SKB; j++) if (c < 0 || c * SKB + j >= w) e[j] = 0.0;
-                        }
-                        ring_peek(s + 1 < UB ? a + (unsigned)(SKB * sizeof(double)) : in_next, epk[s & 1]);
-                    }
-                };
-                edge_ready();
-                if (!RINGFEED && s + 1 < UB) {
-#pragma unroll
-                    for (int j = 0; j < SKB; j++) ecar[j] = ecur[(s + 1) * SKB + j];
-                }
-                unsigned done_bar = 0;
-                if (r == 0) {
-                    done_bar = empty0 + 8u * st;
+            for (int u = 0; u < UB; u++) {
+                /* the upper neighbours: shuffled out of the adjacent lane as soon as it had them (below), i.e. half a
+                 * macro-step / a whole macro-step before they are needed */
+                double up0 = sh0, up1 = sh1;
+                if (u == UB - 1) {
+                    done_bar = empty0 + 8u * (unsigned)st;
                     const bool wrap = st == S - 1;
                     st = wrap ? 0 : st + 1;
                     ph ^= wrap ? 1u : 0u;
-                    tile = ring_lane + (unsigned)(st * STAGE * (int)sizeof(double));
-                    { IFL_TW_BEGIN mbar_wait_u32(full0 + 8u * st, ph); IFL_TW_END(tw_op) }
+                    tnext = ring_lane + (unsigned)(st * STAGE * (int)sizeof(double));
+                    mbar_wait_u32(full0 + 8u * (unsigned)st, ph);
                 }
-                load_step<DIR, WITH_DOT>(ops[(s + 1) & 1], tile, r);
-                const double* en = RINGFEED ? &epk[(s + 1) & 1][0] : (s + 1 < UB ? &ecar[0] : nullptr);
-                sweep_step<DIR, WITH_DOT, CHECKED, MASKED, OUTRING>(ops[s & 1], dn, en, t0 + DIR * s, lane, is_out, w, yok,
-                                                           pdst + DIR * s * (32 * SKB),
-                                                           po_lane + (OUTRING ? SKB : ostep_l) * s, dummy,
-                                                           dprev, cxprev, acc, xw_b + s * SKB,
-                                                           xr_b + (unsigned)(s * SKB * (int)sizeof(double)), is_in_feed);
-                if (RINGFEED) ring_rearm(in_rest + (unsigned)(s * SKB * (int)sizeof(double)), sent_hi);   /* after it was read */
-                /* every row of the finished tile is in registers (the loads are warp-wide instructions issued, in
-                 * order, before this arrive): hand the stage back to the loader warp */
-                if (r == 0) mbar_arrive_if(lane0, done_bar);
-            }
-        };
-
-        double eb0[SW_GV], eb1[SW_GV];                                     /* edge values from a global row: two blocks, ping-pong */
-#pragma unroll
-        for (int j = 0; j < SW_GV; j++) { eb0[j] = 0.0; eb1[j] = 0.0; }
-        constexpr std::false_type F{}; constexpr std::true_type T{};
-        const int nsteps = nblk * UB;
-
-        /* credit: the last step of the next two blocks must not lap the consumer's ring */
-        auto credit_wait = [&](const int last_step) {
-            IFL_TW_BEGIN
-            for (unsigned spins = 0; last_step - s_credit[warp] >= SW_RB && spins < (1u << 24); spins++) {}
-            IFL_TW_END(tw_credit)
-        };
-        if (ring_feed) {
-            /* prologue: the producer's macro-steps 24..31 (one slot group); only the last one carries a column of mine */
-            const unsigned a = inbox0 + (unsigned)(24 * SKB * (int)sizeof(double));
-            double e0[SKB];
-            for (int i = 0; i < 8; i++) {
-                ring_peek(a + (unsigned)(i * SKB * (int)sizeof(double)), e0);
-                ring_wait(a + (unsigned)(i * SKB * (int)sizeof(double)), e0, true, true IFL_TW_PASS);
-                ring_rearm(a + (unsigned)(i * SKB * (int)sizeof(double)), sent_hi);
-            }
-            if (!out_ring) {                                             /* CHECKED strip: do not rely on the padding */
-                const int c = tfirst - E_IN;
-#pragma unroll
-                for (int j = 0; j < SKB; j++) if (c < 0 || c * SKB + j >= w) e0[j] = 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < SKB; j++) {
-                dn[j] = is_in ? e0[j] : 0.0;
-            }
-            ring_peek(inbox0 + (unsigned)(32 * SKB * (int)sizeof(double)), epk[1]);            /* macro-step 1 */
-        }
-        const int last_ring_block = nblk - 4;                             /* the producer's last real macro-step is taken in this block */
-        if (out_ring && !(use_feed && !ring_feed)) {
-            /* both hand-overs through rings (or no incoming edge at all): one code path for every block */
-            for (int b = 0; b < nblk; b++) {
-                const int t0 = tfirst + DIR * b * UB, sc0 = b * UB;
-                if (trace && b == 1) tr_first = (long long)globaltimer_ns();
-#ifdef IFL_SW_TRACE_WAITS
-                if (trace && b == 4) tw_t4 = (long long)globaltimer_ns();
-#endif
-                if ((b & 1) == 0) credit_wait(sc0 + 2 * UB - 1);
-                double* po_lane = (is_out && b >= 3) ? out_base + (sc0 & (SW_RB - 1)) * SKB : oscratch;
-                double* xw_b = (is_out && b >= 3) ? po_lane : xw_own;   /* the edge lane's results go straight into the next ring */
-                if (ring_feed && b <= last_ring_block) run_block(F, T, T, t0, sc0, eb0, po_lane, 0, xw_b);
-                else                                   run_block(F, F, T, t0, sc0, eb0, po_lane, 0, xw_b);
-                pdst += DIR * UB * (32 * SKB);
-                /* I have consumed my producer's steps up to (my step count + 31) */
-                st_int_if(pub_credit, credit_of_prev, (b + 1) * UB + 31);
-            }
-        } else {
-            auto do_block = [&](const int b, double (&ecur)[SW_GV], double (&enext)[SW_GV]) {
-                const int t0 = tfirst + DIR * b * UB;
-                if (trace && b == 1) tr_first = (long long)globaltimer_ns();
-#ifdef IFL_SW_TRACE_WAITS
-                if (trace && b == 4) tw_t4 = (long long)globaltimer_ns();
-#endif
-                const int tlo = DIR > 0 ? t0 : t0 - (UB - 1);
-                const bool interior = (tlo - 31 >= 0) && ((tlo + UB - 1) * SKB + SKB - 1 < w);
-                const int sc0 = b * UB;                                    /* my step count at the block's first step */
-                const int cin = t0 - E_IN;                                 /* column block the edge lane needs first */
-                if (out_ring && (b & 1) == 0) credit_wait(sc0 + 2 * UB - 1);
-                if (use_feed && !ring_feed) {                              /* global boundary row: block by block */
-                    IFL_TW_BEGIN
-                    feed.fetch(enext, cin + DIR * UB, sc0 + UB, DIR);      /* next block */
-                    if (!feed.ready(ecur)) feed.wait(ecur, cin, sc0, DIR);
-                    IFL_TW_END(tw_edge)
-                }
-                const bool rf = ring_feed && b <= last_ring_block;
-                if (out_ring) {
-                    /* ring out, global row in: plain arithmetic and stores in every block (see above) */
-                    double* po_lane = (is_out && b >= 3) ? out_base + (sc0 & (SW_RB - 1)) * SKB : oscratch;
-                    double* xw_b = (is_out && b >= 3) ? po_lane : xw_own;
-                    run_block(F, F, T, t0, sc0, ecur, po_lane, 0, xw_b);
+                load_step(ops[(u + 1) & 1], tnext, (u + 1) % U);
+                const Ops& o = ops[u & 1];
+                if (is_in) { up0 = e[u * SKB]; up1 = e[u * SKB + 1]; }
+                double n0, n1;
+                bool f0 = true, f1 = true;
+                if (DIR > 0) {
+                    double v = o.a[0] - cxp * d1;       /* (aPlusX[i-1]*precon[i-1]) * dst[i-1]   F3:500 */
+                    v = v - o.cy[0] * up0;              /* (aPlusY[i-w]*precon[i-w]) * dst[i-w]   F3:503 */
+                    n0 = v * o.pr[0];
+                    if (MASKED) { f0 = o.pr[0] == o.pr[0]; n0 = f0 ? n0 : 0.0; }   /* NaN precon tags a non-fluid cell: dst stays, */
+                    sh0 = __shfl_up_sync(0xffffffffu, n0, 1);                      /* neighbours see +0.0 (k_precon_coeffs)        */
+                    v = o.a[1] - o.cx[0] * n0;
+                    v = v - o.cy[1] * up1;
+                    n1 = v * o.pr[1];
+                    if (MASKED) { f1 = o.pr[1] == o.pr[1]; n1 = f1 ? n1 : 0.0; }
+                    sh1 = __shfl_up_sync(0xffffffffu, n1, 1);
+                    cxp = o.cx[1];
                 } else {
-                    /* global row out: per-cell predicates in the first and last blocks */
-                    double* po_lane = is_out ? out_base + (t0 - E_OUT) * SKB : dummy;
-                    const int ostep_l = is_out ? DIR * SKB : 0;
-                    double* xw_b = xw_own;
-                    if (rf) {
-                        if (interior) run_block(F, T, F, t0, sc0, ecur, po_lane, ostep_l, xw_b);
-                        else          run_block(T, T, F, t0, sc0, ecur, po_lane, ostep_l, xw_b);
-                    } else {
-                        if (interior) run_block(F, F, F, t0, sc0, ecur, po_lane, ostep_l, xw_b);
-                        else          run_block(T, F, F, t0, sc0, ecur, po_lane, ostep_l, xw_b);
-                    }
+                    double v = o.a[1] - o.cx[1] * d0;   /* (aPlusX[i]*precon[i]) * dst[i+1]       F3:514 */
+                    v = v - o.cy[1] * up1;              /* (aPlusY[i]*precon[i]) * dst[i+w]       F3:517 */
+                    n1 = v * o.pr[1];
+                    if (MASKED) { f1 = o.pr[1] == o.pr[1]; n1 = f1 ? n1 : 0.0; }
+                    sh1 = __shfl_down_sync(0xffffffffu, n1, 1);
+                    v = o.a[0] - o.cx[0] * n1;
+                    v = v - o.cy[0] * up0;
+                    n0 = v * o.pr[0];
+                    if (MASKED) { f0 = o.pr[0] == o.pr[0]; n0 = f0 ? n0 : 0.0; }
+                    sh0 = __shfl_down_sync(0xffffffffu, n0, 1);
                 }
-                pdst += DIR * UB * (32 * SKB);
-                st_int_if(pub_credit, credit_of_prev, (b + 1) * UB + 31);
-            };
-            if (use_feed && !ring_feed) feed.fetch(eb0, tfirst - E_IN, 0, DIR);
-            for (int b = 0; b < nblk; b += 2) {
-                do_block(b, eb0, eb1);
-                if (b + 1 < nblk) do_block(b + 1, eb1, eb0);
+                d0 = n0; d1 = n1;
+                /* unconditional stores: inactive lanes store their +0.0 into padding; a non-fluid cell (MASKED) and a lane that
+                 * is not at the outgoing edge store into per-lane dummy slots (a predicated store becomes a divergent branch) */
+                double* ps = pd + DIR * u * (32 * SKB);
+                if (MASKED) { *(f0 ? ps : dummy) = d0; *(f1 ? ps + 1 : dummy + 1) = d1; }
+                else *reinterpret_cast<double2*>(ps) = make_double2(d0, d1);
+                st_v2_if(pub, u < UB - 1 ? pf + u * SKB : pl, d0, d1);
+                if (WITH_DOT) {                          /* inactive lanes hold +0.0, rr is zero in the padding: adding them is exact */
+                    if (DIR > 0) { acc += d0 * o.rr[0]; acc += d1 * o.rr[1]; }
+                    else         { acc += d1 * o.rr[1]; acc += d0 * o.rr[0]; }
+                }
+                /* every row of the finished tile is in registers (the loads are warp-wide instructions issued, in order,
+                 * before this arrive): hand the stage back to the loader warp */
+                if (u == UB - 1) mbar_arrive_if(lane0, done_bar);
             }
+            pd += DIR * UB * (32 * SKB);
+        };
+
+        /* prologue: the producer publishes from its block 3 on (macro-steps 24..); its macro-steps 24..30 (pair slots
+         * 25..31) are needed by nobody -- they are awaited and re-armed so that a ring slot is always armed when its turn
+         * comes */
+        if (in_base != nullptr) {
+            for (int i = 25; i <= 31; i++) {
+                double v0, v1;
+                for (unsigned spins = 0; spins < (1u << 22); spins++) {
+                    ld_volatile_v2(in_base + i * SKB, v0, v1);
+                    if (!is_sentinel_hi(v0) && !is_sentinel_hi(v1)) break;
+                }
+            }
+            if (lane0) {
+                double* q = const_cast<double*>(in_base);
+                for (int i = 25 * SKB; i < 32 * SKB; i++) q[i] = sentinel();
+            }
+            __syncwarp();
         }
-        if (out_ring) {
-            /* 8 more zero pairs: the consumer takes one slot per macro-step through its block nblk-4 */
+        mbar_wait_u32(full0, 0);
+        load_step(ops[0], ring_lane, 0);
+        edge_fetch(eA, 0);
+        auto one_block = [&](double (&ecur)[UB * SKB], double (&enxt)[UB * SKB], const int b) {
+            if ((b & 1) == 0) credit_wait(b * UB + 2 * UB - 1);
+            edge_fetch(enxt, b + 1);
+            edge_wait(ecur, b);
+            run_block(ecur, b);
+            if (credit_of_prev != nullptr && lane0) *credit_of_prev = (b + 1) * UB + 31;   /* producer macro-steps I have consumed */
+        };
+        for (int b = 0; b < nblk; b += 2) {
+            one_block(eA, eB, b);
+            if (trace && b == 0) tr_first = (long long)globaltimer_ns();
+            if (b + 1 < nblk) one_block(eB, eA, b + 1);
+        }
+        if (can_pub) {
+            /* 8 more zero pairs: the consumer takes 8 pairs per block through its block nblk-4 */
             credit_wait(nsteps + UB - 1);
             if (is_out) {
-                double* p = out_base + (nsteps & (SW_RB - 1)) * SKB;
-                for (int i = 0; i < UB * SKB; i++) p[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < UB; i++) st_v2(out_base + (size_t)((unsigned)(nsteps + 1 + i) & out_mask) * SKB, 0.0, 0.0);
             }
         }
         if (trace && lane == 0) {
             long long* tr = trace + (long long)k * 16;
             tr[0] = tr_enter; tr[1] = tr_first; tr[2] = 0; tr[3] = (long long)globaltimer_ns();
             tr[4] = 0; tr[5] = nblk; tr[6] = slot; tr[7] = (long long)get_smid();
-#ifdef IFL_SW_TRACE_WAITS
-            tr[2] = tw_nstarved * 1000000 + tw_nspins; tr[4] = tw_t4 - tr_first; tr[5] = tw_credit + tw_edge;
-            tr[8] = tw_op;
-#endif
         }
     }
     if (WITH_DOT && live && !loader) {
@@ -1918,7 +1643,7 @@ static inline int rearm_blocks(const SkewGeom& g) {
 #define IFL_TRY(call) do { if ((call) != 0) return -1; } while (0)
 
 int launch_build_precon(SolveCtx& c) {
-    k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
+    k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.inbox_f, c.inbox_b, c.inbox_len, c.sc);
     k_build_precon<<<wf_blocks(c.g), WF_WARPS * 32, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.precon,
                                                                   c.bnd_f, c.sc, c.mic_tau, c.mic_sigma, c.fl);
     /* the MIC(0) factor is built for the whole grid on every rank (a recurrence from strip 0); the packed products only
@@ -1934,7 +1659,7 @@ static size_t sweep_smem(bool two_streams) {
 }
 /* src == nullptr: in place on the current z generation */
 template <int DIR, bool WITH_DOT, bool MASKED, int FUSE>
-static void launch_sweep(SolveCtx& c, const double* src, const double* pack, const double* rr, double* bnd,
+static void launch_sweep(SolveCtx& c, const double* src, const double* pack, const double* rr, double* inbox,
                          int dot_mode, int check_done, long long* trace) {
     /* the opt-in to > 48 KB of dynamic shared memory is per device and per kernel instance */
     static unsigned long long attr_devices = 0ull;
@@ -1949,7 +1674,7 @@ static void launch_sweep(SolveCtx& c, const double* src, const double* pack, con
     }
     const int nown = c.g.s1 - c.g.s0;
     double* peer = nullptr;
-    if (c.comm) peer = DIR > 0 ? c.peer_bnd_f_next : c.peer_bnd_b_prev;
+    if (c.comm) peer = DIR > 0 ? c.peer_inbox_f_next : c.peer_inbox_b_prev;
     const int nblocks = (nown + SW_WARPS - 1) / SW_WARPS;
     int cl = SW_CL_MAX;
     while (cl > 1 && cl > nblocks) cl >>= 1;                       /* cluster of 8 blocks = 8 * SW_WARPS consecutive strips */
@@ -1962,8 +1687,8 @@ static void launch_sweep(SolveCtx& c, const double* src, const double* pack, con
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = cl; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_precon_sweep<DIR, WITH_DOT, MASKED, FUSE>, c.g, src, c.zb[0], c.zb[1], pack, rr, bnd, peer,
-                       c.strip_part, c.sc, dot_mode, check_done, trace, c.tolerance, c.rank_max,
+    cudaLaunchKernelEx(&cfg, k_precon_sweep<DIR, WITH_DOT, MASKED, FUSE>, c.g, src, c.zb[0], c.zb[1], pack, rr, inbox, peer,
+                       c.inbox_len, c.strip_part, c.sc, dot_mode, check_done, trace, c.tolerance, c.rank_max,
                        c.comm ? c.comm->rank : 0, single_gpu(c));
 }
 
@@ -1982,25 +1707,25 @@ static int enqueue_precon(SolveCtx& c, int fuse_r_update, int dot_mode, int chec
         fuse_r_update = 0;
     }
     if (fuse_r_update) {
-        if (!masked)                launch_sweep<1, false, false, 1>(c, c.r, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
-        else if (c.mask_vector_ops) launch_sweep<1, false, true, 2>(c, c.r, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
-        else                        launch_sweep<1, false, true, 1>(c, c.r, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
+        if (!masked)                launch_sweep<1, false, false, 1>(c, c.r, c.pack_f, nullptr, c.inbox_f, DOT_NONE, check_done, c.trace);
+        else if (c.mask_vector_ops) launch_sweep<1, false, true, 2>(c, c.r, c.pack_f, nullptr, c.inbox_f, DOT_NONE, check_done, c.trace);
+        else                        launch_sweep<1, false, true, 1>(c, c.r, c.pack_f, nullptr, c.inbox_f, DOT_NONE, check_done, c.trace);
         count(c);
         IFL_TRY(dist_max(c, 0));
     } else {
-        if (masked) launch_sweep<1, false, true, 0>(c, c.r, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
-        else        launch_sweep<1, false, false, 0>(c, c.r, c.pack_f, nullptr, c.bnd_f, DOT_NONE, check_done, c.trace);
+        if (masked) launch_sweep<1, false, true, 0>(c, c.r, c.pack_f, nullptr, c.inbox_f, DOT_NONE, check_done, c.trace);
+        else        launch_sweep<1, false, false, 0>(c, c.r, c.pack_f, nullptr, c.inbox_f, DOT_NONE, check_done, c.trace);
         count(c);
     }
     prof_mark(c, ps, 2);
     int fused_mode = c.sequential ? DOT_NONE : dot_mode;
     long long* tr2 = c.trace ? c.trace + 16 * c.g.nstrips : nullptr;
     if (dot_mode != DOT_NONE) {
-        if (masked) launch_sweep<-1, true, true, 0>(c, nullptr, c.pack_b, c.r, c.bnd_b, fused_mode, check_done, tr2);
-        else        launch_sweep<-1, true, false, 0>(c, nullptr, c.pack_b, c.r, c.bnd_b, fused_mode, check_done, tr2);
+        if (masked) launch_sweep<-1, true, true, 0>(c, nullptr, c.pack_b, c.r, c.inbox_b, fused_mode, check_done, tr2);
+        else        launch_sweep<-1, true, false, 0>(c, nullptr, c.pack_b, c.r, c.inbox_b, fused_mode, check_done, tr2);
     } else {
-        if (masked) launch_sweep<-1, false, true, 0>(c, nullptr, c.pack_b, nullptr, c.bnd_b, DOT_NONE, check_done, tr2);
-        else        launch_sweep<-1, false, false, 0>(c, nullptr, c.pack_b, nullptr, c.bnd_b, DOT_NONE, check_done, tr2);
+        if (masked) launch_sweep<-1, false, true, 0>(c, nullptr, c.pack_b, nullptr, c.inbox_b, DOT_NONE, check_done, tr2);
+        else        launch_sweep<-1, false, false, 0>(c, nullptr, c.pack_b, nullptr, c.inbox_b, DOT_NONE, check_done, tr2);
     }
     count(c);
     if (c.sequential && dot_mode != DOT_NONE) {
@@ -2013,7 +1738,7 @@ static int enqueue_precon(SolveCtx& c, int fuse_r_update, int dot_mode, int chec
 
 /* applyPreconditioner(z, r) on its own (IFL_STAGE_APPLY_PRECON, the wavefront trace) */
 int launch_apply_precon(SolveCtx& c, int as_in_loop) {
-    k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
+    k_sweep_rearm<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.inbox_f, c.inbox_b, c.inbox_len, c.sc);
     count(c);
     /* slab decomposition: no neighbour may store into an inbox row before its owner has re-armed it */
     if (!single_gpu(c)) IFL_TRY(comm_all_gather(*c.comm, c.rank_max + c.comm->rank, c.rank_max, sizeof(unsigned long long)));
@@ -2073,7 +1798,7 @@ static int dist_halo_rows(SolveCtx& c) {
 /* project() F3:590-602: p = 0; z = M^-1 r; s = z; maxError; sigma = z.r */
 int pcg_enqueue_init(SolveCtx& c) {
     cudaMemsetAsync(c.p_first, 0, sizeof(double) * (size_t)(c.g.s1 - c.g.s0) * (size_t)c.g.ss, c.stream);
-    k_solve_reset<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
+    k_solve_reset<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.inbox_f, c.inbox_b, c.inbox_len, c.sc);
     count(c);
     /* every rank's inboxes must be re-armed before any neighbour starts writing into them */
     if (!single_gpu(c)) IFL_TRY(comm_all_gather(*c.comm, c.rank_max + c.comm->rank, c.rank_max, sizeof(unsigned long long)));
@@ -2113,11 +1838,11 @@ int pcg_enqueue_iterations(SolveCtx& c, int n) {
         if (c.const_matrix)
             k_step_a<true><<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.zb[0], c.zb[1], c.sb[0], c.sb[1], c.p,
                                                             c.partials, c.strip_part, c.strip_ctr, c.sc, dm, mfl, single_gpu(c),
-                                                            c.const_scale, c.bnd_f, c.bnd_b);
+                                                            c.const_scale);
         else
             k_step_a<false><<<eg, EW_THREADS, 0, c.stream>>>(c.g, c.adiag, c.aplusx, c.aplusy, c.zb[0], c.zb[1], c.sb[0], c.sb[1], c.p,
                                                              c.partials, c.strip_part, c.strip_ctr, c.sc, dm, mfl, single_gpu(c),
-                                                             0.0, c.bnd_f, c.bnd_b);
+                                                             0.0);
         count(c);
         if (c.sequential) {
             k_dot_sequential<<<1, EW_THREADS, 0, c.stream>>>(c.g, c.zb[0], c.zb[1], nullptr, c.sb[0], c.sb[1], c.sc, DOT_ZS, 1, mfl);
@@ -2169,7 +1894,7 @@ int pcg_exchange_pressure_halo(SolveCtx& c) {
 }
 /* Gauss-Seidel project() F1:380: _p is warm-started, so only the control state is reset */
 void gs_enqueue_begin(SolveCtx& c) {
-    k_solve_reset<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.sc);
+    k_solve_reset<<<rearm_blocks(c.g), 256, 0, c.stream>>>(c.g, c.bnd_f, c.bnd_b, c.inbox_f, c.inbox_b, c.inbox_len, c.sc);
     count(c);
 }
 /* returns the number of iterations it has enqueued: `n`, or everything up to `limit` at once when the whole solve runs

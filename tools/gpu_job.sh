@@ -1,4 +1,4 @@
 cd /root/repo
-timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -4
-timeout 600 python bench.py --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline > gpurun_out/r2_b_n1_s2.json 2>gpurun_out/r2_b_n1_s2.err; python -c "
-import json; d=json.loads(open('gpurun_out/r2_b_n1_s2.json').read()); print(d['value'], d['ms_per_step'], d['config']['state_hash'], d['e2e']['value'], d['roofline']['traffic'])"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 300 python tools/trace_fused.py - 4096 2>&1 | grep "==" | tee gpurun_out/r2_trace12.log
+for sz in 16384 4096; do timeout 200 python tools/tune_pcg.py - $sz 40 2>&1 | tail -1; done | tee gpurun_out/r2_tune12.log
