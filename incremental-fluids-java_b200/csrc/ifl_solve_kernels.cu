@@ -732,6 +732,9 @@ __device__ __forceinline__ void st_v2(double* p, double a, double b) {          
 __device__ __forceinline__ void st_v2_if(bool p, double* addr, double a, double b) {
     asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.v2.f64 [%1], {%2, %3};\n}" ::"r"((unsigned)p), "l"(addr), "d"(a), "d"(b) : "memory");
 }
+__device__ __forceinline__ void st_int_if(bool p, volatile int* addr, int v) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.volatile.s32 [%1], %2;\n}" ::"r"((unsigned)p), "l"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void lds_cells(unsigned addr, double* out) {
     static_assert(SKB == 2, "one 16-byte shared-memory load per array and macro-step");
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(out[0]), "=d"(out[1]) : "r"(addr));
@@ -1045,6 +1048,7 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
         const bool can_pub = out_base != nullptr;
         volatile int* const credit_of_prev =
             in_ring ? cluster.map_shared_rank((int*)&s_credit[(cslot - 1) % SW_WARPS], (cslot - 1) / SW_WARPS) : nullptr;
+        const bool pub_credit = lane0 && credit_of_prev != nullptr;
         double* const dummy = &s_dummy[warp][lane][0];
         const int last_edge_block = nblk - 4;           /* the producer's last real macro-step is taken in this block */
 
@@ -1068,17 +1072,31 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
                 for (int i = 0; i < UB * SKB; i++) e[i] = 0.0;   /* no neighbour, or columns right / left of the grid */
             }
         };
+        /* A pair is stored with ONE 16-byte store, so it is visible as a whole: testing its first value is enough.  While
+         * values are missing, only the pair that is stored last is polled (one load per round trip); the others are
+         * re-read afterwards, because stores to different addresses need not become visible in order. */
         auto edge_wait = [&](double (&e)[UB * SKB], const int b) {
             if (in_base == nullptr || b > last_edge_block) return;
             for (unsigned spins = 0;; spins++) {
                 bool ok = true;
 #pragma unroll
-                for (int i = 0; i < UB * SKB; i++) ok = ok && !is_sentinel_hi(e[i]);
+                for (int i = 0; i < UB * SKB; i += SKB) ok = ok && !is_sentinel_hi(e[i]);
                 if (ok) break;
                 if (spins > (1u << 22)) {                  /* dead producer: give up instead of hanging the GPU */
 #pragma unroll
                     for (int i = 0; i < UB * SKB; i++) if (is_sentinel_hi(e[i])) e[i] = 0.0;
                     break;
+                }
+                const unsigned slot_last = ((unsigned)(b * UB + 32) & in_mask) + (unsigned)(UB - 1);
+                double l0, l1;
+                unsigned inner = 0;
+                if (in_ring) {
+                    const unsigned q = in_ring_addr + slot_last * (unsigned)(SKB * sizeof(double));
+                    do { asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(l0), "=d"(l1) : "r"(q) : "memory"); }
+                    while (is_sentinel_hi(l0) && ++inner < (1u << 20));
+                } else {
+                    const double* q = in_base + (size_t)slot_last * SKB;
+                    do { ld_volatile_v2(q, l0, l1); } while (is_sentinel_hi(l0) && ++inner < (1u << 20));
                 }
                 edge_fetch(e, b);
             }
@@ -1217,6 +1235,14 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
             }
             __syncwarp();
         }
+        if (in_base != nullptr && !in_ring && last_edge_block >= 1) {
+            /* a global inbox row costs an L2 round trip per poll: start one block later than necessary (wait for the last
+             * pair of block 1), so that from then on a block's pairs are already there when they are requested a block ahead */
+            const double* q = in_base + (size_t)(UB + 32 + UB - 1) * SKB;
+            double l0, l1;
+            unsigned spins = 0;
+            do { ld_volatile_v2(q, l0, l1); } while (is_sentinel_hi(l0) && ++spins < (1u << 22));
+        }
         mbar_wait_u32(full0, 0);
         load_step(ops[0], ring_lane, 0);
         edge_fetch(eA, 0);
@@ -1225,7 +1251,7 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
             edge_fetch(enxt, b + 1);
             edge_wait(ecur, b);
             run_block(ecur, b);
-            if (credit_of_prev != nullptr && lane0) *credit_of_prev = (b + 1) * UB + 31;   /* producer macro-steps I have consumed */
+            if (pub_credit) *credit_of_prev = (b + 1) * UB + 31;                            /* producer macro-steps I have consumed */
         };
         for (int b = 0; b < nblk; b += 2) {
             one_block(eA, eB, b);
