@@ -119,12 +119,15 @@ __device__ __forceinline__ double cubic_pulse(double x) {   /* F2:107 */
     x = jmin(jabsf(x), 1.0);
     return 1.0 - x * x * (3.0 - 2.0 * x);
 }
-__global__ void k_add_inflow(double* __restrict__ src, int w, int xlo, int xhi, int ylo, int yhi, int smooth,
+__global__ void k_add_inflow(double* __restrict__ src, int w, size_t total, int xlo, int xhi, int ylo, int yhi, int smooth,
                              double hx, double x0, double y0, double x1, double y1, double v) {
     int x = xlo + blockIdx.x * blockDim.x + threadIdx.x;
     int y = ylo + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= xhi || y >= yhi) return;
     size_t i = (size_t)x + (size_t)y * w;
+    /* the x range is clipped with _h (F1:209, kept): on a grid with w < h an index can run into the next row, like in the
+     * Java array, but never past the end of the buffer (where the reference throws ArrayIndexOutOfBoundsException) */
+    if (i >= total) return;
     double vi = v;
     if (smooth) {
         double lx = (2.0 * (x + 0.5) * hx - (x0 + x1)) / (x1 - x0);
@@ -154,7 +157,7 @@ void launch_add_inflow(cudaStream_t st, int variant, QGeom q, double* src, doubl
     if (xhi <= xlo || yhi <= ylo) return;
     dim3 block(32, 8);
     dim3 grid((xhi - xlo + 31) / 32, (yhi - ylo + 7) / 8);
-    k_add_inflow<<<grid, block, 0, st>>>(src, q.w, xlo, xhi, ylo, yhi, variant != IFL_F1_MATRIXLESS,
+    k_add_inflow<<<grid, block, 0, st>>>(src, q.w, (size_t)q.w * q.h, xlo, xhi, ylo, yhi, variant != IFL_F1_MATRIXLESS,
                                          hx, x0, y0, x1, y1, value);
 }
 

@@ -1,5 +1,11 @@
 cd /root/repo
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 300 python tools/trace_fused.py - 4096 2>&1 | grep "==" | tee gpurun_out/r2_trace14.log
-for sz in 16384 4096 1024; do timeout 200 python tools/tune_pcg.py - $sz 40 2>&1 | tail -1; done | tee gpurun_out/r2_tune14.log
-timeout 600 python -m pytest tests/test_parity_at_size_gpu.py -q -m gpu -x 2>&1 | tail -3
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
+( time timeout 900 python bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err ) 2>&1 | grep real
+head -c 300 gpurun_out/r2_bench_n1.json; echo; tail -3 gpurun_out/r2_bench_n1.err
+NCU="ncu --clock-control none"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-other-configs --no-hash"
+timeout 300 $CMD > gpurun_out/plain_c5.log 2>&1 && timeout 900 $NCU --metrics gpu__time_duration.sum -s 5600 -c 300 --csv --log-file gpurun_out/launches_c5_r02.csv $CMD > gpurun_out/ncu_c5.log 2>&1
+timeout 300 python tools/prof_target.py c5 1 12 > gpurun_out/plain_c5b.log 2>&1 && timeout 900 $NCU --set full --import-source on -k regex:"k_step_a|k_precon_sweep" -s 12 -c 3 -o gpurun_out/prof_pcg_c5_r02 python tools/prof_target.py c5 1 12 > gpurun_out/ncu_c5b.log 2>&1
+timeout 300 python tools/trace_fused.py - 16384 2>&1 | grep "==" | tee gpurun_out/r2_trace_final.log
+ls -la gpurun_out/prof_pcg_c5_r02.ncu-rep gpurun_out/launches_c5_r02.csv

@@ -8,7 +8,8 @@ from importlib import import_module
 if len(sys.argv) > 1 and sys.argv[1] != "-":
     import_module(ifl.FluidSolver.__module__.rsplit(".", 1)[0] + "._lib").LIB_PATH = os.path.abspath(sys.argv[1])
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
-g = ifl.FluidSolver(n, n, 0.1, variant=ifl.abi.F3_CONJUGATE_GRADIENTS, solver_limit=3)
+flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+g = ifl.FluidSolver(n, n, 0.1, variant=ifl.abi.F3_CONJUGATE_GRADIENTS, solver_limit=3, flags=flags)
 g.addInflow(0.45, 0.2, 0.15, 0.03, 1.0, 0.0, 3.0)
 g.update(0.005)
 for rep in range(3):
