@@ -666,6 +666,7 @@ static constexpr int SW_WARPS = IFL_SW_WARPS;       /* strips per block of the s
                                                      * grid only ever has ~ (w/SKB + 31) / 40 strips in flight at a time */
 static constexpr int SW_TILE = SW_U * 32 * SKB;     /* doubles per array per block (2 KB) */
 static constexpr int SW_PACK = 3 * SW_TILE;         /* packed coefficient block: 3 arrays (6 KB) */
+static constexpr int SW_THREADS = (2 * SW_WARPS + 1) * 32;   /* strip warps, their loader warps, one edge-mover warp */
 static constexpr int SW_FG = 8;                     /* macro-steps per block of the sweep loop (edge-feed group, hand-over granularity) */
 static_assert(SW_FG % SW_U == 0 && SW_FG % 2 == 0, "a block is a whole, even number of staged tiles");
 
@@ -797,7 +798,7 @@ __device__ __forceinline__ unsigned pin_u32(unsigned v) { asm volatile("mov.u32 
  * If the solve turns out to have converged the sweep's output is simply not used (the reference returns before
  * applyPreconditioner; z is dead until the next solve overwrites it). */
 template <int DIR, bool WITH_DOT, bool MASKED, int FUSE>
-__global__ void __launch_bounds__(2 * SW_WARPS * 32)
+__global__ void __launch_bounds__(SW_THREADS)
 k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, const double* __restrict__ pack,
                const double* __restrict__ rr, double* inbox, double* inbox_peer, int inbox_len, double* strip_part,
                SolveScalars* sc, int dot_mode, int check_done, long long* trace,
@@ -819,6 +820,7 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
     extern __shared__ __align__(128) unsigned char wf_smem[];
     __shared__ __align__(16) double s_inbox[SW_WARPS][SW_RB * SKB];   /* edge-row rings of this block's strips */
     __shared__ volatile int s_credit[SW_WARPS];          /* macro-steps of MINE the strip after me has consumed */
+    __shared__ volatile int s_mcredit;                   /* the same, for the edge mover of this block's strip 0 */
     __shared__ __align__(16) double s_dummy[SW_WARPS][32][SKB];           /* where a non-fluid cell (MASKED) stores */
     __shared__ int s_ticket;
     cg::cluster_group cluster = cg::this_cluster();
@@ -829,15 +831,17 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
     const double* const src = src_fixed != nullptr ? src_fixed : dst;
     const long long tr_enter = trace ? (long long)globaltimer_ns() : 0;
     const int lane = threadIdx.x & 31;
-    const bool loader = threadIdx.x >= SW_WARPS * 32;
-    const int warp = (threadIdx.x >> 5) - (loader ? SW_WARPS : 0);    /* strip warp index (own, or the one served) */
+    const bool mover = threadIdx.x >= 2 * SW_WARPS * 32;              /* last warp: feeds strip warp 0 from its global inbox row */
+    const bool loader = !mover && threadIdx.x >= SW_WARPS * 32;
+    const int warp = mover ? 0 : (threadIdx.x >> 5) - (loader ? SW_WARPS : 0);    /* strip warp index (own, or the one served) */
     /* per-strip operand ring: S stages of [src tile | coefficient pack | rr tile]; then per strip S full + S empty mbarriers */
     double* ring = reinterpret_cast<double*>(wf_smem) + (size_t)warp * S * STAGE;
     unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(
         wf_smem + (size_t)SW_WARPS * S * STAGE * sizeof(double)) + warp * 3 * S;
     unsigned long long* bar_empty = bar_full + S;
     unsigned long long* bar_ready = bar_empty + S;       /* FUSE: the loader warp has updated r in the staged tile */
-    if (!loader) {
+    if (mover && lane == 0) s_mcredit = 0;
+    if (!loader && !mover) {
         s_dummy[warp][lane][0] = 0.0; s_dummy[warp][lane][SKB - 1] = 0.0;
         for (int i = lane; i < SW_RB * SKB; i += 32) s_inbox[warp][i] = sentinel();
         if (lane == 0) {
@@ -1020,6 +1024,32 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
                 }
             }
         }
+    } else if (live && mover) {
+        /* The first strip of a cluster (or of a GPU's slab) has its predecessor in another cluster: that one stores its edge
+         * pairs into this strip's row of global memory.  This warp moves them into the strip's shared-memory ring, so that
+         * every strip warp consumes its edge values the same way, from shared memory: lane i polls pair slots i, i+32, ...
+         * (one L2 round trip per poll, 32 polls in flight), hands a pair over as soon as it is there and the ring has room
+         * (the strip warp's credit), and re-arms the slot in the row for the next sweep. */
+        const bool has_prev = DIR > 0 ? (k > 0) : (k < g.nstrips - 1);
+        if (crank == 0 && has_prev) {
+            const int last = nblk * UB + 7;                          /* the strip consumes slots 25 .. nsteps + 7 */
+            double* const row = inbox + (long long)k * inbox_len;
+            const unsigned ring_addr = smem_u32(&s_inbox[0][0]);
+            const double sv = sentinel();
+            int slot = 25 + lane;
+            for (unsigned spins = 0; spins < (1u << 24) && __any_sync(0xffffffffu, slot <= last); spins++) {
+                if (slot <= last) {
+                    double v0, v1;
+                    ld_volatile_v2(row + (size_t)slot * SKB, v0, v1);
+                    if (!is_sentinel_hi(v0) && slot - s_mcredit <= SW_RB) {
+                        asm volatile("st.volatile.shared.v2.f64 [%0], {%1, %2};"
+                                     ::"r"(ring_addr + ((unsigned)slot & (unsigned)(SW_RB - 1)) * (unsigned)(SKB * sizeof(double))), "d"(v0), "d"(v1) : "memory");
+                        st_v2(row + (size_t)slot * SKB, sv, sv);
+                        slot += 32;
+                    }
+                }
+            }
+        }
     } else if (live) {
         const int nsteps = nblk * UB;                                     /* macro-steps of a strip (>= column blocks + 31) */
         const int tfirst = DIR > 0 ? 0 : nsteps - 1;
@@ -1029,10 +1059,9 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
         const bool is_in = lane == E_IN;
         const bool lane0 = lane == 0;
         /* incoming edge values: my shared-memory ring if my predecessor runs in this cluster, else my global inbox row */
-        const bool in_ring = cslot > 0;
-        const double* const in_base = !has_prev ? nullptr : (in_ring ? &s_inbox[warp][0] : inbox + (long long)k * inbox_len);
-        const unsigned in_mask = in_ring ? (unsigned)(SW_RB - 1) : 0xffffffffu;
-        const unsigned in_ring_addr = in_ring ? smem_u32(&s_inbox[warp][0]) : 0u;
+        const double* const in_base = !has_prev ? nullptr : &s_inbox[warp][0];
+        const unsigned in_mask = (unsigned)(SW_RB - 1);
+        const unsigned in_ring_addr = smem_u32(&s_inbox[warp][0]);
         /* outgoing edge values: the next strip's ring (mapped shared memory of its block), or its global inbox row --
          * in the neighbour GPU's memory when the next strip belongs to the next rank */
         const bool out_ring = (cslot < csize * SW_WARPS - 1) && (slot + 1 < nown);
@@ -1046,67 +1075,18 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
             out_base = (to_peer ? inbox_peer : inbox) + (long long)(k + DIR) * inbox_len;
         }
         const bool can_pub = out_base != nullptr;
-        volatile int* const credit_of_prev =
-            in_ring ? cluster.map_shared_rank((int*)&s_credit[(cslot - 1) % SW_WARPS], (cslot - 1) / SW_WARPS) : nullptr;
+        volatile int* const credit_of_prev = !has_prev ? nullptr :
+            (cslot > 0 ? cluster.map_shared_rank((int*)&s_credit[(cslot - 1) % SW_WARPS], (cslot - 1) / SW_WARPS) : (int*)&s_mcredit);
         const bool pub_credit = lane0 && credit_of_prev != nullptr;
         double* const dummy = &s_dummy[warp][lane][0];
         const int last_edge_block = nblk - 4;           /* the producer's last real macro-step is taken in this block */
 
-        /* edge values of block b: consumer macro-steps 8b .. 8b+7 = producer macro-steps 8b+31 .. 8b+38 = pair slots
-         * 8b+32 .. 8b+39.  Every lane reads the same addresses (a broadcast), so the flag-in-data test is warp uniform. */
-        auto edge_fetch = [&](double (&e)[UB * SKB], const int b) {
-            if (in_base != nullptr && b <= last_edge_block) {
-                const unsigned slot0 = (unsigned)(b * UB + 32) & in_mask;
-                if (in_ring) {                              /* warp uniform */
-                    const unsigned q = in_ring_addr + slot0 * (unsigned)(SKB * sizeof(double));
-#pragma unroll
-                    for (int i = 0; i < UB * SKB; i += 2)
-                        asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e[i]), "=d"(e[i + 1]) : "r"(q + 8u * i) : "memory");
-                } else {
-                    const double* q = in_base + (size_t)slot0 * SKB;
-#pragma unroll
-                    for (int i = 0; i < UB * SKB; i += 2) ld_volatile_v2(q + i, e[i], e[i + 1]);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < UB * SKB; i++) e[i] = 0.0;   /* no neighbour, or columns right / left of the grid */
-            }
-        };
-        /* A pair is stored with ONE 16-byte store, so it is visible as a whole: testing its first value is enough.  While
-         * values are missing, only the pair that is stored last is polled (one load per round trip); the others are
-         * re-read afterwards, because stores to different addresses need not become visible in order. */
-        auto edge_wait = [&](double (&e)[UB * SKB], const int b) {
-            if (in_base == nullptr || b > last_edge_block) return;
-            for (unsigned spins = 0;; spins++) {
-                bool ok = true;
-#pragma unroll
-                for (int i = 0; i < UB * SKB; i += SKB) ok = ok && !is_sentinel_hi(e[i]);
-                if (ok) break;
-                if (spins > (1u << 22)) {                  /* dead producer: give up instead of hanging the GPU */
-#pragma unroll
-                    for (int i = 0; i < UB * SKB; i++) if (is_sentinel_hi(e[i])) e[i] = 0.0;
-                    break;
-                }
-                const unsigned slot_last = ((unsigned)(b * UB + 32) & in_mask) + (unsigned)(UB - 1);
-                double l0, l1;
-                unsigned inner = 0;
-                if (in_ring) {
-                    const unsigned q = in_ring_addr + slot_last * (unsigned)(SKB * sizeof(double));
-                    do { asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(l0), "=d"(l1) : "r"(q) : "memory"); }
-                    while (is_sentinel_hi(l0) && ++inner < (1u << 20));
-                } else {
-                    const double* q = in_base + (size_t)slot_last * SKB;
-                    do { ld_volatile_v2(q, l0, l1); } while (is_sentinel_hi(l0) && ++inner < (1u << 20));
-                }
-                edge_fetch(e, b);
-            }
-            if (lane0) {                                    /* re-arm what was taken */
-                double* q = const_cast<double*>(in_base) + (size_t)((unsigned)(b * UB + 32) & in_mask) * SKB;
-                const double sv = sentinel();
-#pragma unroll
-                for (int i = 0; i < UB * SKB; i += 2) st_v2(q + i, sv, sv);
-            }
-        };
+        /* Incoming edge values: consumer macro-step c needs the pair of producer macro-step c + 31 = pair slot c + 32 of
+         * the ring in shared memory (written by the strip before, or by the edge mover).  Every lane reads the same
+         * addresses (a broadcast), so the flag-in-data test is warp uniform.  The 8 pairs of a block are taken at its
+         * start; while one is missing the whole fetch is repeated, so a strip that has caught up with its producer
+         * advances block by block with it, 39 macro-steps behind.  (A pair is stored with ONE 16-byte store, so testing
+         * its first value is enough.) */
         /* credit: the last macro-step of the next two blocks must not lap the consumer's ring */
         auto credit_wait = [&](const int last_step) {
             if (!out_ring) return;
@@ -1139,15 +1119,18 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
         for (int i = 0; i < 2; i++)
 #pragma unroll
             for (int j = 0; j < SKB; j++) { ops[i].a[j] = 0.0; ops[i].cx[j] = 0.0; ops[i].cy[j] = 0.0; ops[i].pr[j] = 0.0; ops[i].rr[j] = 0.0; }
-        double eA[UB * SKB], eB[UB * SKB];
+        double e[UB][SKB];                                /* incoming edge pairs, indexed by macro-step & 7 */
+#pragma unroll
+        for (int i = 0; i < UB; i++) { e[i][0] = 0.0; e[i][1] = 0.0; }
         long long tr_first = 0;
 
         /* One block = one staged tile = 8 macro-steps, fully unrolled: the recurrence, two shuffles, the operand loads of the
          * next macro-step (from the next tile at the last one, which is awaited first; the loader provides one tile more
          * than the strip has) and two stores per macro-step.  The edge lane's pairs go to slots s0+1 .. s0+8 of the next
-         * strip's inbox: the first seven are consecutive (`pf`), only the last one can wrap around a ring (`pl`); every
-         * other lane stores into its own dummy slots. */
-        auto run_block = [&](const double (&e)[UB * SKB], const int b) {
+         * strip's inbox: the first seven are consecutive (`pf`), only the last one can wrap around a ring (`pl`).
+         * EDGE = false: no incoming edge (first strip; columns right / left of the grid). */
+        auto run_block = [&](auto edge_c, const int b) {
+            constexpr bool EDGE = decltype(edge_c)::value;
             const int s0 = b * UB;
             const bool pub = is_out && can_pub && b >= 3;       /* only the lane at the outgoing edge stores (predicated) */
             double* pf = dummy;
@@ -1158,6 +1141,23 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
             }
             const unsigned tile = ring_lane + (unsigned)(st * STAGE * (int)sizeof(double));
             unsigned done_bar = 0, tnext = tile;
+            if (EDGE) {
+                const unsigned q = in_ring_addr + ((unsigned)(s0 + 32) & in_mask) * (unsigned)(SKB * sizeof(double));
+                for (unsigned spins = 0;; spins++) {
+                    bool ok = true;
+#pragma unroll
+                    for (int i = 0; i < UB; i++) {
+                        asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e[i][0]), "=d"(e[i][1]) : "r"(q + 16u * i) : "memory");
+                        ok = ok && !is_sentinel_hi(e[i][0]);
+                    }
+                    if (ok) break;
+                    if (spins > (1u << 22)) {                  /* dead producer: give up instead of hanging the GPU */
+#pragma unroll
+                        for (int i = 0; i < UB; i++) if (is_sentinel_hi(e[i][0])) { e[i][0] = 0.0; e[i][1] = 0.0; }
+                        break;
+                    }
+                }
+            }
 #pragma unroll
             for (int u = 0; u < UB; u++) {
                 /* the upper neighbours: shuffled out of the adjacent lane as soon as it had them (below), i.e. half a
@@ -1173,7 +1173,7 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
                 }
                 load_step(ops[(u + 1) & 1], tnext, (u + 1) % U);
                 const Ops& o = ops[u & 1];
-                if (is_in) { up0 = e[u * SKB]; up1 = e[u * SKB + 1]; }
+                if (is_in) { up0 = EDGE ? e[u][0] : 0.0; up1 = EDGE ? e[u][1] : 0.0; }
                 double n0, n1;
                 bool f0 = true, f1 = true;
                 if (DIR > 0) {
@@ -1201,8 +1201,8 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
                     sh0 = __shfl_down_sync(0xffffffffu, n0, 1);
                 }
                 d0 = n0; d1 = n1;
-                /* unconditional stores: inactive lanes store their +0.0 into padding; a non-fluid cell (MASKED) and a lane that
-                 * is not at the outgoing edge store into per-lane dummy slots (a predicated store becomes a divergent branch) */
+                /* unconditional stores: inactive lanes store their +0.0 into padding; a non-fluid cell (MASKED) stores into
+                 * a per-lane dummy slot (a predicated store becomes a divergent branch) */
                 double* ps = pd + DIR * u * (32 * SKB);
                 if (MASKED) { *(f0 ? ps : dummy) = d0; *(f1 ? ps + 1 : dummy + 1) = d1; }
                 else *reinterpret_cast<double2*>(ps) = make_double2(d0, d1);
@@ -1235,28 +1235,27 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
             }
             __syncwarp();
         }
-        if (in_base != nullptr && !in_ring && last_edge_block >= 1) {
-            /* a global inbox row costs an L2 round trip per poll: start one block later than necessary (wait for the last
-             * pair of block 1), so that from then on a block's pairs are already there when they are requested a block ahead */
-            const double* q = in_base + (size_t)(UB + 32 + UB - 1) * SKB;
-            double l0, l1;
-            unsigned spins = 0;
-            do { ld_volatile_v2(q, l0, l1); } while (is_sentinel_hi(l0) && ++spins < (1u << 22));
-        }
         mbar_wait_u32(full0, 0);
         load_step(ops[0], ring_lane, 0);
-        edge_fetch(eA, 0);
-        auto one_block = [&](double (&ecur)[UB * SKB], double (&enxt)[UB * SKB], const int b) {
+        /* the blocks that take edge values: 0 .. last_edge_block (the producer's last real macro-step is in the last one);
+         * after each, lanes 0..7 re-arm its 8 slots with one store and the credit goes back to the producer */
+        int b_rest = 0;
+        if (in_base != nullptr) {
+            const double sv = sentinel();
+            for (int b = 0; b <= last_edge_block; b++) {
+                if ((b & 1) == 0) credit_wait(b * UB + 2 * UB - 1);
+                run_block(std::true_type(), b);
+                if (lane < UB) st_v2(const_cast<double*>(in_base) + (size_t)(((unsigned)(b * UB + 32) & in_mask) + (unsigned)lane) * SKB, sv, sv);
+                __syncwarp();
+                if (pub_credit) *credit_of_prev = (b + 1) * UB + 31;                        /* producer macro-steps I have consumed */
+                if (trace && b == 0) tr_first = (long long)globaltimer_ns();
+            }
+            b_rest = last_edge_block + 1;
+        }
+        for (int b = b_rest; b < nblk; b++) {
             if ((b & 1) == 0) credit_wait(b * UB + 2 * UB - 1);
-            edge_fetch(enxt, b + 1);
-            edge_wait(ecur, b);
-            run_block(ecur, b);
-            if (pub_credit) *credit_of_prev = (b + 1) * UB + 31;                            /* producer macro-steps I have consumed */
-        };
-        for (int b = 0; b < nblk; b += 2) {
-            one_block(eA, eB, b);
+            run_block(std::false_type(), b);
             if (trace && b == 0) tr_first = (long long)globaltimer_ns();
-            if (b + 1 < nblk) one_block(eB, eA, b + 1);
         }
         if (can_pub) {
             /* 8 more zero pairs: the consumer takes 8 pairs per block through its block nblk-4 */
@@ -1272,7 +1271,7 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
             tr[4] = 0; tr[5] = nblk; tr[6] = slot; tr[7] = (long long)get_smid();
         }
     }
-    if (WITH_DOT && live && !loader) {
+    if (WITH_DOT && live && !loader && !mover) {
         double ws = warp_sum(acc);
         if (lane == 0) {
             strip_part[k] = ws;
@@ -1706,7 +1705,7 @@ static void launch_sweep(SolveCtx& c, const double* src, const double* pack, con
     while (cl > 1 && cl > nblocks) cl >>= 1;                       /* cluster of 8 blocks = 8 * SW_WARPS consecutive strips */
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(((nblocks + cl - 1) / cl) * cl);
-    cfg.blockDim = dim3(2 * SW_WARPS * 32);                        /* strip warps + loader warps */
+    cfg.blockDim = dim3(SW_THREADS);                               /* strip warps + loader warps + edge mover */
     cfg.dynamicSmemBytes = sweep_smem(WITH_DOT || FUSE);
     cfg.stream = c.stream;
     cudaLaunchAttribute attr;

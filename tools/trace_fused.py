@@ -24,6 +24,9 @@ for sw, name in ((0, "forward (fused r update)"), (1, "backward (fused dot)")):
     dur = end - start
     print(f"== {name}: total {end.max():.1f} us; strip-to-strip lag median {np.median(lag):.2f} us (sum {lag.sum():.0f}); strip duration "
           f"first {dur[0]:.0f} median {np.median(dur):.0f} last {dur[-1]:.0f} us")
+    print("   durations of strips 0..39 (us):", " ".join(f"{d:.0f}" for d in dur[:40]))
+    print("   start lags of strips 1..40 (us):", " ".join(f"{d:.1f}" for d in lag[:40]))
+    print("   end lags of strips 1..40 (us):", " ".join(f"{d:.1f}" for d in np.diff(end)[:40]))
     print(f"   strip warp, median clocks->us: waiting operand tiles {np.median(t[:,8])/CLK/1e3:.1f}, credit+edge {np.median(t[:,5])/CLK/1e3:.1f}; "
           f"starved macro-steps {np.median(t[:,2]//1000000):.0f}")
     if t[:, 12].max() > 0:
