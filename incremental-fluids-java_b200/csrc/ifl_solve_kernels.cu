@@ -813,6 +813,9 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
 #ifndef IFL_SW_LAG
 #define IFL_SW_LAG 2
 #endif
+#ifndef IFL_SW_G
+#define IFL_SW_G 8                                                     /* edge pairs taken at once (divides 8) */
+#endif
     constexpr int LAG = IFL_SW_LAG;                                   /* FUSE: tiles between a bulk copy and its r update (< S - 1) */
     static_assert(LAG < SW_STAGES - 1, "the strip warp needs tile b+1 before it releases tile b");
     constexpr int E_IN = DIR > 0 ? 0 : 31;
@@ -1141,28 +1144,30 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
             }
             const unsigned tile = ring_lane + (unsigned)(st * STAGE * (int)sizeof(double));
             unsigned done_bar = 0, tnext = tile;
-            if (EDGE) {
+            /* the pairs of `G` macro-steps at once (slots s0+32+u0 ..); while one is missing the fetch is repeated */
+            auto edge_take = [&](const int u0) {
                 const unsigned q = in_ring_addr + ((unsigned)(s0 + 32) & in_mask) * (unsigned)(SKB * sizeof(double));
                 for (unsigned spins = 0;; spins++) {
                     bool ok = true;
 #pragma unroll
-                    for (int i = 0; i < UB; i++) {
+                    for (int i = u0; i < u0 + IFL_SW_G; i++) {
                         asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e[i][0]), "=d"(e[i][1]) : "r"(q + 16u * i) : "memory");
                         ok = ok && !is_sentinel_hi(e[i][0]);
                     }
                     if (ok) break;
                     if (spins > (1u << 22)) {                  /* dead producer: give up instead of hanging the GPU */
 #pragma unroll
-                        for (int i = 0; i < UB; i++) if (is_sentinel_hi(e[i][0])) { e[i][0] = 0.0; e[i][1] = 0.0; }
+                        for (int i = u0; i < u0 + IFL_SW_G; i++) if (is_sentinel_hi(e[i][0])) { e[i][0] = 0.0; e[i][1] = 0.0; }
                         break;
                     }
                 }
-            }
+            };
 #pragma unroll
             for (int u = 0; u < UB; u++) {
                 /* the upper neighbours: shuffled out of the adjacent lane as soon as it had them (below), i.e. half a
                  * macro-step / a whole macro-step before they are needed */
                 double up0 = sh0, up1 = sh1;
+                if (EDGE && u % IFL_SW_G == 0) edge_take(u);
                 if (u == UB - 1) {
                     done_bar = empty0 + 8u * (unsigned)st;
                     const bool wrap = st == S - 1;

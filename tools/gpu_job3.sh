@@ -1,7 +1,9 @@
 cd /root/repo
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_parity_at_size_gpu.py -q -x -k "f3 or f4" 2>&1 | tail -3
-timeout 300 python tools/tune_pcg.py - 16384 12 2>&1 | tail -4
-timeout 300 python tools/trace_fused.py - 16384 2>&1 | grep -v "^   strip warp\|loader warp" | tee gpurun_out/r2_trace_mover.log | cut -c1-330
-timeout 300 python tools/tune_pcg.py - 4096 40 2>&1 | tail -2
-timeout 300 python tools/tune_pcg.py - 1024 100 2>&1 | tail -2
+timeout 600 python -m pytest tests/test_parity_at_size_gpu.py -q -x -k "f3 or f4" 2>&1 | tail -2
+for lib in - tools/_variants/lib_g2.so tools/_variants/lib_g8.so; do
+timeout 300 python tools/tune_pcg.py $lib 16384 12 2>&1 | tail -1
+timeout 300 python tools/tune_pcg.py $lib 4096 40 2>&1 | tail -1
+timeout 300 python tools/tune_pcg.py $lib 1024 100 2>&1 | tail -1
+done
+timeout 300 python tools/trace_fused.py - 16384 2>&1 | grep "==" 
