@@ -379,8 +379,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    if world > 1 and name != "c5":
-        raise SystemExit("only configs[4] (c5) is slab-decomposed; run the other workloads on one GPU")
+    if world > 1 and name not in ("c2", "c3", "c5"):
+        raise SystemExit("several GPUs: the MIC(0)-PCG workloads c2, c5 (F3: slab decomposition) and c3 (F7: slab-decomposed "
+                         "solver loops, every other stage repeated by every rank); c1 (Gauss-Seidel) and c4 (particles) run on one GPU")
+    # F4-F7 on several GPUs: every rank holds the whole state, so a host that owns the state writes whole fields on every rank
+    replicated = world > 1 and name == "c3"
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -454,7 +457,7 @@ def main():
         host = {}
         for f in wl["fields"]:
             nr, nc = shapes[f]
-            lo, hi = (0, nr) if world == 1 else (row0, row1 + (1 if (f == "v" and rank == world - 1) else 0))
+            lo, hi = (0, nr) if (world == 1 or replicated) else (row0, row1 + (1 if (f == "v" and rank == world - 1) else 0))
             host[f] = (torch.zeros((hi - lo) * nc, dtype=torch.float64).pin_memory(), lo, hi - lo)
             if f == "t":
                 host[f][0].fill_(294.0)
@@ -467,7 +470,7 @@ def main():
         def e2e_step():
             nonlocal hp
             for f, (t, lo, nr) in host.items():                       # H2D from pinned host memory
-                if world == 1:
+                if world == 1 or replicated:
                     g2.write_field(f, t.numpy())
                 else:
                     g2.write_field_rows(f, lo, nr, t.numpy())
@@ -477,7 +480,7 @@ def main():
                 g2.add_inflow(*wl["inflow"])
             g2.update(wl["dt"], want_status=False)
             for f, (t, lo, nr) in host.items():                       # D2H result
-                if world == 1:
+                if world == 1 or replicated:
                     g2.read_field(f, t.numpy())
                 else:
                     g2.read_field_rows(f, lo, nr, t.numpy())
@@ -553,6 +556,8 @@ def main():
                              f"of this grid is {10 * 8 * W * H / 2**30:.1f} GiB (L2 is 126 MB)",
                        "state_hash": shash,
                        "multi_gpu": "single GPU" if world == 1 else
+                       (f"solver loops (heat and pressure MIC(0)-PCG) slab-decomposed over {world} ranks; every rank holds the "
+                        "whole state and repeats the other stages; the strips of p are gathered after a solve") if replicated else
                        f"grid slab-decomposed over {world} ranks: every rank computes only its rows (advection with a wide "
                        "halo sized from the CFL reduction, RHS, PCG, applyPressure); strip hand-over of the triangular "
                        "sweeps by peer stores over NVLink, row halos by ncclSend/Recv, scalars by grouped ncclBroadcast"},

@@ -199,7 +199,12 @@ int ifl_default_config(ifl_config* cfg, int32_t variant, int32_t w, int32_t h);
  * ifl_config.comm_id together with its rank / world_size.  One process per GPU.  Every rank computes only the rows it
  * owns (ifl_slab_rows): RHS, PCG, applyPressure and the semi-Lagrangian advection, whose halo of
  * ceil(dt * max|v| / hx) + 4 rows is sized every step from a CFL reduction over all ranks (cf. maxTimestep F1:309) and
- * exchanged with ncclSend/ncclRecv.  Implemented for variant 3. */
+ * exchanged with ncclSend/ncclRecv.  That is variant 3.
+ * Variants 4-7 (solid bodies, heat, variable density) on several GPUs: every rank holds the whole state and repeats
+ * every stage of update() except the solver loops (heat and pressure MIC(0)-PCG, >= 98 % of such a step), which run on
+ * the rank's strips exactly like variant 3's; the strips of p are gathered on every rank after a solve.  Whole-field
+ * reads and writes stay valid on every rank (a host that changes a field writes it on every rank); z and s hold only
+ * the rank's strips.  Variants 1, 2 (Gauss-Seidel) and 8 (particles) are single-GPU. */
 int ifl_comm_unique_id(uint8_t out[128]);
 
 /* new FluidSolver(...)  -- F1:262 F3:339 F4:594 F6:763 F7:769 F8:858 */

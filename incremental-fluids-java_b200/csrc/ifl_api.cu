@@ -90,6 +90,9 @@ static bool has_solids(const ifl_solver* s) { return s->cfg.variant >= IFL_F4_SO
 static bool has_heat(const ifl_solver* s) { return s->cfg.variant >= IFL_F6_HEAT; }
 static bool has_vardens(const ifl_solver* s) { return s->cfg.variant >= IFL_F7_VARIABLE_DENSITY; }
 static bool is_flip(const ifl_solver* s) { return s->cfg.variant == IFL_F8_FLIP; }
+/* several GPUs, F4-F7: every rank holds the whole state and repeats every stage except the solver loop, which runs on the
+ * rank's strips (the MIC(0)-PCG iterations are >= 98 % of such a step); F3 instead partitions the fields themselves */
+static bool replicated_stages(const ifl_solver* s) { return s->cfg.world_size > 1 && has_solids(s) && !is_flip(s); }
 
 extern "C" {
 
@@ -244,11 +247,15 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
      * Slab decomposition: the vectors only the solver loop touches (r p z s, both generations) and the packed sweep
      * coefficients hold this rank's strips plus one halo strip on either side; they are addressed with the GLOBAL strip
      * index through a base pointer shifted by -s0 strips.  The matrix and the MIC(0) factor stay whole-grid: the factor
-     * is a recurrence from strip 0 that every rank repeats for itself (its inputs depend on the grid position only). */
+     * is a recurrence from strip 0 that every rank repeats for itself (its inputs depend on the grid position only).
+     * Variants with solid bodies (F4-F7) on several GPUs keep every field and vector whole on every rank: all stages but
+     * the solver loop are repeated by every rank (replicated_stages()), so r and p must be whole-grid. */
     const size_t guard = (size_t)g.ss;
     const size_t per = (size_t)g.total + 2 * guard;
     const int nown = g.s1 - g.s0;
-    const size_t per_slab = (size_t)(nown + 2) * g.ss;
+    const bool slab_local = world > 1 && cfg->variant == IFL_F3_CONJUGATE_GRADIENTS;
+    const int strip_shift = slab_local ? g.s0 : 0;
+    const size_t per_slab = slab_local ? (size_t)(nown + 2) * g.ss : per;
     const int nfull = 4, nslab = 6;
     s->slab_bytes = sizeof(double) * (per * nfull + per_slab * nslab);
     CU(cudaMalloc(&s->skew_block, s->slab_bytes));
@@ -257,8 +264,8 @@ static int create_impl(const ifl_config* cfg, ifl_solver* s) {
     for (int i = 0; i < nfull; i++) *full_vecs[i] = s->skew_block + per * i + guard;
     double** slab_vecs[nslab] = {&s->sx.r, &s->sx.p, &s->sx.zb[0], &s->sx.zb[1], &s->sx.sb[0], &s->sx.sb[1]};
     double* slab0 = s->skew_block + per * nfull;
-    for (int i = 0; i < nslab; i++) *slab_vecs[i] = slab0 + per_slab * i + (long long)(1 - g.s0) * g.ss;
-    s->sx.p_first = slab0 + per_slab * 1 + g.ss;            /* this rank's strips of p (what a solve starts by clearing) */
+    for (int i = 0; i < nslab; i++) *slab_vecs[i] = slab0 + per_slab * i + (long long)(1 - strip_shift) * g.ss;
+    s->sx.p_first = s->sx.p + (long long)g.s0 * g.ss;       /* this rank's strips of p (what a solve starts by clearing) */
     const size_t pstrip = (size_t)g.tl * 32 * IFL_SKB * 3;
     const size_t npack = (size_t)nown * pstrip;
     CU(cudaMalloc(&s->pack_alloc, sizeof(double) * npack * 2));
@@ -348,8 +355,9 @@ int ifl_create(const ifl_config* cfg, ifl_solver** out) {
             INVALID("w*h*particles_max_per_cell must fit a 32-bit int (F8:1549)");
     }
     if (cfg->world_size > 1) {
-        if (cfg->variant != IFL_F3_CONJUGATE_GRADIENTS) {
-            snprintf(g_err, sizeof g_err, "slab decomposition is implemented for variant 3 (MIC(0)-PCG), not for variant %d", cfg->variant);
+        if (cfg->variant < IFL_F3_CONJUGATE_GRADIENTS || cfg->variant > IFL_F7_VARIABLE_DENSITY) {
+            snprintf(g_err, sizeof g_err, "several GPUs: implemented for the MIC(0)-PCG variants 3 (slab decomposition) and 4-7 "
+                     "(slab-decomposed solver loop), not for variant %d", cfg->variant);
             return IFL_ERR_UNSUPPORTED;
         }
         if (cfg->flags & IFL_FLAG_SEQUENTIAL_REDUCTIONS) INVALID("IFL_FLAG_SEQUENTIAL_REDUCTIONS is single-GPU only");
@@ -483,6 +491,10 @@ static int stage_project(ifl_solver* s, double timestep) {
     if (rc) return rc;
     if (uses_pcg(s)) COMM(pcg_enqueue_finish(c, s->cfg.solver_limit));
     else gs_enqueue_finish(c, s->cfg.solver_limit);
+    /* F4-F7 on several GPUs: every rank solved for its strips of p; the stages that follow (applyPressure, T <- p) are
+     * repeated by every rank on the whole grid, so every rank needs every strip (strips are contiguous in the skewed
+     * layout: one grouped broadcast, in place) */
+    if (replicated_stages(s)) COMM(comm_all_gather_strips(s->comm, c.p, c.g.nstrips, (size_t)c.g.ss));
     return IFL_OK;
 }
 static int stage_apply_pressure(ifl_solver* s, double timestep) {
@@ -1016,7 +1028,7 @@ static int field_io(ifl_solver* s, int32_t field, double* host, size_t count, lo
     int rc = field_ptr(s, field, &p, &n, &kind, &width);
     if (rc) return rc;
     const bool whole = nrows < 0;
-    if (whole && s->cfg.world_size > 1) {
+    if (whole && s->cfg.world_size > 1 && !replicated_stages(s)) {
         snprintf(g_err, sizeof g_err, "slab decomposition: a rank holds only its rows of field %d -- use ifl_%s_field_rows", field,
                  write ? "write" : "read");
         return IFL_ERR_UNSUPPORTED;
@@ -1025,7 +1037,7 @@ static int field_io(ifl_solver* s, int32_t field, double* host, size_t count, lo
     if (whole) { row0 = 0; nrows = (long long)total_rows; }
     if (row0 < 0 || nrows < 0 || (size_t)(row0 + nrows) > total_rows) INVALID("row range outside the field");
     if ((size_t)nrows * width != count) INVALID(whole ? "count does not match ifl_field_size" : "count does not match nrows * row length");
-    if (kind == KIND_SKEW && s->cfg.world_size > 1) {
+    if (kind == KIND_SKEW && s->cfg.world_size > 1 && !replicated_stages(s)) {
         const long long o0 = 32LL * s->sx.g.s0, o1 = 32LL * s->sx.g.s1 < s->h ? 32LL * s->sx.g.s1 : (long long)s->h;
         if (row0 < o0 || row0 + nrows > o1) INVALID("slab decomposition: a solver vector holds only the rows this rank owns (ifl_slab_rows)");
     }

@@ -68,3 +68,21 @@ def test_two_rank_rendezvous_gloo(tmp_path):
                          env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "rank0-ok" in out.stdout and "rank1-ok" in out.stdout
+
+
+@pytest.mark.parametrize("variant,accepted", [("F1_MATRIXLESS", False), ("F2_BETTER_ADVECTION", False), ("F3_CONJUGATE_GRADIENTS", True),
+                                              ("F4_SOLID_BOUNDARIES", True), ("F5_CURVED_BOUNDARIES", True), ("F6_HEAT", True),
+                                              ("F7_VARIABLE_DENSITY", True), ("F8_FLIP", False)])
+def test_which_variants_run_on_several_gpus(ifl, variant, accepted):
+    """ifl_create validates rank / world_size before it touches a device: the MIC(0)-PCG variants 3 (slab decomposition)
+    and 4-7 (slab-decomposed solver loops) are accepted -- and then fail loudly here for want of a GPU -- while the
+    Gauss-Seidel variants and FLIP are refused as unsupported."""
+    import torch
+    if accepted and torch.cuda.is_available():
+        pytest.skip("with a GPU present ifl_create would go on to an NCCL rendezvous; tools/slab_check.py covers that")
+    abi = ifl.abi
+    cfg = abi.default_config(getattr(abi, variant), 256, 256, rank=1, world_size=2)
+    lib, fn = ifl.load()
+    h = C.c_void_p()
+    rc = fn["ifl_create"](C.byref(cfg), C.byref(h))
+    assert rc == (abi.ERR_CUDA if accepted else abi.ERR_UNSUPPORTED), rc
