@@ -210,8 +210,11 @@ k_matvec(SkewGeom g, const double* __restrict__ adiag, const double* __restrict_
  * In the first iteration (iterations == 0) s already is the copy of z made by k_init_s (F3:596): s is carried over
  * unchanged and nothing is added to p.
  * Moves 48 B/cell for F3 (R z,s,p  W s,p,z), against 16 + 40 for separate mat-vec and update kernels. */
+/* resident blocks per SM the register allocation aims at.  F3 (matrix re-derived from the grid position): 5 (48 registers, a
+ * few spilled values) measured 4 % faster than 4 (64 registers), 6 is 35 % slower.  The array-reading instance (F4+):
+ * 4 (64 registers) measured 11 % faster than unconstrained (96 registers, 2 blocks) and 16 % faster than 5 */
 template <bool CONSTM>
-__global__ void __launch_bounds__(EW_THREADS)
+__global__ void __launch_bounds__(EW_THREADS, CONSTM ? 5 : 4)
 k_step_a(SkewGeom g, const double* __restrict__ adiag, const double* __restrict__ ax, const double* __restrict__ ay,
          double* z0, double* z1, double* s0, double* s1, double* __restrict__ p,
          double* partials, double* strip_part, unsigned* strip_ctr, SolveScalars* sc, int dot_mode,
