@@ -1,3 +1,5 @@
+# N=1 measurement recipe of profiles/r02_summary.md section A (run on a GPU box from the repo root): default bench line,
+# ncu launch list of one timed step, ncu --set full capture of the three PCG kernels (each only after the plain command exited 0).
 cd /root/repo
 mkdir -p gpurun_out
 ( time timeout 900 python bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err ) 2>&1 | grep real

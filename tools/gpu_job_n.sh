@@ -1,3 +1,4 @@
+# bash tools/gpu_job_n.sh N : slab check at 4096^2 and the default bench line on N GPUs (profiles/bench_c5_nN_r02.json, slab_check_nN_r02.log).
 cd /root/repo
 N=$1
 mkdir -p gpurun_out
