@@ -1163,7 +1163,7 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
                         ok = ok && !is_sentinel_hi(e[i][0]);
                     }
                     if (ok) break;
-                    if (spins > (1u << 22)) {                  /* dead producer: give up instead of hanging the GPU */
+                    if (spins > (1u << 25)) {                  /* dead producer: give up instead of hanging the GPU */
 #pragma unroll
                         for (int i = u0; i < u0 + IFL_SW_G; i++) if (is_sentinel_hi(e[i][0])) { e[i][0] = 0.0; e[i][1] = 0.0; }
                         break;
@@ -1237,7 +1237,7 @@ k_precon_sweep(SkewGeom g, const double* src_fixed, double* dst0, double* dst1, 
         if (in_base != nullptr) {
             for (int i = 25; i <= 31; i++) {
                 double v0, v1;
-                for (unsigned spins = 0; spins < (1u << 22); spins++) {
+                for (unsigned spins = 0; spins < (1u << 26); spins++) {
                     ld_volatile_v2(in_base + i * SKB, v0, v1);
                     if (!is_sentinel_hi(v0) && !is_sentinel_hi(v1)) break;
                 }
