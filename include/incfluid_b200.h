@@ -244,9 +244,9 @@ int ifl_field_size(const ifl_solver* s, int32_t field, size_t* count);
 /* Copy a field device -> host / host -> device.  `count` must equal ifl_field_size. */
 int ifl_read_field(ifl_solver* s, int32_t field, double* host, size_t count);
 int ifl_write_field(ifl_solver* s, int32_t field, const double* host, size_t count);
-/* Rows [row0, row0 + nrows) of a field (count = nrows * row length).  In a slab decomposition a rank holds -- and a
- * host reads and writes -- only the rows it owns, ifl_slab_rows(); the whole-field calls above return
- * IFL_ERR_UNSUPPORTED there. */
+/* Rows [row0, row0 + nrows) of a field (count = nrows * row length).  In the slab decomposition of variant 3 a rank holds
+ * -- and a host reads and writes -- only the rows it owns, ifl_slab_rows(); the whole-field calls above return
+ * IFL_ERR_UNSUPPORTED there.  (Variants 4-7 on several GPUs keep whole fields on every rank: both forms work.) */
 int ifl_read_field_rows(ifl_solver* s, int32_t field, int32_t row0, int32_t nrows, double* host, size_t count);
 int ifl_write_field_rows(ifl_solver* s, int32_t field, int32_t row0, int32_t nrows, const double* host, size_t count);
 /* The rows of `field` this rank owns: the rows of its 32-row strips (balanced contiguous ranges: nstrips / world strips

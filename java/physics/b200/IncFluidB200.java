@@ -49,6 +49,15 @@ public final class IncFluidB200 implements AutoCloseable {
     // int ifl_particle_count(s, int32*)                        -- ParticleQuantities._particleCount F8:1771
     private static final MethodHandle PARTICLE_COUNT = fn("ifl_particle_count", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle LAST_ERROR = fn("ifl_last_error", FunctionDescriptor.of(ADDRESS));
+    // several GPUs, one JVM per GPU (INTEGRATION.md section 3; the reference has no distributed path):
+    // int ifl_comm_unique_id(uint8_t out[128]); int ifl_slab_rows(s, int32 field, int32* row0, int32* nrows);
+    // int ifl_read_field_rows / ifl_write_field_rows(s, int32 field, int32 row0, int32 nrows, double*, size_t count)
+    private static final MethodHandle COMM_UNIQUE_ID = fn("ifl_comm_unique_id", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle SLAB_ROWS = fn("ifl_slab_rows", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle READ_FIELD_ROWS = fn("ifl_read_field_rows",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG));
+    private static final MethodHandle WRITE_FIELD_ROWS = fn("ifl_write_field_rows",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG));
 
     /** struct ifl_config (include/incfluid_b200.h) */
     static final StructLayout CONFIG = MemoryLayout.structLayout(
@@ -86,12 +95,23 @@ public final class IncFluidB200 implements AutoCloseable {
 
     /** FluidSolver(w, h, rhoAir, rhoSoot, diffusion, bodies) of F6-F8 (NaN = keep the default of ifl_default_config) */
     public IncFluidB200(int variant, int w, int h, double density, double densitySoot, double diffusion) {
+        this(variant, w, h, density, densitySoot, diffusion, 0, 0, 1, null);
+    }
+
+    /** One rank of a solver group on several GPUs (one JVM per GPU): F3 slab-decomposed, F4-F7 with slab-decomposed solver
+     *  loops.  commId = the 128 bytes rank 0 got from commUniqueId() and handed to the other JVMs. */
+    public IncFluidB200(int variant, int w, int h, double density, double densitySoot, double diffusion,
+                        int device, int rank, int worldSize, byte[] commId) {
         try {
             MemorySegment cfg = arena.allocate(CONFIG);
             check((int) DEFAULT_CONFIG.invokeExact(cfg, variant, w, h));
             cfg.set(JAVA_DOUBLE, offset("density"), density);
             if (!Double.isNaN(densitySoot)) cfg.set(JAVA_DOUBLE, offset("density_soot"), densitySoot);
             if (!Double.isNaN(diffusion)) cfg.set(JAVA_DOUBLE, offset("diffusion"), diffusion);
+            cfg.set(JAVA_INT, offset("device"), device);
+            cfg.set(JAVA_INT, offset("rank"), rank);
+            cfg.set(JAVA_INT, offset("world_size"), worldSize);
+            if (commId != null) MemorySegment.copy(commId, 0, cfg, JAVA_BYTE, offset("comm_id"), 128);
             tAmbient = cfg.get(JAVA_DOUBLE, offset("t_ambient"));
             MemorySegment out = arena.allocate(ADDRESS);
             check((int) CREATE.invokeExact(cfg, out));
@@ -161,6 +181,36 @@ public final class IncFluidB200 implements AutoCloseable {
         try (Arena a = Arena.ofConfined()) {
             MemorySegment buf = a.allocateFrom(JAVA_DOUBLE, src);
             check((int) WRITE_FIELD.invokeExact(handle, field, buf, (long) src.length));
+        } catch (Throwable e) { throw wrap(e); }
+    }
+    /** rank 0 of a solver group: the 128-byte id every rank passes to the constructor */
+    public static byte[] commUniqueId() {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment buf = a.allocate(128);
+            check((int) COMM_UNIQUE_ID.invokeExact(buf));
+            return buf.toArray(JAVA_BYTE);
+        } catch (Throwable e) { throw wrap(e); }
+    }
+    /** {row0, nrows} of `field` this rank owns (everything on a single GPU) */
+    public int[] slabRows(int field) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment r0 = a.allocate(JAVA_INT), nr = a.allocate(JAVA_INT);
+            check((int) SLAB_ROWS.invokeExact(handle, field, r0, nr));
+            return new int[] {r0.get(JAVA_INT, 0), nr.get(JAVA_INT, 0)};
+        } catch (Throwable e) { throw wrap(e); }
+    }
+    /** rows [row0, row0 + nrows) of a device field; dst.length = nrows * row length */
+    public void readFieldRows(int field, int row0, int nrows, double[] dst) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment buf = a.allocate(JAVA_DOUBLE, dst.length);
+            check((int) READ_FIELD_ROWS.invokeExact(handle, field, row0, nrows, buf, (long) dst.length));
+            MemorySegment.copy(buf, JAVA_DOUBLE, 0, dst, 0, dst.length);
+        } catch (Throwable e) { throw wrap(e); }
+    }
+    public void writeFieldRows(int field, int row0, int nrows, double[] src) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment buf = a.allocateFrom(JAVA_DOUBLE, src);
+            check((int) WRITE_FIELD_ROWS.invokeExact(handle, field, row0, nrows, buf, (long) src.length));
         } catch (Throwable e) { throw wrap(e); }
     }
     /** F8: ParticleQuantities._particleCount */
