@@ -2,8 +2,9 @@
 
 A thread-block cluster of the triangular sweeps covers 16 strips = 512 rows, the strip hand-over rings have 128 slots
 (256 columns) and the operand rings 5 stages of 16 columns, so only grids taller than 512 rows and wider than 256 columns
-exercise the global boundary rows between clusters (`feed.mode == 1`), the per-cell-predicated last strip of a cluster,
-the ticket order across clusters and the ring wrap.  Every BASELINE.json config is compared here at its own size:
+exercise the hand-over between clusters (the producer's stores into a row of global memory and the edge-mover warp that
+feeds the consumer's ring from it), the credit protocol of a wrapping ring, the ticket order across clusters and the
+ragged last strip.  Every BASELINE.json config is compared here at its own size:
 
   config                                   strict mode (serial dot products)        fast path (fixed-tree dot products)
   F3 2048x640, 16384x1024 (capped solves)  bit-exact p r d u v                      <= 1e-9 relative (north_star bar)
